@@ -1,0 +1,296 @@
+/*
+ * mrq.h — C-ABI of the Blackwell-native multi-raft quorum engine ("mrq").
+ *
+ * This is the drop-in boundary for the hot path of chzchzchz/raftsql: everything the
+ * reference reaches through github.com/coreos/etcd/raft's Node interface
+ * (reference raft.go:152-165 construct, :214 Propose, :224 Tick, :227 Ready, :235 Advance,
+ * :269 Step) — but for G independent raft groups at once, on one B200 (or one shard of G
+ * on each of N B200s).  One engine == this node's replica of every group, exactly as one
+ * reference process == this node's replica of one group (reference raft.go:62-78).
+ *
+ * Rules of the boundary (cgo / ctypes friendly):
+ *   - plain C: opaque handle, POD structs, pointers + sizes; no C++/torch types;
+ *   - every call returns 0 on success, <0 (MRQ_E_*) on error; mrq_last_error() gives text;
+ *     the library never aborts or exits (contrast the reference's log.Fatalf sites,
+ *     reference raft.go:102,107,114,126,251,256,263);
+ *   - the caller owns every host buffer it passes; the engine copies before returning
+ *     unless the call is documented as asynchronous-with-pinned-buffers;
+ *   - one engine is driven by ONE thread at a time (mirrors the single select-loop goroutine,
+ *     reference raft.go:221-245); distinct engines are independent;
+ *   - no callbacks from C into the host.
+ *
+ * Identifiers: replica ids are 1..R (reference raft.go:150 `raft.Peer{ID: uint64(i + 1)}`),
+ * 0 is etcd-raft's `None`.  All terms / indices are uint64 (raftpb).
+ */
+#ifndef MRQ_H
+#define MRQ_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRQ_ABI_VERSION 1u
+#define MRQ_MAX_REPLICAS 8u /* ids and the vote record are packed 4+2 bits per replica */
+
+/* ---- error codes ------------------------------------------------------------------- */
+#define MRQ_OK 0
+#define MRQ_E_INVAL (-1)   /* bad argument                                  */
+#define MRQ_E_CUDA (-2)    /* CUDA runtime error (text in mrq_last_error)   */
+#define MRQ_E_NOMEM (-3)   /* host or device allocation failed              */
+#define MRQ_E_STATE (-4)   /* call not valid in this state                  */
+#define MRQ_E_NCCL (-5)    /* NCCL not loadable / NCCL call failed          */
+#define MRQ_E_NODEVICE (-6)/* no usable CUDA device: there is NO CPU fallback */
+
+/* ---- roles (etcd-raft StateType order) -------------------------------------------------- */
+#define MRQ_ROLE_FOLLOWER 0u
+#define MRQ_ROLE_CANDIDATE 1u
+#define MRQ_ROLE_LEADER 2u
+
+/* ---- message types: etcd-raft raftpb.MessageType numbering of the v2.2/v2.3 era ------- */
+#define MRQ_MSG_NONE 0u          /* empty inbox slot (MsgHup is local-only upstream)       */
+#define MRQ_MSG_APP 3u           /* MsgApp, host-resolved: see mrq_inbox                   */
+#define MRQ_MSG_APP_RESP 4u      /* MsgAppResp                                              */
+#define MRQ_MSG_VOTE 5u          /* MsgVote                                                 */
+#define MRQ_MSG_VOTE_RESP 6u     /* MsgVoteResp                                             */
+#define MRQ_MSG_HEARTBEAT 8u     /* MsgHeartbeat                                            */
+#define MRQ_MSG_HEARTBEAT_RESP 9u/* MsgHeartbeatResp                                        */
+#define MRQ_MSG_TYPE_MASK 0x0Fu
+#define MRQ_MSG_REJECT 0x80u     /* raftpb.Message.Reject, OR-ed into the type byte        */
+
+/* ---- per-group output word (the engine's stand-in for Ready.Messages, raft.go:227-230) -- */
+#define MRQ_OUT_CAMPAIGN 0x01u      /* campaign(): send MsgVote{Index:lastIndex,LogTerm:lastTerm} to all peers */
+#define MRQ_OUT_BECAME_LEADER 0x02u /* becomeLeader(): an empty entry was appended at term_start               */
+#define MRQ_OUT_BCAST_APPEND 0x04u  /* bcastAppend(): new entries and/or a new commit index to replicate       */
+#define MRQ_OUT_BCAST_HEARTBEAT 0x08u /* MsgBeat fired: bcastHeartbeat()                                       */
+#define MRQ_OUT_STEPPED_DOWN 0x10u  /* leader/candidate -> follower this tick                                  */
+#define MRQ_OUT_PROP_DROPPED 0x20u  /* proposals dropped (candidate, or follower without a leader)             */
+#define MRQ_OUT_PROP_FORWARD 0x40u  /* proposals to be forwarded to `lead` (follower with a leader)            */
+#define MRQ_OUT_COMMIT_ADVANCED 0x80u /* committed[g] moved this tick                                          */
+#define MRQ_OUT_VOTE_REPLY_SHIFT 8u /* bits 8..23: 2 bits per sender slot r: 0 none, 1 MsgVoteResp grant, 2 reject */
+#define MRQ_OUT_ACK_REPLY_SHIFT 24u /* bits 24..31: 1 bit per sender slot r: reply MsgAppResp/MsgHeartbeatResp */
+
+/* ---- configuration ------------------------------------------------------------------- */
+typedef struct mrq_config {
+  uint32_t abi_version;    /* MRQ_ABI_VERSION                                                     */
+  uint32_t n_replicas;     /* R = len(peers), 1..MRQ_MAX_REPLICAS (reference raft.go:148)         */
+  uint64_t n_groups;       /* G: raft groups owned by THIS engine (the shard, not the job total)  */
+  uint64_t group_base;     /* global id of local group 0 (shard offset; keys the RNG / traces)    */
+  uint32_t election_tick;  /* raft.Config.ElectionTick, reference raft.go:154 (10); 1..2047       */
+  uint32_t heartbeat_tick; /* raft.Config.HeartbeatTick, reference raft.go:155 (1); 1..255        */
+  uint64_t seed;           /* keys the randomized election timeout draw                           */
+  uint32_t self_id;        /* raft.Config.ID, reference raft.go:153: 1..R for every group, or 0 = */
+                           /* rotate: self id of global group g is (g % R) + 1                    */
+  int32_t device;          /* CUDA device ordinal                                                 */
+  void *stream;            /* optional cudaStream_t to run on (NULL: the engine creates one)      */
+  uint32_t inbox_slots;    /* number of device inbox buffers to rotate through (>=1; default 2)   */
+  uint32_t flags;          /* reserved, 0                                                         */
+} mrq_config;
+
+/* Fill a config with the reference's defaults (ElectionTick 10, HeartbeatTick 1; raft.go:154-155). */
+void mrq_config_default(mrq_config *cfg);
+
+typedef struct mrq_engine mrq_engine;
+
+/* StartNode for G groups: every group a follower at term 0 with an empty log, like
+ * raft.StartNode on a fresh MemoryStorage (reference raft.go:161-165) minus the conf-change
+ * bootstrap entries (membership is the static peer list, reference raft.go:148-151). */
+int mrq_create(const mrq_config *cfg, mrq_engine **out);
+void mrq_destroy(mrq_engine *e);
+/* Text of the last error on this engine (or of the last failed mrq_create when e == NULL). */
+const char *mrq_last_error(const mrq_engine *e);
+
+/* ---- state import / export (HardState + volatile state, SoA host arrays) -------------- */
+/* All arrays have n_groups elements unless noted; a NULL pointer skips that column.
+ * match / votes are replica-major: element [r * n_groups + g].  */
+typedef struct mrq_state {
+  uint64_t *term;        /* HardState.Term                                                     */
+  uint64_t *vote;        /* HardState.Vote (0 = None)                                           */
+  uint64_t *committed;   /* HardState.Commit                                                    */
+  uint64_t *last_index;  /* raftLog.lastIndex()                                                 */
+  uint64_t *last_term;   /* raftLog.lastTerm()                                                  */
+  uint64_t *term_start;  /* index of the empty entry appended by becomeLeader (valid if leader; */
+                         /* UINT64_MAX otherwise: the commit gate can never pass)               */
+  uint64_t *match;       /* [R][G] Progress.Match (meaningful for leaders)                     */
+  uint8_t *role;         /* MRQ_ROLE_*                                                          */
+  uint8_t *lead;         /* raft.lead (0 = None)                                                */
+  uint8_t *self_id;      /* this node's id in the group (1..R)                                  */
+  uint8_t *votes;        /* [R][G] poll() record: 0 absent, 1 granted, 2 rejected               */
+  uint16_t *election_elapsed;
+  uint16_t *heartbeat_elapsed;
+  uint16_t *randomized_timeout; /* in [ElectionTick, 2*ElectionTick-1]                          */
+} mrq_state;
+
+int mrq_export_state(mrq_engine *e, mrq_state *out); /* blocking: device -> caller arrays      */
+int mrq_import_state(mrq_engine *e, const mrq_state *in); /* blocking: caller arrays -> device */
+/* Progress.Next is message-construction state; without rejections it is exactly
+ * max(term_start, match+1) (reset() sets Next = lastIndex+1 == term_start; maybeUpdate raises it
+ * to n+1).  Exported as a convenience for the host's sendAppend.  out is [R][G].              */
+int mrq_export_next(mrq_engine *e, uint64_t *next_out);
+uint64_t mrq_tick_count(const mrq_engine *e);
+int mrq_set_tick_count(mrq_engine *e, uint64_t t);
+
+/* ---- the inbox: what node.Step(m) receives (reference raft.go:268-270) ---------------- */
+/* Dense form: one slot per (sender replica r, group g) per tick, replica-major [r*G + g].
+ * Field meaning per type (raftpb.Message fields):
+ *   MSG_VOTE        term, index = candidate lastIndex, logterm = candidate lastTerm
+ *   MSG_VOTE_RESP   term, REJECT bit
+ *   MSG_APP_RESP    term, index = follower's acknowledged index, REJECT bit
+ *   MSG_HEARTBEAT   term, commit
+ *   MSG_HEARTBEAT_RESP term
+ *   MSG_APP         term; HOST-RESOLVED: the host keeps the log, ran maybeAppend, and reports the
+ *                   outcome: index/logterm = the log's (lastIndex,lastTerm) after the append,
+ *                   commit = min(m.Commit, lastnewi).  With REJECT the log did not match: only
+ *                   the term rule, electionElapsed=0 and lead=From apply.
+ * Slots are Step()ped in sender order r = 0..R-1, then proposals, then the tick — the
+ * canonical per-tick serialisation.                                           */
+typedef struct mrq_inbox {
+  const uint8_t *type;     /* [R][G] MRQ_MSG_* | MRQ_MSG_REJECT                                */
+  const uint64_t *term;    /* [R][G]                                                           */
+  const uint64_t *index;   /* [R][G]                                                           */
+  const uint64_t *logterm; /* [R][G]                                                           */
+  const uint64_t *commit;  /* [R][G]                                                           */
+  const uint32_t *prop_count; /* [G] entries proposed at this node this tick (raft.go:214); may be NULL */
+} mrq_inbox;
+
+/* Copy a dense inbox from host memory into inbox slot `slot` (async on the engine stream when the
+ * source is pinned; the engine otherwise stages through its own pinned buffer).  NULL columns are
+ * treated as all-zero.                                                                         */
+int mrq_post_inbox_dense(mrq_engine *e, uint32_t slot, const mrq_inbox *in);
+
+/* Sparse form: a list of messages, scattered into inbox slot `slot` on the device.  The slot is
+ * cleared first unless `accumulate` is non-zero.  If several messages hit the same (from, group)
+ * slot the last one in the list wins.                                                          */
+typedef struct mrq_msg {
+  uint64_t group; /* local group index 0..G-1 */
+  uint64_t term;
+  uint64_t index;
+  uint64_t logterm;
+  uint64_t commit;
+  uint8_t type; /* MRQ_MSG_* | MRQ_MSG_REJECT */
+  uint8_t from; /* sender id 1..R */
+  uint8_t pad[6];
+} mrq_msg;
+int mrq_post_inbox_delta(mrq_engine *e, uint32_t slot, const mrq_msg *msgs, size_t n, int accumulate);
+
+/* Packed dense form for the PCIe-bound host path: one 32-bit word per (sender, group) slot, decoded
+ * on the device against the receiver's own state (exact, with an escape to the wide form):
+ *   bits  0..3   type        bit 4 REJECT
+ *   bits  5..6   term code:  0 => term == receiver's current term, 1 => term+1, 2 => term+2,
+ *                            3 => escape: the full message is in the `wide` list instead
+ *   bits  7..31  payload (25 bits), by type:
+ *        MSG_APP_RESP      lag:  index  = last_index - lag   (escape if lag >= 2^25)
+ *        MSG_VOTE          bits 7..8 logterm code (0 => == receiver last_term, 1 => +1, 2 => -1... see DESIGN)
+ *        MSG_HEARTBEAT     commit = committed + payload
+ * Escaped / wide messages ride in `wide` (n_wide entries) and override their slot.            */
+typedef struct mrq_inbox_packed {
+  const uint32_t *word;       /* [R][G] */
+  const uint8_t *prop_count8; /* [G] proposals (0..255) or NULL */
+  const mrq_msg *wide;        /* escape list */
+  size_t n_wide;
+} mrq_inbox_packed;
+int mrq_post_inbox_packed(mrq_engine *e, uint32_t slot, const mrq_inbox_packed *in);
+
+/* Proposals only (node.Propose, reference raft.go:211-215): sparse (group, count) pairs added to
+ * inbox slot `slot`'s prop_count.                                                             */
+int mrq_propose(mrq_engine *e, uint32_t slot, const uint64_t *groups, const uint32_t *counts, size_t n);
+
+/* Zero inbox slot `slot` on the device (async). */
+int mrq_clear_inbox(mrq_engine *e, uint32_t slot);
+
+/* ---- the hot path ------------------------------------------------------------------- */
+/* One raft tick for every group: Step() every message of inbox slot `slot` in canonical order,
+ * apply proposals, then Tick() (election / heartbeat timers, campaign).  Asynchronous on the
+ * engine stream.  The fused sm_100a kernel covers SURVEY §8a rows a3–a16.  If a communicator is
+ * attached (mrq_comm_init), the tick also all-gathers committed[] across ranks.               */
+int mrq_tick(mrq_engine *e, uint32_t slot);
+/* n ticks with an empty inbox (timers only). */
+int mrq_tick_idle(mrq_engine *e, uint32_t n);
+
+/* The standalone quorum kernel (K3; SURVEY §8a rows a15–a16): for every leader group,
+ * mci = q-th largest of match[0..R-1][g]; committed = mci iff mci > committed && mci >= term_start.
+ * Reads 8R+16 bytes per group, writes 8 when the commit index moves.  Asynchronous.           */
+int mrq_quorum_commit(mrq_engine *e);
+
+/* Element-wise Progress.maybeUpdate on the device for a sparse list of acks (a14), without a tick:
+ * match[from-1][group] = max(match, index).                                                    */
+int mrq_match_update(mrq_engine *e, const uint64_t *groups, const uint8_t *from, const uint64_t *index, size_t n);
+
+/* ---- outputs: the Ready() drain (reference raft.go:227-235) -------------------------- */
+/* Blocking: waits for the stream, copies device -> caller.  NULL pointers are skipped.        */
+int mrq_sync_commits(mrq_engine *e, uint64_t *committed_out, uint8_t *role_out, uint64_t *term_out);
+/* Per-group output word of the last tick (MRQ_OUT_*). */
+int mrq_sync_out(mrq_engine *e, uint32_t *out_words);
+/* Compact commit drain for the host path: per-group advance of committed since the previous
+ * drain, saturated to 255 in a byte (255 => read the full value with mrq_sync_commits).       */
+int mrq_sync_commit_deltas(mrq_engine *e, uint8_t *delta_out);
+int mrq_synchronize(mrq_engine *e);
+
+/* ---- synthetic vote/append traces, generated on the device (include/mrq_trace.h) -------- */
+struct mrq_trace_params;
+int mrq_gen_trace(mrq_engine *e, uint32_t slot, const struct mrq_trace_params *p, uint64_t tick);
+/* Read an inbox slot back to host arrays (testing / oracle feeding). Non-const view required. */
+typedef struct mrq_inbox_out {
+  uint8_t *type;
+  uint64_t *term, *index, *logterm, *commit;
+  uint32_t *prop_count;
+} mrq_inbox_out;
+int mrq_read_inbox(mrq_engine *e, uint32_t slot, mrq_inbox_out *out);
+
+/* ---- counters --------------------------------------------------------------------- */
+typedef struct mrq_counters {
+  uint64_t ticks;
+  uint64_t kernel_launches;   /* kernels this library launched since create */
+  uint64_t campaigns;         /* a10 */
+  uint64_t elections_won;     /* a9  */
+  uint64_t step_downs;        /* a12 */
+  uint64_t commits_advanced;  /* a16: groups whose commit index moved */
+  uint64_t votes_granted;     /* a13 */
+  uint64_t errors;            /* invariant violations seen on device (e.g. commit > lastIndex) */
+} mrq_counters;
+int mrq_get_counters(mrq_engine *e, mrq_counters *out); /* blocking */
+
+/* ---- timing on the engine stream (CUDA events) --------------------------------------- */
+int mrq_timer_start(mrq_engine *e);
+int mrq_timer_stop(mrq_engine *e, float *elapsed_ms); /* blocking */
+
+/* ---- multi-GPU: groups shard across ranks; one all-gather of committed[] per tick -------- */
+#define MRQ_COMM_ID_BYTES 128
+/* NCCL is dlopen()ed on first use (libnccl.so.2); single-GPU use never needs it. */
+int mrq_comm_unique_id(uint8_t id_out[MRQ_COMM_ID_BYTES]);
+/* Attach this engine (rank `rank` of `world`) to a communicator.  Every rank must own the same
+ * n_groups.  After this, mrq_tick() ends with ncclAllGather(committed[G]) -> gathered[world*G]. */
+int mrq_comm_init(mrq_engine *e, const uint8_t id[MRQ_COMM_ID_BYTES], uint32_t rank, uint32_t world);
+/* mode 0: ncclAllGather of uint64 committed[] (default); mode 1: peer-store gather fused into the
+ * tick kernel over CUDA-IPC mapped peer buffers (requires mrq_ipc_attach).                      */
+int mrq_comm_set_mode(mrq_engine *e, uint32_t mode);
+int mrq_sync_gathered(mrq_engine *e, uint64_t *gathered_out); /* blocking; world*G elements     */
+/* CUDA-IPC plumbing for the fused peer-store gather: export this rank's gather buffer, then attach
+ * every rank's handle (handles is world * MRQ_IPC_HANDLE_BYTES, in rank order).                  */
+#define MRQ_IPC_HANDLE_BYTES 64
+int mrq_ipc_export(mrq_engine *e, uint8_t handle_out[MRQ_IPC_HANDLE_BYTES]);
+int mrq_ipc_attach(mrq_engine *e, const uint8_t *handles, uint32_t rank, uint32_t world);
+
+/* ---- raw device pointers (zero-copy integration with a host that already lives on the GPU;
+ * also lets tests / torch wrap the buffers).  `which` is an MRQ_PTR_* id.                    */
+#define MRQ_PTR_TERM 0
+#define MRQ_PTR_META 1
+#define MRQ_PTR_LAST_INDEX 2
+#define MRQ_PTR_LAST_TERM 3
+#define MRQ_PTR_COMMITTED 4
+#define MRQ_PTR_TERM_START 5
+#define MRQ_PTR_MATCH 6
+#define MRQ_PTR_OUT 7
+#define MRQ_PTR_GATHERED 8
+void *mrq_device_ptr(mrq_engine *e, int which);
+void *mrq_stream(mrq_engine *e);
+
+/* Library/version probe: returns MRQ_ABI_VERSION; *sm_arch gets 100 (built for sm_100a). */
+uint32_t mrq_version(uint32_t *sm_arch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRQ_H */
