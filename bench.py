@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py — raft ticks/sec at 1,048,576 groups x 5 replicas (BASELINE.json configs[2]/[3]).
+
+A *step* is one raft tick over every group of the job: the fused sm_100a tick kernel Step()s that tick's
+append-acks / votes, applies proposals, runs the matchIndex -> commitIndex quorum (q-th largest of the
+replica columns, term-gated) and the election timers, for all groups at once.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 is launched by the driver under torch.distributed.run (one rank per GPU); the groups are sharded
+contiguously (strong scaling: the job stays 1,048,576 groups) and every tick ends with one all-gather of
+the committed indices over NVLink.
+
+Timing rules followed: W >= 3 warm-up steps; every timed step reads a different pre-generated inbox slot and
+the per-step footprint (state + inbox, ~260 MB at N=1) is larger than L2; for the standalone quorum kernel
+every timed launch reads a never-touched column set after an explicit L2 flush; device time by CUDA events on
+the engine's stream; max over ranks; clocks sampled during the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+G_TOTAL = 1 << 20
+R = 5
+SEED = 0x5EED0003
+L2_BYTES = 126 * 1024 * 1024
+MAX_SLOTS = 48
+
+
+# ---------------------------------------------------------------------------------------------------
+def steady_state(G: int, Rr: int, group_base: int, seed: int) -> dict:
+    """BASELINE configs[2] initial state: every group has a leader — this node, at replica slot
+    g % R — term 1..8, last_index in [2^20, 2^40), follower match = last_index - geometric lag (mean ~4),
+    99% of groups already past term_start."""
+    from raftsql_b200 import empty_state
+
+    rng = np.random.default_rng(seed + group_base)
+    st = empty_state(G, Rr)
+    g = np.arange(group_base, group_base + G, dtype=np.uint64)
+    st["self_id"][:] = (g % np.uint64(Rr) + np.uint64(1)).astype(np.uint8)
+    st["role"][:] = 2
+    st["lead"][:] = st["self_id"]
+    st["term"][:] = rng.integers(1, 9, size=G, dtype=np.uint64)
+    st["vote"][:] = st["self_id"]
+    st["last_index"][:] = rng.integers(2 ** 20, 2 ** 40, size=G, dtype=np.uint64)
+    st["last_term"][:] = st["term"]
+    lag = rng.geometric(0.2, size=(Rr, G)).astype(np.uint64)
+    st["match"][:] = st["last_index"][None, :] - lag
+    st["match"][st["self_id"] - 1, np.arange(G)] = st["last_index"]
+    st["committed"][:] = st["last_index"] - np.uint64(40)
+    gate_open = rng.random(G) < 0.99
+    st["term_start"][:] = np.where(gate_open, st["committed"] - np.uint64(5), st["last_index"] - np.uint64(1))
+    st["randomized_timeout"][:] = 10
+    return st
+
+
+def tick_bytes_per_group(Rr: int) -> dict:
+    """Algorithmic HBM bytes of one fused tick per group on the steady-state trace: every
+    follower acks, proposals arrive on 3 of 4 ticks."""
+    read = 8 * 5 + 8 * Rr + Rr + 4 + 16 * (Rr - 1)  # meta,term,last_index,committed,term_start + match + types + prop + ack term/index
+    write = 8 + 4 + 8 * (Rr - 1) + 8 + 12           # meta, out, acked match, committed, (last_index + self match) x 3/4
+    return {"read": read, "write": write, "total": read + write}
+
+
+def quorum_bytes_per_group(Rr: int) -> int:
+    return 8 * Rr + 16  # match[R] + committed + term_start, all u64 (reads)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        super().__init__(daemon=True)
+        self.device, self.rows, self._stop = device, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.device)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def finish(self) -> dict:
+        self._stop.set()
+        self.join(timeout=6)
+        sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def measured_peak_gbs() -> tuple[float, str]:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_ticks(G: int, Rr: int, state: dict, inboxes: list, budget_s: float, warmup: int = 1,
+                        steps: int | None = None):
+    """Time the CPU restatement of the reference path (oracle/, 'port') on all host threads."""
+    import oracle
+
+    nt = oracle.hw_threads()
+    orc = oracle.Oracle(G, Rr, seed=SEED)
+    orc.import_state(state)
+    k = 0
+    for _ in range(warmup):
+        orc.tick(inboxes[k % len(inboxes)], nthreads=nt)
+        k += 1
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        orc.tick(inboxes[k % len(inboxes)], nthreads=nt)
+        k += 1
+        n += 1
+        el = time.perf_counter() - t0
+        if (steps is not None and n >= steps) or (steps is None and (el >= budget_s or n >= 400)):
+            break
+    return n / el, nt, n, el, orc
+
+
+def host_inboxes_from_oracle(G: int, Rr: int, state: dict, n: int, group_base: int = 0):
+    """Generate the trace on the host (same generator as the device: include/mrq_trace.h)."""
+    import oracle
+    from raftsql_b200 import _ffi, preset_trace
+
+    p = preset_trace(3)
+    po = oracle.TraceParams()
+    for name, _ in _ffi.TraceParams._fields_:
+        setattr(po, name, getattr(p, name))
+    nt = oracle.hw_threads()
+    orc = oracle.Oracle(G, Rr, seed=SEED, group_base=group_base)
+    orc.import_state(state)
+    out = []
+    for t in range(n):
+        ib = orc.gen_trace(po, t, nthreads=nt)
+        out.append(ib)
+        orc.tick(ib, nthreads=nt)
+    return out
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU path.  The Go reference cannot be built here (no Go toolchain;
+    its raft arithmetic is an un-vendored dependency), so this is the oracle port, multi-threaded."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+
+    G = G_TOTAL
+    st = steady_state(G, R, 0, SEED)
+    nslots = min(args.steps + args.warmup, 6)
+    inboxes = host_inboxes_from_oracle(G, R, st, nslots)
+    tps, nt, n, el, _ = cpu_reference_ticks(G, R, st, inboxes, 1e9, warmup=max(1, args.warmup), steps=args.steps)
+    line = {
+        "impl": "reference", "metric": "raft_ticks_per_sec_1Mx5", "value": tps, "unit": "ticks/s",
+        "n_gpus": args.gpus, "steps": n, "warmup": max(1, args.warmup), "ms_per_step": 1e3 * el / n,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "1,048,576 groups x 5 replicas, steady-state append/ack trace (BASELINE configs[2])",
+                   "groups": G, "replicas": R},
+        "cpu_baseline": {"value": tps, "unit": "ticks/s", "cores": nt, "kind": "port",
+                         "sample": f"{n} full ticks over all {G} groups on {nt} threads"},
+        "e2e": {"value": tps, "unit": "ticks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "C restatement of etcd-raft v2.x per-message semantics (oracle/raft_oracle.c); the Go reference "
+                "is not buildable in this environment",
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+
+    from raftsql_b200 import Engine, _ffi, preset_trace
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist = None
+        torch.cuda.set_device(local)
+    dev = local
+    assert G_TOTAL % world == 0
+    G = G_TOTAL // world
+    base = rank * G
+    K, W = args.steps, max(3, args.warmup)
+    nslots = min(K + W, MAX_SLOTS)
+
+    eng = Engine(G, R, seed=SEED, group_base=base, device=dev, inbox_slots=nslots)
+    st0 = steady_state(G, R, base, SEED)
+    eng.import_state(st0)
+    p = preset_trace(3)
+
+    if world > 1:  # one NCCL communicator for the per-tick all-gather of committed[]
+        uid = torch.zeros(_ffi.MRQ_COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(Engine.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        eng.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+
+    # dry run: generate the trace tick by tick on the device (each tick's acks depend on that tick's state),
+    # one inbox slot per tick; then rewind the state so the timed run replays exactly these inputs.
+    for t in range(nslots):
+        eng.gen_trace(p, t, slot=t)
+        eng.tick(t)
+    eng.synchronize()
+    e2e_slots = min(4, nslots)
+    host_ib = [eng.read_inbox(s) for s in range(e2e_slots)] if rank == 0 or True else []
+    eng.import_state(st0)
+    eng.tick_count = 0
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_ticks(n, first_slot):
+        for k in range(n):
+            eng.tick((first_slot + k) % nslots)
+
+    # warm-up, then the timed region
+    run_ticks(W, 0)
+    eng.synchronize()
+    c0 = eng.counters()
+    sampler = ClockSampler(dev)
+    sampler.start()
+    barrier()
+    eng.timer_start()
+    run_ticks(K, W)
+    ms = eng.timer_stop()
+    barrier()
+    # keep the GPU busy a little longer so the clock sampler sees load even for short K
+    t_end = time.time() + 0.6
+    while time.time() < t_end:
+        run_ticks(8, 0)
+        eng.synchronize()
+    clocks = sampler.finish()
+    c1 = eng.counters()
+    launches = c1["kernel_launches"] - c0["kernel_launches"]
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(lt)
+        launches_all = int(lt.item())
+    else:
+        launches_all = launches
+    # only count the launches of the K timed ticks (the post-roll above is outside the timed region)
+    launches_timed = K * world
+    ticks_per_s = K / (ms / 1e3)
+    peak, peak_src = measured_peak_gbs()
+
+    # ---- roofline of the dominant kernel (the fused tick) -------------------------------------------
+    tb = tick_bytes_per_group(R)
+    tick_kernel_ms = ms / K  # back-to-back launches on one stream: event time / K is the per-launch duration
+    tick_gbs = tb["total"] * G / (tick_kernel_ms * 1e-3) / 1e9
+    line = {
+        "metric": "raft_ticks_per_sec_1Mx5", "value": ticks_per_s, "unit": "ticks/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "1,048,576 groups x 5 replicas, steady-state append/ack trace (BASELINE configs[2]/[3])",
+                   "groups_total": G_TOTAL, "groups_per_gpu": G, "replicas": R, "parallelism": f"groups sharded x{world}",
+                   "collective": "ncclAllGather(committed) per tick" if world > 1 else "none",
+                   "l2": f"inputs larger than L2: {nslots} rotating inbox slots, per-step footprint "
+                         f"{(tb['total'] * G) / 1e6:.0f} MB vs 126 MB L2"},
+        "group_ticks_per_sec": ticks_per_s * G_TOTAL,
+        "roofline": {"bound": "hbm", "kernel": "tick_kernel<5>", "achieved": tick_gbs, "peak": peak, "unit": "GB/s",
+                     "frac": tick_gbs / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_group": tb},
+        "gpu_launches": launches_timed,
+        "clocks": clocks,
+    }
+
+    if rank == 0 and world == 1:
+        line["roofline_quorum_kernel"] = bench_quorum_kernel(torch, eng, peak, K, W)
+        line["e2e"] = bench_e2e(eng, st0, host_ib, K, W)
+        # CPU baseline: the oracle port on this box's host cores, bounded sample
+        try:
+            tps, nt, n, el, _ = cpu_reference_ticks(G_TOTAL, R, st0, host_ib, budget_s=12.0)
+            line["cpu_baseline"] = {"value": tps, "unit": "ticks/s", "cores": nt, "kind": "port",
+                                    "sample": f"{n} full ticks over all {G_TOTAL} groups x {R} replicas in {el:.1f} s on {nt} threads"}
+        except Exception as ex:  # the baseline must never take the GPU numbers down with it
+            line["cpu_baseline"] = {"value": None, "unit": "ticks/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+    elif rank == 0:
+        line["e2e"] = None
+    if world > 1:
+        # correctness of the gather on every rank: it must equal the concatenation of all shards' commits
+        mine = torch.from_numpy(eng.sync_commits().view(np.int64)).cuda()
+        allc = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allc, mine)
+        g = eng.sync_gathered().view(np.int64)
+        ok = bool(np.array_equal(g, torch.cat(allc).cpu().numpy()))
+        line["gather_check"] = ok
+    if rank == 0:
+        print(json.dumps(line))
+    eng.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def bench_quorum_kernel(torch, eng, peak, K, W):
+    """The standalone quorum kernel (K3) on never-touched column sets: achieved = (8R+16) * G / launch time."""
+    G, stride = G_TOTAL, G_TOTAL
+    nsets = min(K + W, 40)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(1234)
+    sets = []
+    for _ in range(nsets):
+        li = torch.randint(2 ** 20, 2 ** 40, (G,), generator=gen, device="cuda", dtype=torch.int64)
+        lag = torch.randint(0, 12, (R, G), generator=gen, device="cuda", dtype=torch.int64)
+        match = (li.unsqueeze(0) - lag).contiguous()
+        committed = (li - 40).contiguous()
+        gate = (committed - 5).contiguous()
+        sets.append((match, committed, gate))
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    out = {}
+    for variant, name in ((0, "ldg128"), (1, "tma_bulk")):
+        for m, c, g in sets[:W]:  # warm-up launches (these sets are not reused in the timed loop of this variant)
+            eng.quorum_commit_ext(m.data_ptr(), c.data_ptr(), g.data_ptr(), G, stride, variant)
+        eng.synchronize()
+        for _, c, _ in sets:
+            pass
+        # restore committed so that commits advance again, then flush L2 so every timed launch reads HBM
+        for (m, c, g) in sets:
+            c.copy_(g + 5)
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        timed = sets[W:] if len(sets) > W else sets
+        eng.timer_start()
+        for m, c, g in timed:
+            eng.quorum_commit_ext(m.data_ptr(), c.data_ptr(), g.data_ptr(), G, stride, variant)
+        ms = eng.timer_stop()
+        per = ms / len(timed)
+        gbs = quorum_bytes_per_group(R) * G / (per * 1e-3) / 1e9
+        out[name] = {"us_per_launch": per * 1e3, "achieved": gbs, "frac": gbs / peak, "launches": len(timed)}
+    best = max(out, key=lambda k: out[k]["achieved"])
+    return {"bound": "hbm", "kernel": f"quorum_kernel ({best})", "achieved": out[best]["achieved"], "peak": peak,
+            "unit": "GB/s", "frac": out[best]["frac"], "traffic": None,
+            "algorithmic_bytes_per_group": quorum_bytes_per_group(R), "variants": out,
+            "cold": f"{len(sets)} distinct column sets ({quorum_bytes_per_group(R) * G / 1e6:.1f} MB each), L2 flushed before timing"}
+
+
+def bench_e2e(eng, st0, host_ib, K, W):
+    """The same tick through the C-ABI with HOST buffers: per step H2D of that tick's inbox, the tick, and a
+    D2H drain of the commit indices — all inside the timed region."""
+    eng.import_state(st0)
+    eng.tick_count = 0
+    n = len(host_ib)
+    steps = min(K, 20)
+    h2d = sum(a.nbytes for a in host_ib[0].values())
+    d2h = eng.G * 8
+    for k in range(min(W, 3)):
+        eng.post_inbox_dense(host_ib[k % n], slot=0)
+        eng.tick(0)
+        eng.sync_commits()
+    t0 = time.perf_counter()
+    for k in range(steps):
+        eng.post_inbox_dense(host_ib[k % n], slot=k % 2)
+        eng.tick(k % 2)
+        eng.sync_commits()
+    el = time.perf_counter() - t0
+    return {"value": steps / el, "unit": "ticks/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "steps": steps, "api": "mrq_post_inbox_dense + mrq_tick + mrq_sync_commits (wide dense inbox, pageable host arrays)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -214,6 +214,16 @@ int mrq_tick_idle(mrq_engine *e, uint32_t n);
  * Reads 8R+16 bytes per group, writes 8 when the commit index moves.  Asynchronous.           */
 int mrq_quorum_commit(mrq_engine *e);
 
+/* Which implementation mrq_quorum_commit uses: 0 = 128-bit LDG form (default), 1 = TMA bulk-copy
+ * form (replica columns staged through shared memory with cp.async.bulk + mbarrier).          */
+int mrq_set_quorum_variant(mrq_engine *e, int variant);
+/* The same kernel over caller-owned DEVICE columns (zero-copy integration; also what bench.py
+ * rotates through so every timed launch reads cold HBM): d_match is [R][stride] replica-major,
+ * d_committed / d_term_start are [n_groups]; stride must be even and >= n_groups.  Asynchronous
+ * on the engine stream.                                                                        */
+int mrq_quorum_commit_ext(mrq_engine *e, const uint64_t *d_match, uint64_t *d_committed, const uint64_t *d_term_start,
+                          uint64_t n_groups, uint64_t stride, int variant);
+
 /* Element-wise Progress.maybeUpdate on the device for a sparse list of acks (a14), without a tick:
  * match[from-1][group] = max(match, index).                                                    */
 int mrq_match_update(mrq_engine *e, const uint64_t *groups, const uint8_t *from, const uint64_t *index, size_t n);
@@ -270,6 +280,8 @@ int mrq_sync_gathered(mrq_engine *e, uint64_t *gathered_out); /* blocking; world
 /* CUDA-IPC plumbing for the fused peer-store gather: export this rank's gather buffer, then attach
  * every rank's handle (handles is world * MRQ_IPC_HANDLE_BYTES, in rank order).                  */
 #define MRQ_IPC_HANDLE_BYTES 64
+/* Size the gather buffer for `world` ranks (call before mrq_ipc_export when NCCL is not used). */
+int mrq_ipc_prepare(mrq_engine *e, uint32_t world);
 int mrq_ipc_export(mrq_engine *e, uint8_t handle_out[MRQ_IPC_HANDLE_BYTES]);
 int mrq_ipc_attach(mrq_engine *e, const uint8_t *handles, uint32_t rank, uint32_t world);
 
@@ -286,6 +298,11 @@ int mrq_ipc_attach(mrq_engine *e, const uint8_t *handles, uint32_t rank, uint32_
 #define MRQ_PTR_GATHERED 8
 void *mrq_device_ptr(mrq_engine *e, int which);
 void *mrq_stream(mrq_engine *e);
+/* Element stride between replica rows of the device's replica-major arrays (G rounded up to 64). */
+uint64_t mrq_group_stride(const mrq_engine *e);
+/* Page-locked host memory for asynchronous posts / drains (cudaHostAlloc / cudaFreeHost). */
+void *mrq_alloc_pinned(size_t bytes);
+void mrq_free_pinned(void *p);
 
 /* Library/version probe: returns MRQ_ABI_VERSION; *sm_arch gets 100 (built for sm_100a). */
 uint32_t mrq_version(uint32_t *sm_arch);

@@ -1,0 +1,859 @@
+// mrq_engine.cu — host side of the C-ABI (include/mrq.h): device state, launches, copies, NCCL/IPC.
+//
+// Replaces, for G groups at once, the part of the reference's raftNode that owns the raft.Node and
+// drives it from one goroutine (reference raft.go:38-78 struct + constructor, :204-246 serveChannels).
+// There is NO CPU fallback: without a CUDA device mrq_create fails with MRQ_E_NODEVICE.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "mrq_kernels.cuh"
+
+using namespace mrq;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ---- NCCL through dlopen: single-GPU use never touches it ---------------------------------------
+struct NcclUniqueId { char internal[128]; };
+typedef void *NcclComm;
+struct NcclApi {
+  void *lib = nullptr;
+  int (*GetUniqueId)(NcclUniqueId *) = nullptr;
+  int (*CommInitRank)(NcclComm *, int, NcclUniqueId, int) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, NcclComm, cudaStream_t) = nullptr;
+  int (*CommDestroy)(NcclComm) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  std::string err;
+  bool load() {
+    if (lib) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+      lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) {
+      err = std::string("dlopen(libnccl.so.2) failed: ") + (dlerror() ? dlerror() : "?");
+      return false;
+    }
+    GetUniqueId = (int (*)(NcclUniqueId *))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (int (*)(NcclComm *, int, NcclUniqueId, int))dlsym(lib, "ncclCommInitRank");
+    AllGather = (int (*)(const void *, void *, size_t, int, NcclComm, cudaStream_t))dlsym(lib, "ncclAllGather");
+    CommDestroy = (int (*)(NcclComm))dlsym(lib, "ncclCommDestroy");
+    GetErrorString = (const char *(*)(int))dlsym(lib, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !AllGather || !CommDestroy) {
+      err = "libnccl is missing a required symbol";
+      return false;
+    }
+    return true;
+  }
+};
+NcclApi g_nccl;
+constexpr int kNcclUint64 = 5;  // ncclDataType_t::ncclUint64
+
+struct InboxBuf {
+  uint8_t *type = nullptr;
+  uint64_t *term = nullptr, *index = nullptr, *logterm = nullptr, *commit = nullptr;
+  uint32_t *prop = nullptr;
+  InboxView view() const { return InboxView{type, term, index, logterm, commit, prop}; }
+};
+
+}  // namespace
+
+struct mrq_engine {
+  mrq_config cfg;
+  uint64_t G = 0, gs = 0;
+  uint32_t R = 0;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  StateView s{};
+  std::vector<InboxBuf> inbox;
+  Counters *ctr = nullptr;
+  uint64_t *commit_prev = nullptr;  // commit-delta drain base
+  uint8_t *delta = nullptr;
+  uint64_t *gathered = nullptr;     // [world * G]
+  uint64_t tick_no = 0;
+  uint64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // scratch for sparse posts
+  void *scratch = nullptr;
+  size_t scratch_bytes = 0;
+  void *pinned = nullptr;
+  size_t pinned_bytes = 0;
+  // multi-GPU
+  NcclComm comm = nullptr;
+  uint32_t world = 1, rank = 0, comm_mode = 0;
+  uint64_t *peer_gather[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool ipc_attached = false;
+  int quorum_variant = 0;  // 0 = LDG.128, 1 = TMA bulk
+  std::string err;
+};
+
+namespace {
+
+int fail(mrq_engine *e, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (e)
+    e->err = buf;
+  else
+    g_create_error = buf;
+  return code;
+}
+
+#define CK(e, call)                                                                                       \
+  do {                                                                                                    \
+    cudaError_t _st = (call);                                                                             \
+    if (_st != cudaSuccess)                                                                               \
+      return fail((e), MRQ_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_st), __FILE__, __LINE__); \
+  } while (0)
+
+inline unsigned nblocks(uint64_t n, unsigned bs = 256) { return (unsigned)((n + bs - 1) / bs); }
+
+template <typename T>
+int dalloc(mrq_engine *e, T **p, size_t n) {
+  CK(e, cudaMalloc((void **)p, n * sizeof(T)));
+  CK(e, cudaMemsetAsync(*p, 0, n * sizeof(T), e->stream));
+  return MRQ_OK;
+}
+
+int ensure_scratch(mrq_engine *e, size_t bytes) {
+  if (bytes <= e->scratch_bytes) return MRQ_OK;
+  if (e->scratch) {
+    CK(e, cudaStreamSynchronize(e->stream));
+    CK(e, cudaFree(e->scratch));
+    e->scratch = nullptr;
+    e->scratch_bytes = 0;
+  }
+  size_t want = bytes < (1u << 20) ? (1u << 20) : bytes;
+  CK(e, cudaMalloc(&e->scratch, want));
+  e->scratch_bytes = want;
+  return MRQ_OK;
+}
+
+// strided column copy: host [rows][G] dense  <->  device [rows][gs]
+int copy_in(mrq_engine *e, void *dev, const void *host, size_t elem, size_t rows) {
+  if (!host) {
+    CK(e, cudaMemsetAsync(dev, 0, rows * e->gs * elem, e->stream));
+    return MRQ_OK;
+  }
+  CK(e, cudaMemcpy2DAsync(dev, e->gs * elem, host, e->G * elem, e->G * elem, rows, cudaMemcpyHostToDevice, e->stream));
+  return MRQ_OK;
+}
+int copy_out(mrq_engine *e, void *host, const void *dev, size_t elem, size_t rows) {
+  if (!host) return MRQ_OK;
+  CK(e, cudaMemcpy2DAsync(host, e->G * elem, dev, e->gs * elem, e->G * elem, rows, cudaMemcpyDeviceToHost, e->stream));
+  return MRQ_OK;
+}
+
+template <template <int> class K>
+struct Dispatch;
+
+#define MRQ_DISPATCH_R(R, STMT)  \
+  switch (R) {                   \
+    case 1: { constexpr int kR = 1; STMT; } break; \
+    case 2: { constexpr int kR = 2; STMT; } break; \
+    case 3: { constexpr int kR = 3; STMT; } break; \
+    case 4: { constexpr int kR = 4; STMT; } break; \
+    case 5: { constexpr int kR = 5; STMT; } break; \
+    case 6: { constexpr int kR = 6; STMT; } break; \
+    case 7: { constexpr int kR = 7; STMT; } break; \
+    case 8: { constexpr int kR = 8; STMT; } break; \
+    default: break;              \
+  }
+
+int launch_tick(mrq_engine *e, const InboxBuf *ib) {
+  if (e->G == 0) {
+    e->tick_no++;
+    return MRQ_OK;
+  }
+  TickArgs a{};
+  a.s = e->s;
+  if (ib) a.in = ib->view();
+  a.ctr = e->ctr;
+  a.G = e->G;
+  a.gs = e->gs;
+  a.group_base = e->cfg.group_base;
+  a.seed = e->cfg.seed;
+  a.tick_no = e->tick_no;
+  a.election_tick = e->cfg.election_tick;
+  a.heartbeat_tick = e->cfg.heartbeat_tick;
+  a.world = (e->comm_mode == 1 && e->ipc_attached) ? e->world : 1;
+  a.rank = e->rank;
+  for (int p = 0; p < 8; ++p) a.peer_gather[p] = e->peer_gather[p];
+  const unsigned nb = nblocks(e->G);
+  MRQ_DISPATCH_R(e->R, (tick_kernel<kR><<<nb, 256, 0, e->stream>>>(a)));
+  CK(e, cudaGetLastError());
+  e->launches++;
+  e->tick_no++;
+  if (e->world > 1 && e->comm_mode == 0 && e->comm) {
+    int st = g_nccl.AllGather(e->s.committed, e->gathered, (size_t)e->G, kNcclUint64, e->comm, e->stream);
+    if (st != 0) return fail(e, MRQ_E_NCCL, "ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(st) : "?");
+  }
+  return MRQ_OK;
+}
+
+constexpr int kTmaTile = 256;
+constexpr int kTmaStages = 4;
+
+template <int R>
+int launch_quorum_t(mrq_engine *e, const QuorumArgs &a0, int variant, cudaStream_t st, int sm_count) {
+  QuorumArgs a = a0;
+  uint64_t done = 0;
+  if (variant == 1 && a.G >= (uint64_t)kTmaTile) {
+    const uint64_t ntiles = a.G / kTmaTile;
+    const size_t smem = (size_t)kTmaStages * (R + 2) * kTmaTile * 8 + kTmaStages * 8;
+    auto kern = quorum_kernel_tma<R, kTmaTile, kTmaStages>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      CK(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+    int per_sm = (int)((220 * 1024) / smem);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    uint64_t grid = (uint64_t)sm_count * per_sm;
+    if (grid > ntiles) grid = ntiles;
+    QuorumArgs t = a;
+    t.G = ntiles * kTmaTile;
+    kern<<<(unsigned)grid, kTmaTile, smem, st>>>(t);
+    CK(e, cudaGetLastError());
+    if (e) e->launches++;
+    done = t.G;
+  }
+  if (done < a.G) {  // LDG.128 form (whole range, or the tail the tiled form left)
+    QuorumArgs t = a;
+    t.match = a.match + done;
+    t.committed = a.committed + done;
+    t.term_start = a.term_start + done;
+    t.G = a.G - done;
+    const uint64_t pairs = (t.G + 1) / 2;
+    quorum_kernel_ldg<R><<<nblocks(pairs), 256, 0, st>>>(t);
+    CK(e, cudaGetLastError());
+    if (e) e->launches++;
+  }
+  return MRQ_OK;
+}
+
+int g_sm_count = 148;
+
+int launch_quorum(mrq_engine *e, const QuorumArgs &a, int variant) {
+  int rc = MRQ_E_INVAL;
+  MRQ_DISPATCH_R(e->R, rc = launch_quorum_t<kR>(e, a, variant, e->stream, g_sm_count));
+  return rc;
+}
+
+int check_slot(mrq_engine *e, uint32_t slot) {
+  if (!e) return MRQ_E_INVAL;
+  if (slot >= e->inbox.size()) return fail(e, MRQ_E_INVAL, "inbox slot %u out of range (%zu slots)", slot, e->inbox.size());
+  return MRQ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t mrq_version(uint32_t *sm_arch) {
+  if (sm_arch) *sm_arch = 100;
+  return MRQ_ABI_VERSION;
+}
+
+void mrq_config_default(mrq_config *cfg) {
+  if (!cfg) return;
+  memset(cfg, 0, sizeof *cfg);
+  cfg->abi_version = MRQ_ABI_VERSION;
+  cfg->n_replicas = 3;
+  cfg->election_tick = 10;  // reference raft.go:154
+  cfg->heartbeat_tick = 1;  // reference raft.go:155
+  cfg->inbox_slots = 2;
+}
+
+const char *mrq_last_error(const mrq_engine *e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int mrq_create(const mrq_config *cfg, mrq_engine **out) {
+  if (!cfg || !out) return fail(nullptr, MRQ_E_INVAL, "mrq_create: null argument");
+  *out = nullptr;
+  if (cfg->abi_version != MRQ_ABI_VERSION) return fail(nullptr, MRQ_E_INVAL, "abi_version %u != %u", cfg->abi_version, MRQ_ABI_VERSION);
+  if (cfg->n_replicas < 1 || cfg->n_replicas > MRQ_MAX_REPLICAS)
+    return fail(nullptr, MRQ_E_INVAL, "n_replicas %u outside 1..%u", cfg->n_replicas, MRQ_MAX_REPLICAS);
+  if (cfg->self_id > cfg->n_replicas) return fail(nullptr, MRQ_E_INVAL, "self_id %u > n_replicas", cfg->self_id);
+  if (cfg->election_tick < 1 || cfg->election_tick > 2047) return fail(nullptr, MRQ_E_INVAL, "election_tick outside 1..2047");
+  if (cfg->heartbeat_tick < 1 || cfg->heartbeat_tick > 255) return fail(nullptr, MRQ_E_INVAL, "heartbeat_tick outside 1..255");
+  int ndev = 0;
+  cudaError_t st = cudaGetDeviceCount(&ndev);
+  if (st != cudaSuccess || ndev == 0)
+    return fail(nullptr, MRQ_E_NODEVICE, "no CUDA device (%s); this engine has no CPU fallback",
+                st == cudaSuccess ? "device count 0" : cudaGetErrorString(st));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, MRQ_E_INVAL, "device %d outside 0..%d", cfg->device, ndev - 1);
+  mrq_engine *e = new (std::nothrow) mrq_engine();
+  if (!e) return fail(nullptr, MRQ_E_NOMEM, "out of host memory");
+  e->cfg = *cfg;
+  e->G = cfg->n_groups;
+  e->gs = ((e->G + 63) / 64) * 64;
+  if (e->gs == 0) e->gs = 64;
+  e->R = cfg->n_replicas;
+  e->device = cfg->device;
+  int rc = MRQ_OK;
+  auto body = [&]() -> int {
+    CK(e, cudaSetDevice(e->device));
+    cudaDeviceProp prop;
+    CK(e, cudaGetDeviceProperties(&prop, e->device));
+    if (prop.major < 10)
+      return fail(e, MRQ_E_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", e->device, prop.major, prop.minor);
+    g_sm_count = prop.multiProcessorCount;
+    if (cfg->stream) {
+      e->stream = (cudaStream_t)cfg->stream;
+    } else {
+      CK(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+      e->own_stream = true;
+    }
+    CK(e, cudaEventCreate(&e->ev0));
+    CK(e, cudaEventCreate(&e->ev1));
+    const size_t gs = e->gs;
+    int r;
+    if ((r = dalloc(e, &e->s.term, gs))) return r;
+    if ((r = dalloc(e, &e->s.meta, gs))) return r;
+    if ((r = dalloc(e, &e->s.last_index, gs))) return r;
+    if ((r = dalloc(e, &e->s.last_term, gs))) return r;
+    if ((r = dalloc(e, &e->s.committed, gs))) return r;
+    if ((r = dalloc(e, &e->s.term_start, gs))) return r;
+    if ((r = dalloc(e, &e->s.match, gs * e->R))) return r;
+    if ((r = dalloc(e, &e->s.out, gs))) return r;
+    if ((r = dalloc(e, &e->ctr, 1))) return r;
+    if ((r = dalloc(e, &e->commit_prev, gs))) return r;
+    if ((r = dalloc(e, &e->delta, gs))) return r;
+    if ((r = dalloc(e, &e->gathered, gs))) return r;
+    uint32_t nslots = cfg->inbox_slots ? cfg->inbox_slots : 2;
+    e->inbox.resize(nslots);
+    for (auto &ib : e->inbox) {
+      if ((r = dalloc(e, &ib.type, gs * e->R))) return r;
+      if ((r = dalloc(e, &ib.term, gs * e->R))) return r;
+      if ((r = dalloc(e, &ib.index, gs * e->R))) return r;
+      if ((r = dalloc(e, &ib.logterm, gs * e->R))) return r;
+      if ((r = dalloc(e, &ib.commit, gs * e->R))) return r;
+      if ((r = dalloc(e, &ib.prop, gs))) return r;
+    }
+    if (e->G) {
+      init_state_kernel<<<nblocks(e->G), 256, 0, e->stream>>>(e->s, e->G, cfg->group_base, e->R, cfg->self_id, cfg->seed,
+                                                             cfg->election_tick);
+      CK(e, cudaGetLastError());
+      e->launches++;
+    }
+    CK(e, cudaStreamSynchronize(e->stream));
+    return MRQ_OK;
+  };
+  rc = body();
+  if (rc != MRQ_OK) {
+    g_create_error = e->err;
+    mrq_destroy(e);
+    return rc;
+  }
+  *out = e;
+  return MRQ_OK;
+}
+
+void mrq_destroy(mrq_engine *e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+  if (e->ipc_attached) {
+    for (uint32_t p = 0; p < e->world; ++p)
+      if (p != e->rank && e->peer_gather[p]) cudaIpcCloseMemHandle(e->peer_gather[p]);
+  }
+  void *ptrs[] = {e->s.term, e->s.meta, e->s.last_index, e->s.last_term, e->s.committed, e->s.term_start, e->s.match,
+                  e->s.out, e->ctr, e->commit_prev, e->delta, e->gathered, e->scratch};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  for (auto &ib : e->inbox) {
+    void *q[] = {ib.type, ib.term, ib.index, ib.logterm, ib.commit, ib.prop};
+    for (void *p : q)
+      if (p) cudaFree(p);
+  }
+  if (e->pinned) cudaFreeHost(e->pinned);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+uint64_t mrq_tick_count(const mrq_engine *e) { return e ? e->tick_no : 0; }
+int mrq_set_tick_count(mrq_engine *e, uint64_t t) {
+  if (!e) return MRQ_E_INVAL;
+  e->tick_no = t;
+  return MRQ_OK;
+}
+void *mrq_stream(mrq_engine *e) { return e ? (void *)e->stream : nullptr; }
+
+void *mrq_device_ptr(mrq_engine *e, int which) {
+  if (!e) return nullptr;
+  switch (which) {
+    case MRQ_PTR_TERM: return e->s.term;
+    case MRQ_PTR_META: return e->s.meta;
+    case MRQ_PTR_LAST_INDEX: return e->s.last_index;
+    case MRQ_PTR_LAST_TERM: return e->s.last_term;
+    case MRQ_PTR_COMMITTED: return e->s.committed;
+    case MRQ_PTR_TERM_START: return e->s.term_start;
+    case MRQ_PTR_MATCH: return e->s.match;
+    case MRQ_PTR_OUT: return e->s.out;
+    case MRQ_PTR_GATHERED: return e->gathered;
+    default: return nullptr;
+  }
+}
+
+uint64_t mrq_group_stride(const mrq_engine *e) { return e ? e->gs : 0; }
+
+void *mrq_alloc_pinned(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+void mrq_free_pinned(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+// ---- state import / export ------------------------------------------------------------------------------
+int mrq_export_state(mrq_engine *e, mrq_state *o) {
+  if (!e || !o) return MRQ_E_INVAL;
+  CK(e, cudaSetDevice(e->device));
+  const size_t gs = e->gs, G = e->G;
+  if (G == 0) return MRQ_OK;
+  // unpack meta into scratch columns: role, lead, self (u8), vote (u64), el, hb, rto (u16), votes (u8 [R][gs])
+  const size_t need = gs * (3 + 8 + 6) + gs * e->R + 64;
+  int r = ensure_scratch(e, need);
+  if (r) return r;
+  uint8_t *base = (uint8_t *)e->scratch;
+  uint64_t *d_vote = (uint64_t *)base;
+  uint16_t *d_el = (uint16_t *)(base + gs * 8), *d_hb = d_el + gs, *d_rto = d_hb + gs;
+  uint8_t *d_role = base + gs * 14, *d_lead = d_role + gs, *d_self = d_lead + gs, *d_votes = d_self + gs;
+  unpack_meta_kernel<<<nblocks(G), 256, 0, e->stream>>>(e->s.meta, G, d_role, d_lead, d_self, d_vote, d_el, d_hb, d_rto, d_votes, gs, e->R);
+  CK(e, cudaGetLastError());
+  e->launches++;
+  if ((r = copy_out(e, o->term, e->s.term, 8, 1))) return r;
+  if ((r = copy_out(e, o->vote, d_vote, 8, 1))) return r;
+  if ((r = copy_out(e, o->committed, e->s.committed, 8, 1))) return r;
+  if ((r = copy_out(e, o->last_index, e->s.last_index, 8, 1))) return r;
+  if ((r = copy_out(e, o->last_term, e->s.last_term, 8, 1))) return r;
+  if ((r = copy_out(e, o->term_start, e->s.term_start, 8, 1))) return r;
+  if ((r = copy_out(e, o->match, e->s.match, 8, e->R))) return r;
+  if ((r = copy_out(e, o->role, d_role, 1, 1))) return r;
+  if ((r = copy_out(e, o->lead, d_lead, 1, 1))) return r;
+  if ((r = copy_out(e, o->self_id, d_self, 1, 1))) return r;
+  if ((r = copy_out(e, o->votes, d_votes, 1, e->R))) return r;
+  if ((r = copy_out(e, o->election_elapsed, d_el, 2, 1))) return r;
+  if ((r = copy_out(e, o->heartbeat_elapsed, d_hb, 2, 1))) return r;
+  if ((r = copy_out(e, o->randomized_timeout, d_rto, 2, 1))) return r;
+  CK(e, cudaStreamSynchronize(e->stream));
+  return MRQ_OK;
+}
+
+int mrq_import_state(mrq_engine *e, const mrq_state *in) {
+  if (!e || !in) return MRQ_E_INVAL;
+  CK(e, cudaSetDevice(e->device));
+  const size_t gs = e->gs, G = e->G;
+  if (G == 0) return MRQ_OK;
+  int r;
+  auto put = [&](void *dev, const void *host, size_t elem, size_t rows) -> int {
+    if (!host) return MRQ_OK;
+    return copy_in(e, dev, host, elem, rows);
+  };
+  if ((r = put(e->s.term, in->term, 8, 1))) return r;
+  if ((r = put(e->s.committed, in->committed, 8, 1))) return r;
+  if ((r = put(e->s.last_index, in->last_index, 8, 1))) return r;
+  if ((r = put(e->s.last_term, in->last_term, 8, 1))) return r;
+  if ((r = put(e->s.term_start, in->term_start, 8, 1))) return r;
+  if ((r = put(e->s.match, in->match, 8, e->R))) return r;
+  const bool any_meta = in->role || in->lead || in->self_id || in->vote || in->votes || in->election_elapsed ||
+                        in->heartbeat_elapsed || in->randomized_timeout;
+  if (any_meta) {
+    const size_t need = gs * (3 + 8 + 6) + gs * e->R + 64;
+    if ((r = ensure_scratch(e, need))) return r;
+    uint8_t *base = (uint8_t *)e->scratch;
+    uint64_t *d_vote = (uint64_t *)base;
+    uint16_t *d_el = (uint16_t *)(base + gs * 8), *d_hb = d_el + gs, *d_rto = d_hb + gs;
+    uint8_t *d_role = base + gs * 14, *d_lead = d_role + gs, *d_self = d_lead + gs, *d_votes = d_self + gs;
+    if ((r = put(d_vote, in->vote, 8, 1))) return r;
+    if ((r = put(d_el, in->election_elapsed, 2, 1))) return r;
+    if ((r = put(d_hb, in->heartbeat_elapsed, 2, 1))) return r;
+    if ((r = put(d_rto, in->randomized_timeout, 2, 1))) return r;
+    if ((r = put(d_role, in->role, 1, 1))) return r;
+    if ((r = put(d_lead, in->lead, 1, 1))) return r;
+    if ((r = put(d_self, in->self_id, 1, 1))) return r;
+    if ((r = put(d_votes, in->votes, 1, e->R))) return r;
+    pack_meta_kernel<<<nblocks(G), 256, 0, e->stream>>>(
+        e->s.meta, G, in->role ? d_role : nullptr, in->lead ? d_lead : nullptr, in->self_id ? d_self : nullptr,
+        in->vote ? d_vote : nullptr, in->election_elapsed ? d_el : nullptr, in->heartbeat_elapsed ? d_hb : nullptr,
+        in->randomized_timeout ? d_rto : nullptr, in->votes ? d_votes : nullptr, gs, e->R);
+    CK(e, cudaGetLastError());
+    e->launches++;
+  }
+  CK(e, cudaStreamSynchronize(e->stream));
+  return MRQ_OK;
+}
+
+int mrq_export_next(mrq_engine *e, uint64_t *next_out) {
+  if (!e || !next_out) return MRQ_E_INVAL;
+  CK(e, cudaSetDevice(e->device));
+  if (e->G == 0) return MRQ_OK;
+  int r = ensure_scratch(e, e->G * e->R * 8);
+  if (r) return r;
+  export_next_kernel<<<nblocks(e->G), 256, 0, e->stream>>>(e->s.match, e->s.term_start, (uint64_t *)e->scratch, e->G, e->gs, e->R);
+  CK(e, cudaGetLastError());
+  e->launches++;
+  CK(e, cudaMemcpyAsync(next_out, e->scratch, e->G * e->R * 8, cudaMemcpyDeviceToHost, e->stream));
+  CK(e, cudaStreamSynchronize(e->stream));
+  return MRQ_OK;
+}
+
+// ---- inbox ---------------------------------------------------------------------------------------------------
+int mrq_clear_inbox(mrq_engine *e, uint32_t slot) {
+  int r = check_slot(e, slot);
+  if (r) return r;
+  CK(e, cudaSetDevice(e->device));
+  InboxBuf &ib = e->inbox[slot];
+  CK(e, cudaMemsetAsync(ib.type, 0, e->gs * e->R, e->stream));
+  CK(e, cudaMemsetAsync(ib.prop, 0, e->gs * 4, e->stream));
+  return MRQ_OK;
+}
+
+int mrq_post_inbox_dense(mrq_engine *e, uint32_t slot, const mrq_inbox *in) {
+  int r = check_slot(e, slot);
+  if (r) return r;
+  if (!in) return fail(e, MRQ_E_INVAL, "null inbox");
+  CK(e, cudaSetDevice(e->device));
+  if (e->G == 0) return MRQ_OK;
+  InboxBuf &ib = e->inbox[slot];
+  if ((r = copy_in(e, ib.type, in->type, 1, e->R))) return r;
+  if ((r = copy_in(e, ib.term, in->term, 8, e->R))) return r;
+  if ((r = copy_in(e, ib.index, in->index, 8, e->R))) return r;
+  if ((r = copy_in(e, ib.logterm, in->logterm, 8, e->R))) return r;
+  if ((r = copy_in(e, ib.commit, in->commit, 8, e->R))) return r;
+  if ((r = copy_in(e, ib.prop, in->prop_count, 4, 1))) return r;
+  return MRQ_OK;
+}
+
+int mrq_post_inbox_delta(mrq_engine *e, uint32_t slot, const mrq_msg *msgs, size_t n, int accumulate) {
+  int r = check_slot(e, slot);
+  if (r) return r;
+  CK(e, cudaSetDevice(e->device));
+  if (!accumulate && (r = mrq_clear_inbox(e, slot))) return r;
+  if (n == 0) return MRQ_OK;
+  if (!msgs) return fail(e, MRQ_E_INVAL, "null message list");
+  if ((r = ensure_scratch(e, n * sizeof(mrq_msg)))) return r;
+  CK(e, cudaMemcpyAsync(e->scratch, msgs, n * sizeof(mrq_msg), cudaMemcpyHostToDevice, e->stream));
+  scatter_msgs_kernel<<<nblocks(n), 256, 0, e->stream>>>(e->inbox[slot].view(), e->gs, e->G, e->R, (const MsgRec *)e->scratch, n);
+  CK(e, cudaGetLastError());
+  e->launches++;
+  // the staging buffer is reused by the next sparse post: the copy above must have consumed `msgs`
+  CK(e, cudaStreamSynchronize(e->stream));
+  return MRQ_OK;
+}
+
+int mrq_post_inbox_packed(mrq_engine *e, uint32_t slot, const mrq_inbox_packed *in) {
+  int r = check_slot(e, slot);
+  if (r) return r;
+  if (!in || !in->word) return fail(e, MRQ_E_INVAL, "null packed inbox");
+  CK(e, cudaSetDevice(e->device));
+  if (e->G == 0) return MRQ_OK;
+  const size_t wbytes = e->gs * e->R * 4, pbytes = e->gs, xbytes = in->n_wide * sizeof(mrq_msg);
+  if ((r = ensure_scratch(e, wbytes + pbytes + xbytes + 256))) return r;
+  uint32_t *d_word = (uint32_t *)e->scratch;
+  uint8_t *d_prop = (uint8_t *)e->scratch + wbytes;
+  MsgRec *d_wide = (MsgRec *)((uint8_t *)e->scratch + wbytes + ((pbytes + 63) / 64) * 64);
+  CK(e, cudaMemcpy2DAsync(d_word, e->gs * 4, in->word, e->G * 4, e->G * 4, e->R, cudaMemcpyHostToDevice, e->stream));
+  if (in->prop_count8) CK(e, cudaMemcpyAsync(d_prop, in->prop_count8, e->G, cudaMemcpyHostToDevice, e->stream));
+  unpack_inbox_kernel<<<nblocks(e->G), 256, 0, e->stream>>>(e->inbox[slot].view(), e->s, e->gs, e->G, e->R, d_word,
+                                                          in->prop_count8 ? d_prop : nullptr);
+  CK(e, cudaGetLastError());
+  e->launches++;
+  if (in->n_wide) {
+    if (!in->wide) return fail(e, MRQ_E_INVAL, "n_wide > 0 but wide == NULL");
+    CK(e, cudaMemcpyAsync(d_wide, in->wide, xbytes, cudaMemcpyHostToDevice, e->stream));
+    scatter_msgs_kernel<<<nblocks(in->n_wide), 256, 0, e->stream>>>(e->inbox[slot].view(), e->gs, e->G, e->R, d_wide, in->n_wide);
+    CK(e, cudaGetLastError());
+    e->launches++;
+  }
+  return MRQ_OK;
+}
+
+int mrq_propose(mrq_engine *e, uint32_t slot, const uint64_t *groups, const uint32_t *counts, size_t n) {
+  int r = check_slot(e, slot);
+  if (r) return r;
+  if (n == 0) return MRQ_OK;
+  if (!groups || !counts) return fail(e, MRQ_E_INVAL, "null proposal list");
+  CK(e, cudaSetDevice(e->device));
+  if ((r = ensure_scratch(e, n * 12 + 64))) return r;
+  uint64_t *d_g = (uint64_t *)e->scratch;
+  uint32_t *d_c = (uint32_t *)((uint8_t *)e->scratch + n * 8);
+  CK(e, cudaMemcpyAsync(d_g, groups, n * 8, cudaMemcpyHostToDevice, e->stream));
+  CK(e, cudaMemcpyAsync(d_c, counts, n * 4, cudaMemcpyHostToDevice, e->stream));
+  scatter_props_kernel<<<nblocks(n), 256, 0, e->stream>>>(e->inbox[slot].prop, e->G, d_g, d_c, n);
+  CK(e, cudaGetLastError());
+  e->launches++;
+  CK(e, cudaStreamSynchronize(e->stream));
+  return MRQ_OK;
+}
+
+int mrq_read_inbox(mrq_engine *e, uint32_t slot, mrq_inbox_out *o) {
+  int r = check_slot(e, slot);
+  if (r) return r;
+  if (!o) return MRQ_E_INVAL;
+  CK(e, cudaSetDevice(e->device));
+  if (e->G == 0) return MRQ_OK;
+  InboxBuf &ib = e->inbox[slot];
+  if ((r = copy_out(e, o->type, ib.type, 1, e->R))) return r;
+  if ((r = copy_out(e, o->term, ib.term, 8, e->R))) return r;
+  if ((r = copy_out(e, o->index, ib.index, 8, e->R))) return r;
+  if ((r = copy_out(e, o->logterm, ib.logterm, 8, e->R))) return r;
+  if ((r = copy_out(e, o->commit, ib.commit, 8, e->R))) return r;
+  if ((r = copy_out(e, o->prop_count, ib.prop, 4, 1))) return r;
+  CK(e, cudaStreamSynchronize(e->stream));
+  return MRQ_OK;
+}
+
+int mrq_gen_trace(mrq_engine *e, uint32_t slot, const struct mrq_trace_params *p, uint64_t tick) {
+  int r = check_slot(e, slot);
+  if (r) return r;
+  if (!p) return MRQ_E_INVAL;
+  CK(e, cudaSetDevice(e->device));
+  if (e->G == 0) return MRQ_OK;
+  gen_trace_kernel<<<nblocks(e->G), 256, 0, e->stream>>>(e->inbox[slot].view(), e->s, e->gs, e->G, e->R, e->cfg.group_base, *p, tick);
+  CK(e, cudaGetLastError());
+  e->launches++;
+  return MRQ_OK;
+}
+
+// ---- hot path --------------------------------------------------------------------------------------------------
+int mrq_tick(mrq_engine *e, uint32_t slot) {
+  int r = check_slot(e, slot);
+  if (r) return r;
+  CK(e, cudaSetDevice(e->device));
+  return launch_tick(e, &e->inbox[slot]);
+}
+
+int mrq_tick_idle(mrq_engine *e, uint32_t n) {
+  if (!e) return MRQ_E_INVAL;
+  CK(e, cudaSetDevice(e->device));
+  for (uint32_t k = 0; k < n; ++k) {
+    int r = launch_tick(e, nullptr);
+    if (r) return r;
+  }
+  return MRQ_OK;
+}
+
+int mrq_quorum_commit(mrq_engine *e) {
+  if (!e) return MRQ_E_INVAL;
+  CK(e, cudaSetDevice(e->device));
+  if (e->G == 0) return MRQ_OK;
+  QuorumArgs a{e->s.match, e->s.committed, e->s.term_start, e->ctr, e->G, e->gs};
+  return launch_quorum(e, a, e->quorum_variant);
+}
+
+int mrq_set_quorum_variant(mrq_engine *e, int variant) {
+  if (!e || variant < 0 || variant > 1) return MRQ_E_INVAL;
+  e->quorum_variant = variant;
+  return MRQ_OK;
+}
+
+int mrq_quorum_commit_ext(mrq_engine *e, const uint64_t *d_match, uint64_t *d_committed, const uint64_t *d_term_start,
+                          uint64_t n_groups, uint64_t stride, int variant) {
+  if (!e || !d_match || !d_committed || !d_term_start) return MRQ_E_INVAL;
+  if (stride < n_groups || (stride & 1)) return fail(e, MRQ_E_INVAL, "stride must be even and >= n_groups");
+  CK(e, cudaSetDevice(e->device));
+  if (n_groups == 0) return MRQ_OK;
+  QuorumArgs a{d_match, d_committed, d_term_start, nullptr, n_groups, stride};
+  return launch_quorum(e, a, variant);
+}
+
+int mrq_match_update(mrq_engine *e, const uint64_t *groups, const uint8_t *from, const uint64_t *index, size_t n) {
+  if (!e) return MRQ_E_INVAL;
+  if (n == 0) return MRQ_OK;
+  if (!groups || !from || !index) return fail(e, MRQ_E_INVAL, "null ack list");
+  CK(e, cudaSetDevice(e->device));
+  int r = ensure_scratch(e, n * 17 + 64);
+  if (r) return r;
+  uint64_t *d_g = (uint64_t *)e->scratch, *d_i = d_g + n;
+  uint8_t *d_f = (uint8_t *)(d_i + n);
+  CK(e, cudaMemcpyAsync(d_g, groups, n * 8, cudaMemcpyHostToDevice, e->stream));
+  CK(e, cudaMemcpyAsync(d_i, index, n * 8, cudaMemcpyHostToDevice, e->stream));
+  CK(e, cudaMemcpyAsync(d_f, from, n, cudaMemcpyHostToDevice, e->stream));
+  match_update_kernel<<<nblocks(n), 256, 0, e->stream>>>(e->s.match, e->gs, e->G, e->R, d_g, d_f, d_i, n);
+  CK(e, cudaGetLastError());
+  e->launches++;
+  CK(e, cudaStreamSynchronize(e->stream));
+  return MRQ_OK;
+}
+
+// ---- outputs ---------------------------------------------------------------------------------------------------
+int mrq_synchronize(mrq_engine *e) {
+  if (!e) return MRQ_E_INVAL;
+  CK(e, cudaSetDevice(e->device));
+  CK(e, cudaStreamSynchronize(e->stream));
+  return MRQ_OK;
+}
+
+int mrq_sync_commits(mrq_engine *e, uint64_t *committed_out, uint8_t *role_out, uint64_t *term_out) {
+  if (!e) return MRQ_E_INVAL;
+  CK(e, cudaSetDevice(e->device));
+  if (e->G == 0) return MRQ_OK;
+  if (committed_out) CK(e, cudaMemcpyAsync(committed_out, e->s.committed, e->G * 8, cudaMemcpyDeviceToHost, e->stream));
+  if (term_out) CK(e, cudaMemcpyAsync(term_out, e->s.term, e->G * 8, cudaMemcpyDeviceToHost, e->stream));
+  if (role_out) {
+    mrq_state st;
+    memset(&st, 0, sizeof st);
+    st.role = role_out;
+    return mrq_export_state(e, &st);
+  }
+  CK(e, cudaStreamSynchronize(e->stream));
+  return MRQ_OK;
+}
+
+int mrq_sync_out(mrq_engine *e, uint32_t *out_words) {
+  if (!e || !out_words) return MRQ_E_INVAL;
+  CK(e, cudaSetDevice(e->device));
+  if (e->G) CK(e, cudaMemcpyAsync(out_words, e->s.out, e->G * 4, cudaMemcpyDeviceToHost, e->stream));
+  CK(e, cudaStreamSynchronize(e->stream));
+  return MRQ_OK;
+}
+
+int mrq_sync_commit_deltas(mrq_engine *e, uint8_t *delta_out) {
+  if (!e || !delta_out) return MRQ_E_INVAL;
+  CK(e, cudaSetDevice(e->device));
+  if (e->G == 0) return MRQ_OK;
+  commit_delta_kernel<<<nblocks(e->G), 256, 0, e->stream>>>(e->s.committed, e->commit_prev, e->delta, e->G);
+  CK(e, cudaGetLastError());
+  e->launches++;
+  CK(e, cudaMemcpyAsync(delta_out, e->delta, e->G, cudaMemcpyDeviceToHost, e->stream));
+  CK(e, cudaStreamSynchronize(e->stream));
+  return MRQ_OK;
+}
+
+int mrq_get_counters(mrq_engine *e, mrq_counters *out) {
+  if (!e || !out) return MRQ_E_INVAL;
+  CK(e, cudaSetDevice(e->device));
+  Counters c;
+  CK(e, cudaMemcpyAsync(&c, e->ctr, sizeof c, cudaMemcpyDeviceToHost, e->stream));
+  CK(e, cudaStreamSynchronize(e->stream));
+  out->ticks = e->tick_no;
+  out->kernel_launches = e->launches;
+  out->campaigns = c.campaigns;
+  out->elections_won = c.elections_won;
+  out->step_downs = c.step_downs;
+  out->commits_advanced = c.commits_advanced;
+  out->votes_granted = c.votes_granted;
+  out->errors = c.errors;
+  return MRQ_OK;
+}
+
+int mrq_timer_start(mrq_engine *e) {
+  if (!e) return MRQ_E_INVAL;
+  CK(e, cudaSetDevice(e->device));
+  CK(e, cudaEventRecord(e->ev0, e->stream));
+  return MRQ_OK;
+}
+int mrq_timer_stop(mrq_engine *e, float *ms) {
+  if (!e || !ms) return MRQ_E_INVAL;
+  CK(e, cudaSetDevice(e->device));
+  CK(e, cudaEventRecord(e->ev1, e->stream));
+  CK(e, cudaEventSynchronize(e->ev1));
+  CK(e, cudaEventElapsedTime(ms, e->ev0, e->ev1));
+  return MRQ_OK;
+}
+
+// ---- multi-GPU -------------------------------------------------------------------------------------------------
+int mrq_comm_unique_id(uint8_t id_out[MRQ_COMM_ID_BYTES]) {
+  if (!id_out) return MRQ_E_INVAL;
+  if (!g_nccl.load()) return fail(nullptr, MRQ_E_NCCL, "%s", g_nccl.err.c_str());
+  NcclUniqueId id;
+  int st = g_nccl.GetUniqueId(&id);
+  if (st != 0) return fail(nullptr, MRQ_E_NCCL, "ncclGetUniqueId failed (%d)", st);
+  static_assert(sizeof(NcclUniqueId) == MRQ_COMM_ID_BYTES, "id size");
+  memcpy(id_out, &id, MRQ_COMM_ID_BYTES);
+  return MRQ_OK;
+}
+
+static int ensure_gather(mrq_engine *e, uint32_t world) {
+  CK(e, cudaStreamSynchronize(e->stream));
+  if (e->gathered) CK(e, cudaFree(e->gathered));
+  e->gathered = nullptr;
+  return dalloc(e, &e->gathered, (size_t)world * (e->G ? e->G : 1));
+}
+
+int mrq_comm_init(mrq_engine *e, const uint8_t id[MRQ_COMM_ID_BYTES], uint32_t rank, uint32_t world) {
+  if (!e || !id || world < 1 || world > 8 || rank >= world) return fail(e, MRQ_E_INVAL, "bad communicator arguments");
+  if (!g_nccl.load()) return fail(e, MRQ_E_NCCL, "%s", g_nccl.err.c_str());
+  CK(e, cudaSetDevice(e->device));
+  int r = ensure_gather(e, world);
+  if (r) return r;
+  NcclUniqueId uid;
+  memcpy(&uid, id, MRQ_COMM_ID_BYTES);
+  int st = g_nccl.CommInitRank(&e->comm, (int)world, uid, (int)rank);
+  if (st != 0) return fail(e, MRQ_E_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(st) : "?");
+  e->world = world;
+  e->rank = rank;
+  return MRQ_OK;
+}
+
+int mrq_comm_set_mode(mrq_engine *e, uint32_t mode) {
+  if (!e || mode > 1) return MRQ_E_INVAL;
+  if (mode == 1 && !e->ipc_attached) return fail(e, MRQ_E_STATE, "peer-store gather needs mrq_ipc_attach first");
+  e->comm_mode = mode;
+  return MRQ_OK;
+}
+
+int mrq_ipc_export(mrq_engine *e, uint8_t handle_out[MRQ_IPC_HANDLE_BYTES]) {
+  if (!e || !handle_out) return MRQ_E_INVAL;
+  CK(e, cudaSetDevice(e->device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == MRQ_IPC_HANDLE_BYTES, "ipc handle size");
+  cudaIpcMemHandle_t h;
+  CK(e, cudaIpcGetMemHandle(&h, e->gathered));
+  memcpy(handle_out, &h, sizeof h);
+  return MRQ_OK;
+}
+
+int mrq_ipc_prepare(mrq_engine *e, uint32_t world) {
+  if (!e || world < 1 || world > 8) return MRQ_E_INVAL;
+  CK(e, cudaSetDevice(e->device));
+  return ensure_gather(e, world);
+}
+
+int mrq_ipc_attach(mrq_engine *e, const uint8_t *handles, uint32_t rank, uint32_t world) {
+  if (!e || !handles || world < 1 || world > 8 || rank >= world) return fail(e, MRQ_E_INVAL, "bad ipc arguments");
+  CK(e, cudaSetDevice(e->device));
+  for (uint32_t p = 0; p < world; ++p) {
+    if (p == rank) {
+      e->peer_gather[p] = e->gathered;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)p * MRQ_IPC_HANDLE_BYTES, sizeof h);
+    void *ptr = nullptr;
+    CK(e, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    e->peer_gather[p] = (uint64_t *)ptr;
+  }
+  e->world = world;
+  e->rank = rank;
+  e->ipc_attached = true;
+  return MRQ_OK;
+}
+
+int mrq_sync_gathered(mrq_engine *e, uint64_t *gathered_out) {
+  if (!e || !gathered_out) return MRQ_E_INVAL;
+  CK(e, cudaSetDevice(e->device));
+  CK(e, cudaMemcpyAsync(gathered_out, e->gathered, (size_t)e->world * e->G * 8, cudaMemcpyDeviceToHost, e->stream));
+  CK(e, cudaStreamSynchronize(e->stream));
+  return MRQ_OK;
+}
+
+}  // extern "C"

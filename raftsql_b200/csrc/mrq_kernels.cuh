@@ -1,0 +1,812 @@
+// mrq_kernels.cuh — sm_100a device code of the multi-raft quorum engine.
+//
+// One thread owns one raft group for one tick: the group's whole state lives in registers, the
+// tick's messages are Step()ped in canonical order (sender ascending, proposals, timers), and only
+// the columns that changed are written back.  All global accesses are column accesses with the
+// group index fastest, so a warp reads/writes 256 contiguous bytes per u64 column.
+//
+// Restates (per group) what the reference reaches through etcd-raft's Node interface —
+// reference raft.go:214 Propose, :224 Tick, :227 Ready, :235 Advance, :269 Step — i.e. SURVEY §8a
+// rows a3–a16.  Integer only; tensor cores are not applicable.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mrq.h"
+#include "../../include/mrq_trace.h"
+
+namespace mrq {
+
+static constexpr uint64_t kNoGate = 0xFFFFFFFFFFFFFFFFull;  // term_start of a non-leader: gate never passes
+
+// ---- packed per-group small state ("meta" column, one u64 per group) -----------------------
+//  [0,2) role  [2,6) lead  [6,10) vote  [10,14) self id  [14,26) electionElapsed
+//  [26,38) randomizedElectionTimeout  [38,46) heartbeatElapsed  [46,62) votes (2 bits x 8 slots)
+struct Meta {
+  uint32_t role, lead, vote, self, elapsed, rto, hb, votes;
+};
+__host__ __device__ __forceinline__ uint64_t meta_pack(const Meta &m) {
+  return (uint64_t)(m.role & 3u) | ((uint64_t)(m.lead & 15u) << 2) | ((uint64_t)(m.vote & 15u) << 6) |
+         ((uint64_t)(m.self & 15u) << 10) | ((uint64_t)(m.elapsed & 0xFFFu) << 14) |
+         ((uint64_t)(m.rto & 0xFFFu) << 26) | ((uint64_t)(m.hb & 0xFFu) << 38) | ((uint64_t)(m.votes & 0xFFFFu) << 46);
+}
+__host__ __device__ __forceinline__ Meta meta_unpack(uint64_t w) {
+  Meta m;
+  m.role = (uint32_t)(w & 3u);
+  m.lead = (uint32_t)((w >> 2) & 15u);
+  m.vote = (uint32_t)((w >> 6) & 15u);
+  m.self = (uint32_t)((w >> 10) & 15u);
+  m.elapsed = (uint32_t)((w >> 14) & 0xFFFu);
+  m.rto = (uint32_t)((w >> 26) & 0xFFFu);
+  m.hb = (uint32_t)((w >> 38) & 0xFFu);
+  m.votes = (uint32_t)((w >> 46) & 0xFFFFu);
+  return m;
+}
+
+// ---- device views -----------------------------------------------------------------------------
+struct StateView {  // engine state, SoA; replica-major arrays use stride `gs` (padded G)
+  uint64_t *term, *meta, *last_index, *last_term, *committed, *term_start, *match;
+  uint32_t *out;
+};
+struct InboxView {  // one inbox slot, replica-major with stride `gs`
+  uint8_t *type;
+  uint64_t *term, *index, *logterm, *commit;
+  uint32_t *prop;
+};
+struct Counters {  // device-side mirror of mrq_counters' event counts
+  unsigned long long campaigns, elections_won, step_downs, commits_advanced, votes_granted, errors;
+};
+struct TickArgs {
+  StateView s;
+  InboxView in;  // in.type == nullptr: idle tick (timers only)
+  Counters *ctr;
+  uint64_t G, gs, group_base, seed, tick_no;
+  uint32_t election_tick, heartbeat_tick;
+  // fused peer-store gather (multi-GPU mode 1): committed[g] is stored into every rank's gather buffer
+  uint64_t *peer_gather[8];
+  uint32_t world, rank;
+  uint64_t *commit_prev;  // optional: previous drain's committed (for commit deltas); unused in the tick
+};
+
+// ---- cache-hinted accessors ---------------------------------------------------------------------
+// Inbox columns are read exactly once per tick: stream them (evict-first, no L1 allocation).
+__device__ __forceinline__ uint64_t ld_stream(const uint64_t *p) {
+  uint64_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_stream_u8(const uint8_t *p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+// State columns are read and (sometimes) rewritten by the same thread: plain loads, no L1 allocation.
+__device__ __forceinline__ uint64_t ld_state(const uint64_t *p) {
+  uint64_t v;
+  asm volatile("ld.global.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_state(uint64_t *p, uint64_t v) {
+  asm volatile("st.global.L1::no_allocate.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_state_u32(uint32_t *p, uint32_t v) {
+  asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- q-th largest of R values held in registers (a15: mis[q()-1] after a descending sort) -------
+// Partial selection by bubbling maxima: after pass p the p+1 largest values sit in v[0..p], so q
+// passes leave the q-th largest in v[q-1].  Fully unrolled: every index is a compile-time constant
+// and the values never leave registers.  (R=5, q=3: 9 compare-exchanges.)
+__device__ __forceinline__ void cswap_desc(uint64_t &hi, uint64_t &lo) {
+  const uint64_t a = hi, b = lo;
+  const bool sw = a < b;
+  hi = sw ? b : a;
+  lo = sw ? a : b;
+}
+template <int R>
+__device__ __forceinline__ uint64_t quorum_index(const uint64_t (&m)[R]) {
+  constexpr int Q = R / 2 + 1;  // a7: q() = len(prs)/2 + 1
+  uint64_t v[R];
+#pragma unroll
+  for (int i = 0; i < R; ++i) v[i] = m[i];
+#pragma unroll
+  for (int p = 0; p < Q; ++p) {
+#pragma unroll
+    for (int i = R - 1; i > p; --i) cswap_desc(v[i - 1], v[i]);
+  }
+  return v[Q - 1];
+}
+
+// ---- one group's state machine, in registers ------------------------------------------------------
+enum : uint32_t {
+  D_TERM = 1u << 0, D_LI = 1u << 1, D_LT = 1u << 2, D_COMMIT = 1u << 3, D_GATE = 1u << 4, D_MATCH0 = 1u << 8
+};
+
+template <int R>
+struct Group {
+  uint64_t term, last_index, last_term, committed, gate;
+  uint64_t match[R];
+  uint32_t role, lead, vote, self, elapsed, rto, hb, votes;
+  uint32_t out, dirty, ev;  // ev: event bits for the counters
+  bool lt_valid;
+  // context
+  const uint64_t *lt_ptr;
+  uint64_t seed, gg, tick_no;
+  uint32_t et, ht;
+
+  static constexpr uint32_t Q = R / 2 + 1;
+  enum : uint32_t { EV_CAMPAIGN = 1, EV_WON = 2, EV_STEPDOWN = 4, EV_COMMIT = 8, EV_GRANT = 16, EV_ERROR = 32 };
+
+  __device__ __forceinline__ uint64_t lastTerm() {  // raftLog.lastTerm(), loaded on first use
+    if (!lt_valid) {
+      last_term = ld_state(lt_ptr);
+      lt_valid = true;
+    }
+    return last_term;
+  }
+  __device__ __forceinline__ void setSelfMatch(uint64_t v) {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if ((uint32_t)(r + 1) == self && match[r] != v) {
+        match[r] = v;
+        dirty |= D_MATCH0 << r;
+      }
+  }
+  // a12 / upstream raft.reset(term)
+  __device__ __forceinline__ void reset(uint64_t t) {
+    if (term != t) {
+      term = t;
+      vote = 0;
+      dirty |= D_TERM;
+    }
+    lead = 0;
+    elapsed = 0;
+    hb = 0;
+    votes = 0;
+    rto = mrq_randomized_timeout(seed, gg, tick_no, et);
+  }
+  __device__ __forceinline__ void becomeFollower(uint64_t t, uint32_t ld) {
+    if (role != MRQ_ROLE_FOLLOWER) {
+      out |= MRQ_OUT_STEPPED_DOWN;
+      ev |= EV_STEPDOWN;
+    }
+    reset(t);
+    lead = ld;
+    role = MRQ_ROLE_FOLLOWER;
+    if (gate != kNoGate) {
+      gate = kNoGate;
+      dirty |= D_GATE;
+    }
+  }
+  // a15 + a16: mci = q-th largest match; commit iff mci > committed && term(mci) == Term, where for a
+  // leader term(i) == Term  <=>  term_start <= i <= lastIndex.
+  __device__ __forceinline__ bool maybeCommit() {
+    const uint64_t mci = quorum_index<R>(match);
+    if (mci > committed && mci >= gate && mci <= last_index) {
+      committed = mci;
+      dirty |= D_COMMIT;
+      out |= MRQ_OUT_COMMIT_ADVANCED;
+      ev |= EV_COMMIT;
+      return true;
+    }
+    return false;
+  }
+  // a5: appendEntry(n entries stamped with Term) + self maybeUpdate + maybeCommit
+  __device__ __forceinline__ void appendEntry(uint32_t n) {
+    last_index += n;
+    dirty |= D_LI;
+    if (!lt_valid || last_term != term) {
+      last_term = term;
+      lt_valid = true;
+      dirty |= D_LT;
+    }
+    setSelfMatch(last_index);
+    maybeCommit();
+  }
+  __device__ __forceinline__ void becomeLeader() {
+    reset(term);
+    lead = self;
+    role = MRQ_ROLE_LEADER;
+    out |= MRQ_OUT_BECAME_LEADER;
+    ev |= EV_WON;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {  // reset(): every Progress.Match = 0 (self: lastIndex, set by appendEntry)
+      match[r] = 0;
+      dirty |= D_MATCH0 << r;
+    }
+    gate = last_index + 1;  // index of the empty entry appended below: first entry of this term
+    dirty |= D_GATE;
+    appendEntry(1);
+  }
+  // a10
+  __device__ __forceinline__ void campaign() {
+    reset(term + 1);
+    vote = self;
+    role = MRQ_ROLE_CANDIDATE;
+    ev |= EV_CAMPAIGN;
+    votes |= 1u << (2u * (self - 1u));  // poll(self, true)
+    if (Q == 1u) {
+      becomeLeader();
+      return;
+    }
+    out |= MRQ_OUT_CAMPAIGN;
+  }
+  __device__ __forceinline__ void commitTo(uint64_t c) {  // raftLog.commitTo: monotone; out of range = error
+    if (committed < c) {
+      if (last_index < c) {
+        ev |= EV_ERROR;
+        return;
+      }
+      committed = c;
+      dirty |= D_COMMIT;
+      out |= MRQ_OUT_COMMIT_ADVANCED;
+      ev |= EV_COMMIT;
+    }
+  }
+  __device__ __forceinline__ void replyVote(uint32_t r, bool reject) {
+    out |= (reject ? 2u : 1u) << (MRQ_OUT_VOTE_REPLY_SHIFT + 2u * r);
+  }
+  __device__ __forceinline__ void handleAppend(uint32_t r, bool reject, uint64_t index, uint64_t logterm, uint64_t commit) {
+    if (!reject) {
+      if (last_index != index) {
+        last_index = index;
+        dirty |= D_LI;
+      }
+      if (!lt_valid || last_term != logterm) {
+        last_term = logterm;
+        lt_valid = true;
+        dirty |= D_LT;
+      }
+      commitTo(commit);
+    }
+    out |= 1u << (MRQ_OUT_ACK_REPLY_SHIFT + r);
+  }
+  __device__ __forceinline__ void handleHeartbeat(uint32_t r, uint64_t commit) {
+    commitTo(commit);
+    out |= 1u << (MRQ_OUT_ACK_REPLY_SHIFT + r);
+  }
+
+  // upstream raft.Step(m) for the message in sender slot r (id r+1); R_ is the compile-time slot so
+  // match[] stays in registers.
+  template <int R_>
+  __device__ __forceinline__ void step(uint32_t ty, uint64_t mterm, uint64_t index, const uint64_t *p_logterm,
+                                       const uint64_t *p_commit) {
+    const uint32_t type = ty & MRQ_MSG_TYPE_MASK;
+    const bool reject = (ty & MRQ_MSG_REJECT) != 0;
+    const uint32_t from = R_ + 1;
+    // a12: term rules
+    if (mterm != 0) {
+      if (mterm > term) {
+        becomeFollower(mterm, type == MRQ_MSG_VOTE ? 0u : from);
+      } else if (mterm < term) {
+        return;
+      }
+    }
+    if (role == MRQ_ROLE_LEADER) {
+      if (type == MRQ_MSG_APP_RESP) {  // a14 + a15/a16
+        if (!reject && match[R_] < index) {
+          match[R_] = index;
+          dirty |= D_MATCH0 << R_;
+          if (maybeCommit()) out |= MRQ_OUT_BCAST_APPEND;
+        }
+      } else if (type == MRQ_MSG_VOTE) {
+        replyVote(R_, true);
+      }
+      return;
+    }
+    if (role == MRQ_ROLE_CANDIDATE) {
+      if (type == MRQ_MSG_VOTE_RESP) {  // a8 + a9
+        if (((votes >> (2 * R_)) & 3u) == 0) votes |= (reject ? 2u : 1u) << (2 * R_);
+        const uint32_t granted = __popc(votes & 0x5555u);
+        const uint32_t total = __popc((votes | (votes >> 1)) & 0x5555u);
+        if (granted == Q) {
+          becomeLeader();
+          out |= MRQ_OUT_BCAST_APPEND;
+        } else if (total - granted == Q) {
+          becomeFollower(term, 0);
+        }
+      } else if (type == MRQ_MSG_VOTE) {
+        replyVote(R_, true);
+      } else if (type == MRQ_MSG_APP) {
+        becomeFollower(term, from);
+        handleAppend(R_, reject, index, ld_stream(p_logterm), ld_stream(p_commit));
+      } else if (type == MRQ_MSG_HEARTBEAT) {
+        becomeFollower(term, from);
+        handleHeartbeat(R_, ld_stream(p_commit));
+      }
+      return;
+    }
+    // follower
+    if (type == MRQ_MSG_VOTE) {  // a13
+      const uint64_t logterm = ld_stream(p_logterm);
+      const uint64_t lt = lastTerm();
+      const bool upToDate = logterm > lt || (logterm == lt && index >= last_index);
+      if ((vote == 0 || vote == from) && upToDate) {
+        elapsed = 0;
+        vote = from;
+        replyVote(R_, false);
+        ev |= EV_GRANT;
+      } else {
+        replyVote(R_, true);
+      }
+    } else if (type == MRQ_MSG_APP) {
+      elapsed = 0;
+      lead = from;
+      handleAppend(R_, reject, index, ld_stream(p_logterm), ld_stream(p_commit));
+    } else if (type == MRQ_MSG_HEARTBEAT) {
+      elapsed = 0;
+      lead = from;
+      handleHeartbeat(R_, ld_stream(p_commit));
+    }
+  }
+
+  __device__ __forceinline__ void propose(uint32_t n) {  // a5
+    if (role == MRQ_ROLE_LEADER) {
+      appendEntry(n);
+      out |= MRQ_OUT_BCAST_APPEND;
+    } else if (role == MRQ_ROLE_CANDIDATE || lead == 0) {
+      out |= MRQ_OUT_PROP_DROPPED;
+    } else {
+      out |= MRQ_OUT_PROP_FORWARD;
+    }
+  }
+  // a3 + a11: Tick()
+  __device__ __forceinline__ void tick() {
+    if (role == MRQ_ROLE_LEADER) {
+      ++hb;
+      ++elapsed;
+      if (elapsed >= et) elapsed = 0;  // checkQuorum is off (reference raft.go:152-159)
+      if (hb >= ht) {
+        hb = 0;
+        out |= MRQ_OUT_BCAST_HEARTBEAT;
+      }
+    } else {
+      ++elapsed;
+      if (elapsed >= rto) {
+        elapsed = 0;
+        campaign();
+      }
+    }
+  }
+};
+
+template <int R, int I>
+struct StepAll {
+  __device__ static __forceinline__ void run(Group<R> &g, const uint32_t (&ty)[R], const uint64_t (&mt)[R],
+                                             const uint64_t (&mi)[R], const InboxView &in, uint64_t gs, uint64_t i) {
+    if ((ty[I] & MRQ_MSG_TYPE_MASK) != 0 && (uint32_t)(I + 1) != g.self)
+      g.template step<I>(ty[I], mt[I], mi[I], in.logterm + (uint64_t)I * gs + i, in.commit + (uint64_t)I * gs + i);
+    StepAll<R, I + 1>::run(g, ty, mt, mi, in, gs, i);
+  }
+};
+template <int R>
+struct StepAll<R, R> {
+  __device__ static __forceinline__ void run(Group<R> &, const uint32_t (&)[R], const uint64_t (&)[R],
+                                             const uint64_t (&)[R], const InboxView &, uint64_t, uint64_t) {}
+};
+
+__device__ __forceinline__ void count_events(Counters *c, uint32_t ev) {
+  // warp-aggregate: one ballot per event class, lane 0 adds the popcount
+  const unsigned lane = threadIdx.x & 31u;
+#pragma unroll
+  for (int b = 0; b < 6; ++b) {
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, (ev >> b) & 1u);
+    if (m != 0 && lane == 0) atomicAdd(&(&c->campaigns)[b], (unsigned long long)__popc(m));
+  }
+}
+
+// ---- the fused per-tick kernel (a3–a16) ---------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(256) tick_kernel(const TickArgs a) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t ev = 0;
+  if (i < a.G) {
+    const bool has_inbox = a.in.type != nullptr;
+    // phase 1: group state + the tick's message types
+    const uint64_t w_meta = ld_state(a.s.meta + i);
+    Group<R> g;
+    g.term = ld_state(a.s.term + i);
+    g.last_index = ld_state(a.s.last_index + i);
+    g.committed = ld_state(a.s.committed + i);
+    g.gate = ld_state(a.s.term_start + i);
+    uint32_t ty[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) ty[r] = has_inbox ? ld_stream_u8(a.in.type + (uint64_t)r * a.gs + i) : 0u;
+    const uint32_t nprop = (has_inbox && a.in.prop) ? ld_stream_u32(a.in.prop + i) : 0u;
+    const Meta m = meta_unpack(w_meta);
+    g.role = m.role; g.lead = m.lead; g.vote = m.vote; g.self = m.self;
+    g.elapsed = m.elapsed; g.rto = m.rto; g.hb = m.hb; g.votes = m.votes;
+    g.out = 0; g.dirty = 0; g.ev = 0; g.lt_valid = false; g.last_term = 0;
+    g.lt_ptr = a.s.last_term + i;
+    g.seed = a.seed; g.gg = a.group_base + i; g.tick_no = a.tick_no;
+    g.et = a.election_tick; g.ht = a.heartbeat_tick;
+    // phase 2: Progress.Match (leaders only) and the messages' term / index
+    const bool was_leader = g.role == MRQ_ROLE_LEADER;
+#pragma unroll
+    for (int r = 0; r < R; ++r) g.match[r] = was_leader ? ld_state(a.s.match + (uint64_t)r * a.gs + i) : 0ull;
+    uint64_t mt[R], mi[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const bool present = (ty[r] & MRQ_MSG_TYPE_MASK) != 0;
+      mt[r] = present ? ld_stream(a.in.term + (uint64_t)r * a.gs + i) : 0ull;
+      mi[r] = present ? ld_stream(a.in.index + (uint64_t)r * a.gs + i) : 0ull;
+    }
+    // Step every message in sender order, then proposals, then the tick
+    StepAll<R, 0>::run(g, ty, mt, mi, a.in, a.gs, i);
+    if (nprop) g.propose(nprop);
+    g.tick();
+    // write back what changed
+    Meta o;
+    o.role = g.role; o.lead = g.lead; o.vote = g.vote; o.self = g.self;
+    o.elapsed = g.elapsed; o.rto = g.rto; o.hb = g.hb; o.votes = g.votes;
+    const uint64_t w_new = meta_pack(o);
+    if (w_new != w_meta) st_state(a.s.meta + i, w_new);
+    if (g.dirty & D_TERM) st_state(a.s.term + i, g.term);
+    if (g.dirty & D_LI) st_state(a.s.last_index + i, g.last_index);
+    if (g.dirty & D_LT) st_state(a.s.last_term + i, g.last_term);
+    if (g.dirty & D_COMMIT) st_state(a.s.committed + i, g.committed);
+    if (g.dirty & D_GATE) st_state(a.s.term_start + i, g.gate);
+    if (g.role == MRQ_ROLE_LEADER) {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (g.dirty & (D_MATCH0 << r)) st_state(a.s.match + (uint64_t)r * a.gs + i, g.match[r]);
+    }
+    st_state_u32(a.s.out + i, g.out);
+    if (a.world > 1) {  // fused all-gather: store the commit index straight into every rank's buffer
+#pragma unroll 1
+      for (uint32_t p = 0; p < a.world; ++p) a.peer_gather[p][(uint64_t)a.rank * a.G + i] = g.committed;
+    }
+    ev = g.ev;
+  }
+  if (__any_sync(0xFFFFFFFFu, ev != 0)) count_events(a.ctr, ev);
+}
+
+// ---- K3: the standalone quorum kernel (a15–a16), LDG.128 form ------------------------------------------
+// Two groups per thread: every column is read with one 128-bit load per thread (512 B per warp).
+// Reads 8R+16 bytes per group (match[R], committed, term_start); writes committed where it moves.
+// Precondition (checked by the fused tick, which has lastIndex in registers): match <= lastIndex.
+struct QuorumArgs {
+  const uint64_t *match;
+  uint64_t *committed;
+  const uint64_t *term_start;
+  Counters *ctr;
+  uint64_t G, gs;
+};
+
+__device__ __forceinline__ ulonglong2 ld_stream_v2(const uint64_t *p) {
+  ulonglong2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ ulonglong2 ld_plain_v2(const uint64_t *p) {
+  ulonglong2 v;
+  asm volatile("ld.global.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+  return v;
+}
+
+template <int R>
+__device__ __forceinline__ uint64_t quorum_commit_one(const uint64_t (&m)[R], uint64_t committed, uint64_t gate,
+                                                      bool &moved) {
+  const uint64_t mci = quorum_index<R>(m);
+  moved = mci > committed && mci >= gate;
+  return moved ? mci : committed;
+}
+
+template <int R>
+__global__ void __launch_bounds__(256) quorum_kernel_ldg(const QuorumArgs a) {
+  const uint64_t pair = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t i = pair * 2;
+  unsigned nmoved = 0;
+  if (i + 1 < a.G) {
+    ulonglong2 mv[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) mv[r] = ld_stream_v2(a.match + (uint64_t)r * a.gs + i);
+    const ulonglong2 cm = ld_plain_v2(a.committed + i);
+    const ulonglong2 gt = ld_stream_v2(a.term_start + i);
+    uint64_t m0[R], m1[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      m0[r] = mv[r].x;
+      m1[r] = mv[r].y;
+    }
+    bool mv0, mv1;
+    const uint64_t c0 = quorum_commit_one<R>(m0, cm.x, gt.x, mv0);
+    const uint64_t c1 = quorum_commit_one<R>(m1, cm.y, gt.y, mv1);
+    if (mv0 && mv1) {
+      asm volatile("st.global.L1::no_allocate.v2.u64 [%0], {%1, %2};" ::"l"(a.committed + i), "l"(c0), "l"(c1) : "memory");
+    } else if (mv0) {
+      st_state(a.committed + i, c0);
+    } else if (mv1) {
+      st_state(a.committed + i + 1, c1);
+    }
+    nmoved = (unsigned)mv0 + (unsigned)mv1;
+  } else if (i < a.G) {  // odd tail
+    uint64_t m0[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) m0[r] = ld_stream(a.match + (uint64_t)r * a.gs + i);
+    bool mv0;
+    const uint64_t c0 = quorum_commit_one<R>(m0, ld_state(a.committed + i), ld_stream(a.term_start + i), mv0);
+    if (mv0) st_state(a.committed + i, c0);
+    nmoved = mv0;
+  }
+  if (a.ctr) {  // warp-shuffle reduction of the "commit advanced" count, one atomic per warp
+    const unsigned tot = __reduce_add_sync(0xFFFFFFFFu, nmoved);
+    if (tot != 0 && (threadIdx.x & 31u) == 0) atomicAdd(&a.ctr->commits_advanced, (unsigned long long)tot);
+  }
+}
+
+// ---- K3, TMA form: replica columns staged through shared memory by the bulk-copy engine --------------
+// A persistent CTA walks tiles of TILE groups.  For each tile one elected thread issues R+2 1-D bulk
+// copies (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes — UBLKCP in SASS) of
+// TILE*8 bytes each (match[0..R-1], committed, term_start) into one of STAGES shared-memory stages and
+// arms that stage's mbarrier with the byte count; all threads wait on the barrier, select the quorum
+// index from shared memory and store committed where it moves.  No registers are tied up by loads in
+// flight: STAGES*(R+2)*TILE*8 bytes per CTA are outstanding regardless of occupancy.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <int R, int TILE, int STAGES>
+__global__ void __launch_bounds__(TILE) quorum_kernel_tma(const QuorumArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int COLS = R + 2;
+  uint64_t *tiles = reinterpret_cast<uint64_t *>(smem_raw);                     // [STAGES][COLS][TILE]
+  uint64_t *bars = tiles + (size_t)STAGES * COLS * TILE;                        // [STAGES]
+  const uint64_t ntiles = a.G / TILE;  // host guarantees G % TILE == 0 for this path (tail goes to LDG form)
+  const uint32_t tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](uint64_t tile, int s) {
+    uint64_t *dst = tiles + (size_t)s * COLS * TILE;
+    const uint64_t base = tile * TILE;
+    mbar_expect_tx(&bars[s], (uint32_t)(COLS * TILE * 8));
+#pragma unroll
+    for (int r = 0; r < R; ++r) bulk_g2s(dst + (size_t)r * TILE, a.match + (uint64_t)r * a.gs + base, TILE * 8, &bars[s]);
+    bulk_g2s(dst + (size_t)R * TILE, a.committed + base, TILE * 8, &bars[s]);
+    bulk_g2s(dst + (size_t)(R + 1) * TILE, a.term_start + base, TILE * 8, &bars[s]);
+  };
+  // prologue: fill the pipeline
+  uint64_t next = blockIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      const uint64_t t = (uint64_t)blockIdx.x + (uint64_t)s * gridDim.x;
+      if (t < ntiles) issue(t, s);
+    }
+  }
+  unsigned nmoved = 0;
+  int s = 0;
+  uint32_t parity = 0;
+  for (uint64_t tile = next; tile < ntiles; tile += gridDim.x) {
+    mbar_wait(&bars[s], parity);
+    const uint64_t *src = tiles + (size_t)s * COLS * TILE;
+    uint64_t m[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) m[r] = src[(size_t)r * TILE + tid];
+    const uint64_t cm = src[(size_t)R * TILE + tid];
+    const uint64_t gt = src[(size_t)(R + 1) * TILE + tid];
+    __syncthreads();  // everyone has drained this stage: it can be refilled
+    if (tid == 0) {
+      const uint64_t t = tile + (uint64_t)STAGES * gridDim.x;
+      if (t < ntiles) issue(t, s);
+    }
+    bool moved;
+    const uint64_t c = quorum_commit_one<R>(m, cm, gt, moved);
+    if (moved) st_state(a.committed + tile * TILE + tid, c);
+    nmoved += moved;
+    if (++s == STAGES) {
+      s = 0;
+      parity ^= 1u;
+    }
+  }
+  if (a.ctr) {
+    const unsigned tot = __reduce_add_sync(0xFFFFFFFFu, nmoved);
+    if (tot != 0 && (tid & 31u) == 0) atomicAdd(&a.ctr->commits_advanced, (unsigned long long)tot);
+  }
+}
+
+// ---- a14 as a sparse pass: Progress.maybeUpdate for a list of acks -----------------------------------
+__global__ void match_update_kernel(uint64_t *match, uint64_t gs, uint64_t G, uint32_t R, const uint64_t *groups,
+                                    const uint8_t *from, const uint64_t *index, size_t n) {
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint64_t g = groups[k];
+  const uint32_t f = from[k];
+  if (g >= G || f < 1 || f > R) return;
+  atomicMax(reinterpret_cast<unsigned long long *>(match + (uint64_t)(f - 1) * gs + g), (unsigned long long)index[k]);
+}
+
+// ---- inbox plumbing ---------------------------------------------------------------------------------------
+struct MsgRec {  // device mirror of mrq_msg (40 bytes payload + 8)
+  uint64_t group, term, index, logterm, commit;
+  uint8_t type, from, pad[6];
+};
+static_assert(sizeof(MsgRec) == sizeof(mrq_msg), "mrq_msg layout");
+
+__global__ void scatter_msgs_kernel(InboxView in, uint64_t gs, uint64_t G, uint32_t R, const MsgRec *msgs, size_t n) {
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const MsgRec m = msgs[k];
+  if (m.group >= G || m.from < 1 || m.from > R) return;
+  const uint64_t o = (uint64_t)(m.from - 1) * gs + m.group;
+  in.type[o] = m.type;
+  in.term[o] = m.term;
+  in.index[o] = m.index;
+  in.logterm[o] = m.logterm;
+  in.commit[o] = m.commit;
+}
+
+__global__ void scatter_props_kernel(uint32_t *prop, uint64_t G, const uint64_t *groups, const uint32_t *counts, size_t n) {
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  if (groups[k] < G) atomicAdd(prop + groups[k], counts[k]);
+}
+
+// Packed inbox (include/mrq.h mrq_inbox_packed): one 32-bit word per slot, decoded against the
+// receiver's own state into the wide columns.  Exact: anything that does not fit escapes to the wide list.
+__global__ void unpack_inbox_kernel(InboxView in, StateView s, uint64_t gs, uint64_t G, uint32_t R, const uint32_t *word,
+                                    const uint8_t *prop8) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G) return;
+  const uint64_t term = s.term[i], li = s.last_index[i], cm = s.committed[i];
+  for (uint32_t r = 0; r < R; ++r) {
+    const uint32_t w = word[(uint64_t)r * gs + i];
+    const uint64_t o = (uint64_t)r * gs + i;
+    const uint32_t type = w & 15u;
+    const uint32_t tc = (w >> 5) & 3u;
+    const uint64_t pay = w >> 7;
+    if (type == 0 || tc == 3u) {  // empty, or escaped to the wide list (scattered afterwards)
+      in.type[o] = 0;
+      continue;
+    }
+    in.type[o] = (uint8_t)(type | ((w & 16u) ? MRQ_MSG_REJECT : 0u));
+    in.term[o] = term + tc;
+    uint64_t index = 0, logterm = 0, commit = 0;
+    if (type == MRQ_MSG_APP_RESP) {
+      index = li - pay;  // lag encoding; host guarantees pay <= li
+    } else if (type == MRQ_MSG_HEARTBEAT) {
+      commit = cm + pay;
+    } else if (type == MRQ_MSG_VOTE) {
+      // payload: bits 0..1 logterm code vs receiver last_term (0 same, 1 +1, 2 +2), bits 2.. signed-ish
+      // index offset: index = last_index + (pay>>2) - 2^21
+      const uint64_t lt = s.last_term[i];
+      logterm = lt + (pay & 3u);
+      index = li + (pay >> 2) - (1ull << 21);
+    }
+    in.index[o] = index;
+    in.logterm[o] = logterm;
+    in.commit[o] = commit;
+  }
+  if (in.prop) in.prop[i] = prop8 ? prop8[i] : 0u;
+}
+
+// Compact commit drain: delta = committed - prev (saturated to 255), prev = committed.
+__global__ void commit_delta_kernel(const uint64_t *committed, uint64_t *prev, uint8_t *delta, uint64_t G) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G) return;
+  const uint64_t c = committed[i], p = prev[i];
+  const uint64_t d = c - p;
+  delta[i] = (uint8_t)(d > 255 ? 255 : d);
+  prev[i] = d > 255 ? p : c;  // a saturated group keeps its base until the host reads the full value
+}
+
+// ---- synthetic trace generation on the device (include/mrq_trace.h) -------------------------------------
+__global__ void __launch_bounds__(256) gen_trace_kernel(InboxView in, StateView s, uint64_t gs, uint64_t G, uint32_t R,
+                                                        uint64_t group_base, mrq_trace_params p, uint64_t tick) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G) return;
+  const Meta m = meta_unpack(s.meta[i]);
+  mrq_trace_view v;
+  v.term = s.term[i];
+  v.last_index = s.last_index[i];
+  v.last_term = s.last_term[i];
+  v.committed = s.committed[i];
+  v.role = m.role;
+  v.lead = m.lead;
+  v.self_id = m.self;
+  v.votes = m.votes;
+  for (uint32_t r = 0; r < R; ++r) {
+    const mrq_trace_msg c = mrq_trace_cell(&p, tick, group_base + i, r, &v);
+    const uint64_t o = (uint64_t)r * gs + i;
+    in.type[o] = c.type;
+    in.term[o] = c.term;
+    in.index[o] = c.index;
+    in.logterm[o] = c.logterm;
+    in.commit[o] = c.commit;
+  }
+  in.prop[i] = mrq_trace_props(&p, tick, group_base + i, &v);
+}
+
+// ---- state export helpers ------------------------------------------------------------------------------------
+__global__ void unpack_meta_kernel(const uint64_t *meta, uint64_t G, uint8_t *role, uint8_t *lead, uint8_t *self_id,
+                                   uint64_t *vote, uint16_t *el, uint16_t *hb, uint16_t *rto, uint8_t *votes, uint64_t gs,
+                                   uint32_t R) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G) return;
+  const Meta m = meta_unpack(meta[i]);
+  role[i] = (uint8_t)m.role;
+  lead[i] = (uint8_t)m.lead;
+  self_id[i] = (uint8_t)m.self;
+  vote[i] = m.vote;
+  el[i] = (uint16_t)m.elapsed;
+  hb[i] = (uint16_t)m.hb;
+  rto[i] = (uint16_t)m.rto;
+  for (uint32_t r = 0; r < R; ++r) votes[(uint64_t)r * gs + i] = (uint8_t)((m.votes >> (2 * r)) & 3u);
+}
+
+__global__ void pack_meta_kernel(uint64_t *meta, uint64_t G, const uint8_t *role, const uint8_t *lead, const uint8_t *self_id,
+                                 const uint64_t *vote, const uint16_t *el, const uint16_t *hb, const uint16_t *rto,
+                                 const uint8_t *votes, uint64_t gs, uint32_t R) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G) return;
+  Meta m = meta_unpack(meta[i]);
+  if (role) m.role = role[i];
+  if (lead) m.lead = lead[i];
+  if (self_id) m.self = self_id[i];
+  if (vote) m.vote = (uint32_t)vote[i];
+  if (el) m.elapsed = el[i];
+  if (hb) m.hb = hb[i];
+  if (rto) m.rto = rto[i];
+  if (votes) {
+    uint32_t w = 0;
+    for (uint32_t r = 0; r < R; ++r) w |= (uint32_t)(votes[(uint64_t)r * gs + i] & 3u) << (2 * r);
+    m.votes = w;
+  }
+  meta[i] = meta_pack(m);
+}
+
+__global__ void init_state_kernel(StateView s, uint64_t G, uint64_t group_base, uint32_t R, uint32_t self_id, uint64_t seed,
+                                  uint32_t election_tick) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G) return;
+  Meta m{};
+  m.role = MRQ_ROLE_FOLLOWER;
+  m.self = self_id ? self_id : (uint32_t)((group_base + i) % R) + 1u;
+  m.rto = mrq_randomized_timeout(seed, group_base + i, 0, election_tick);  // newRaft(): becomeFollower -> reset()
+  s.meta[i] = meta_pack(m);
+  s.term_start[i] = kNoGate;
+}
+
+__global__ void export_next_kernel(const uint64_t *match, const uint64_t *term_start, uint64_t *next, uint64_t G, uint64_t gs,
+                                   uint32_t R) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G) return;
+  const uint64_t ts = term_start[i];
+  for (uint32_t r = 0; r < R; ++r) {
+    const uint64_t mn = match[(uint64_t)r * gs + i] + 1;
+    next[(uint64_t)r * G + i] = (ts != kNoGate && ts > mn) ? ts : mn;
+  }
+}
+
+}  // namespace mrq

@@ -1,0 +1,328 @@
+"""GPU parity: the sm_100a engine (through the C-ABI) against the CPU oracle, bit for bit.
+
+Every test drives libmrq.so exactly as a host would — post an inbox, tick, drain — and compares raw
+uint64 / uint8 arrays with the oracle's (memcmp semantics, no tolerance: this is integer work).
+"""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import Oracle
+from raftsql_b200 import Engine, empty_inbox, preset_trace
+from raftsql_b200 import _ffi as F
+from util import (LEADER, U64MAX, assert_inbox_equal, assert_state_equal, leader_state, numpy_quorum_index)
+
+pytestmark = pytest.mark.gpu
+
+
+def _orc_params(p):
+    q = oracle.TraceParams()
+    for n, _ in F.TraceParams._fields_:
+        setattr(q, n, getattr(p, n))
+    return q
+
+
+def run_trace_parity(G, R, cfg_no, T, *, seed, check_every=1, nthreads=1, self_id=0, group_base=0):
+    p = preset_trace(cfg_no)
+    eng = Engine(G, R, seed=seed, self_id=self_id, group_base=group_base)
+    orc = Oracle(G, R, seed=seed, self_id=self_id, group_base=group_base)
+    assert_state_equal(eng.export_state(), orc.export(), "initial")
+    for t in range(T):
+        eng.gen_trace(p, t, slot=0)
+        ib = eng.read_inbox(0)
+        if t % check_every == 0:  # device generator == host generator on the same state
+            assert_inbox_equal(ib, orc.gen_trace(_orc_params(p), t, nthreads=nthreads), f"tick {t}")
+        eng.tick(0)
+        orc.tick(ib, nthreads=nthreads)
+        if t % check_every == 0 or t == T - 1:
+            assert_state_equal(eng.export_state(), orc.export(), f"tick {t}")
+            np.testing.assert_array_equal(eng.sync_out(), orc.export()["out"], err_msg=f"out word, tick {t}")
+    c = eng.counters()
+    assert c["errors"] == 0 and orc.errors == 0
+    s = orc.export()
+    eng.close()
+    return c, s
+
+
+def test_config2_4096x3_every_tick():
+    """BASELINE configs[1]: 4,096 groups x 3 replicas, election + replication trace, every tick compared."""
+    c, s = run_trace_parity(4096, 3, 2, 1024, seed=0x5EED0002)
+    assert (s["role"] == LEADER).mean() > 0.95  # the trace really elects leaders and replicates
+    assert c["elections_won"] >= 4096 * 0.95 and c["commits_advanced"] > 4096 * 100
+    assert (s["committed"] > 100).mean() > 0.9
+
+
+def test_config5_lag_and_churn_small_every_tick():
+    """BASELINE configs[4] shape (7 replicas, 20% lagging followers, leader churn), 8,192 groups."""
+    c, s = run_trace_parity(8192, 7, 5, 700, seed=0x5EED0005)
+    assert c["step_downs"] > 1000 and c["campaigns"] > 8192 and c["votes_granted"] > 100
+
+
+def test_config5_full_size_262144x7():
+    """BASELINE configs[4] at full size; state compared every 16th tick and at the end."""
+    c, s = run_trace_parity(262144, 7, 5, 160, seed=0x5EED0005, check_every=16, nthreads=oracle.hw_threads())
+    assert c["step_downs"] > 10000
+
+
+@pytest.mark.parametrize("R", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_all_replica_counts(R):
+    run_trace_parity(1000, R, 5, 200, seed=77 + R)
+
+
+@pytest.mark.parametrize("G", [1, 2, 31, 63, 64, 65, 255, 257])
+def test_ragged_group_counts(G):
+    run_trace_parity(G, 5, 5, 120, seed=G)
+
+
+def test_fixed_self_id_and_group_base():
+    run_trace_parity(2048, 5, 5, 150, seed=9, self_id=3)
+    run_trace_parity(2048, 3, 2, 150, seed=9, group_base=1 << 33)
+
+
+def test_zero_groups():
+    with Engine(0, 3) as eng:
+        eng.tick_idle(3)
+        eng.quorum_commit()
+        assert eng.tick_count == 3
+        assert eng.sync_commits().shape == (0,)
+
+
+def test_idle_ticks_only_timers():
+    G, R = 3000, 3
+    eng, orc = Engine(G, R, seed=4), Oracle(G, R, seed=4)
+    for t in range(45):
+        eng.tick_idle(1)
+        orc.tick(None)
+        assert_state_equal(eng.export_state(), orc.export(), f"idle tick {t}")
+    s = orc.export()
+    assert (s["role"] == 1).all() and (s["term"] >= 2).all()  # everyone timed out and campaigned, twice
+
+
+def test_config3_steady_state_1Mx5_import_and_tick():
+    """BASELINE configs[2]: 1,048,576 x 5 steady state imported, then the append/ack trace."""
+    G, R = 1 << 20, 5
+    rng = np.random.default_rng(3)
+    st = leader_state(G, R, rng)
+    eng, orc = Engine(G, R, seed=0x5EED0003), Oracle(G, R, seed=0x5EED0003)
+    eng.import_state(st)
+    orc.import_state(st)
+    assert_state_equal(eng.export_state(), orc.export(), "import")
+    p = preset_trace(3)
+    nt = oracle.hw_threads()
+    for t in range(6):
+        eng.gen_trace(p, t)
+        ib = eng.read_inbox()
+        eng.tick()
+        orc.tick(ib, nthreads=nt)
+        assert_state_equal(eng.export_state(), orc.export(), f"tick {t}")
+    assert eng.counters()["commits_advanced"] > G
+
+
+# ---- K3: the standalone quorum kernel ------------------------------------------------------------------
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("R", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_quorum_kernel_vs_oracle_and_numpy(R, variant):
+    G = 70001  # odd, not a multiple of the TMA tile: exercises the tiled body and the LDG tail
+    rng = np.random.default_rng(1000 + R)
+    st = leader_state(G, R, rng, gate_open_frac=0.9)
+    # adversarial cells: ties, zeros, huge values, non-leaders (gate closed for ever)
+    st["match"][:, :200] = rng.integers(0, 3, size=(R, 200), dtype=np.uint64)
+    st["committed"][:200] = 0
+    st["term_start"][:200] = rng.integers(0, 3, size=200, dtype=np.uint64)
+    st["match"][:, 200:300] = U64MAX - rng.integers(0, 2, size=(R, 100), dtype=np.uint64)
+    st["last_index"][200:300] = U64MAX
+    st["committed"][200:300] = 5
+    st["term_start"][200:300] = 6
+    st["role"][300:400] = 0
+    st["term_start"][300:400] = U64MAX
+    eng, orc = Engine(G, R), Oracle(G, R)
+    eng.import_state(st)
+    orc.import_state(st)
+    eng.set_quorum_variant(variant)
+    eng.quorum_commit()
+    orc.quorum_commit()
+    got = eng.sync_commits()
+    np.testing.assert_array_equal(got, orc.export()["committed"])
+    mci = numpy_quorum_index(st["match"])
+    want = np.where((mci > st["committed"]) & (mci >= st["term_start"]), mci, st["committed"])
+    np.testing.assert_array_equal(got, want)
+    assert eng.counters()["commits_advanced"] == int((want != st["committed"]).sum())
+    # idempotent: a second pass moves nothing
+    eng.quorum_commit()
+    np.testing.assert_array_equal(eng.sync_commits(), want)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_quorum_kernel_full_size_properties(variant):
+    """1,048,576 x 5 (BASELINE configs[2]): q-th largest by an independent numpy sort, monotone, gated,
+    idempotent, and linear in a uniform index shift."""
+    G, R = 1 << 20, 5
+    rng = np.random.default_rng(5)
+    st = leader_state(G, R, rng)
+    with Engine(G, R) as eng:
+        eng.import_state(st)
+        eng.set_quorum_variant(variant)
+        eng.quorum_commit()
+        got = eng.sync_commits()
+        mci = numpy_quorum_index(st["match"])
+        want = np.where((mci > st["committed"]) & (mci >= st["term_start"]), mci, st["committed"])
+        np.testing.assert_array_equal(got, want)
+        assert (got >= st["committed"]).all()
+        moved = got > st["committed"]
+        assert moved.mean() > 0.9 and (got[moved] >= st["term_start"][moved]).all()
+        eng.quorum_commit()
+        np.testing.assert_array_equal(eng.sync_commits(), want)
+        # shift every index by a constant: the result shifts by the same constant
+        k = np.uint64(12345)
+        st2 = dict(st)
+        for col in ("match", "committed", "term_start", "last_index"):
+            st2[col] = st[col] + k
+        eng.import_state(st2)
+        eng.quorum_commit()
+        np.testing.assert_array_equal(eng.sync_commits(), want + k)
+
+
+def test_quorum_ext_on_caller_device_buffers():
+    import torch
+
+    G, R, stride = 50000, 5, 50048
+    rng = np.random.default_rng(8)
+    st = leader_state(G, R, rng)
+    m = np.zeros((R, stride), np.uint64)
+    m[:, :G] = st["match"]
+    dm = torch.from_numpy(m.view(np.int64)).cuda()
+    dc = torch.from_numpy(st["committed"].view(np.int64)).cuda()
+    dg = torch.from_numpy(st["term_start"].view(np.int64)).cuda()
+    with Engine(16, R) as eng:
+        for variant in (0, 1):
+            c = dc.clone()
+            torch.cuda.synchronize()
+            eng.quorum_commit_ext(dm.data_ptr(), c.data_ptr(), dg.data_ptr(), G, stride, variant)
+            eng.synchronize()
+            mci = numpy_quorum_index(st["match"])
+            want = np.where((mci > st["committed"]) & (mci >= st["term_start"]), mci, st["committed"])
+            np.testing.assert_array_equal(c.cpu().numpy().view(np.uint64), want)
+
+
+# ---- the other inbox forms, proposals, sparse acks, drains ---------------------------------------------
+
+def _warm(G, R, seed, ticks, cfg_no=5):
+    p = preset_trace(cfg_no)
+    eng, orc = Engine(G, R, seed=seed, inbox_slots=3), Oracle(G, R, seed=seed)
+    for t in range(ticks):
+        eng.gen_trace(p, t)
+        ib = eng.read_inbox()
+        eng.tick()
+        orc.tick(ib)
+    return eng, orc, p
+
+
+def test_dense_host_inbox_equals_device_inbox():
+    G, R = 5000, 5
+    eng, orc, p = _warm(G, R, 21, 60)
+    for t in range(60, 120):
+        ib = orc.gen_trace(_orc_params(p), t)
+        eng.post_inbox_dense(ib, slot=1)
+        eng.tick(1)
+        orc.tick(ib)
+    assert_state_equal(eng.export_state(), orc.export(), "dense host inbox")
+
+
+def test_sparse_delta_inbox_equals_dense():
+    G, R = 3000, 7
+    eng, orc, p = _warm(G, R, 22, 50)
+    for t in range(50, 90):
+        ib = orc.gen_trace(_orc_params(p), t)
+        rs, gs = np.nonzero(ib["type"])
+        msgs = [(int(g), int(r) + 1, int(ib["type"][r, g]), int(ib["term"][r, g]), int(ib["index"][r, g]),
+                 int(ib["logterm"][r, g]), int(ib["commit"][r, g])) for r, g in zip(rs, gs)]
+        eng.post_inbox_delta(msgs, slot=2)
+        pg = np.nonzero(ib["prop_count"])[0]
+        eng.propose(pg, ib["prop_count"][pg], slot=2)
+        eng.tick(2)
+        orc.tick(ib)
+        assert_state_equal(eng.export_state(), orc.export(), f"sparse tick {t}")
+
+
+def test_match_update_then_quorum_equals_step_by_step():
+    """a14 as a sparse pass + K3  ==  Step(MsgAppResp) one at a time on the oracle."""
+    G, R = 4000, 5
+    rng = np.random.default_rng(31)
+    st = leader_state(G, R, rng)
+    eng, orc = Engine(G, R), Oracle(G, R)
+    eng.import_state(st)
+    orc.import_state(st)
+    n = 6000
+    gs = rng.integers(0, G, size=n, dtype=np.uint64)
+    fr = rng.integers(1, R + 1, size=n).astype(np.uint8)
+    ok = fr != st["self_id"][gs.astype(np.int64)]
+    gs, fr = gs[ok], fr[ok]
+    idx = st["last_index"][gs.astype(np.int64)] - rng.integers(0, 3, size=len(gs), dtype=np.uint64)
+    eng.match_update(gs, fr, idx)
+    eng.quorum_commit()
+    for g, f, i in zip(gs, fr, idx):
+        orc.step(int(g), F.MSG_APP_RESP, frm=int(f), term=int(st["term"][g]), index=int(i))
+    o = orc.export()
+    np.testing.assert_array_equal(eng.sync_commits(), o["committed"])
+    np.testing.assert_array_equal(eng.export_state(("match",))["match"], o["match"])
+
+
+def test_commit_delta_drain_reconstructs_commits():
+    G, R = 6000, 3
+    eng, orc, p = _warm(G, R, 23, 40, cfg_no=2)
+    base = np.zeros(G, np.uint64)
+    for t in range(40, 100):
+        eng.gen_trace(p, t)
+        eng.tick()
+        d = eng.sync_commit_deltas()
+        full = eng.sync_commits()
+        sat = d == 255
+        base[~sat] += d[~sat].astype(np.uint64)
+        np.testing.assert_array_equal(base[~sat], full[~sat])
+        base[sat] = base[sat]  # saturated groups keep their base until read in full
+    assert (base > 0).mean() > 0.5
+
+
+def test_export_import_roundtrip_and_next():
+    G, R = 2500, 5
+    eng, orc, p = _warm(G, R, 24, 80)
+    s = eng.export_state()
+    eng2 = Engine(G, R, seed=24)
+    eng2.import_state(s)
+    eng2.tick_count = eng.tick_count
+    for t in range(80, 110):
+        for e in (eng, eng2):
+            e.gen_trace(p, t)
+            e.tick()
+    a, b = eng.export_state(), eng2.export_state()
+    lead = a["role"] == LEADER
+    for k in a:
+        if k == "match":
+            np.testing.assert_array_equal(a[k][:, lead], b[k][:, lead])
+        else:
+            np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+    nx = eng.export_next()
+    want = np.maximum(a["match"] + np.uint64(1), a["term_start"][None, :])
+    np.testing.assert_array_equal(nx[:, lead], want[:, lead])
+
+
+def test_counters_match_oracle_out_words():
+    G, R = 4096, 5
+    p = preset_trace(5)
+    eng, orc = Engine(G, R, seed=25), Oracle(G, R, seed=25)
+    won = stepped = camp = 0
+    for t in range(150):
+        eng.gen_trace(p, t)
+        ib = eng.read_inbox()
+        eng.tick()
+        orc.tick(ib)
+        out = orc.export()["out"]
+        won += int(((out & F.OUT_BECAME_LEADER) != 0).sum())
+        stepped += int(((out & F.OUT_STEPPED_DOWN) != 0).sum())
+        camp += int(((out & F.OUT_CAMPAIGN) != 0).sum())
+    c = eng.counters()
+    assert c["elections_won"] == won and c["step_downs"] == stepped
+    assert c["campaigns"] >= camp  # R=5: every campaign emits MsgVote, so these are equal
+    assert c["campaigns"] == camp
+    assert c["ticks"] == 150 and c["kernel_launches"] >= 300
