@@ -87,10 +87,10 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, device: int):
         super().__init__(daemon=True)
-        self.device, self.rows, self._stop = device, [], threading.Event()
+        self.device, self.rows, self._halt = device, [], threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
                                       str(self.device)], capture_output=True, text=True, timeout=5).stdout.strip()
@@ -98,10 +98,10 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._halt.wait(0.1)
 
     def finish(self) -> dict:
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=6)
         sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
@@ -226,12 +226,10 @@ def run_ours(args):
     eng.import_state(st0)
     p = preset_trace(3)
 
-    if world > 1:  # one NCCL communicator for the per-tick all-gather of committed[]
-        uid = torch.zeros(_ffi.MRQ_COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid.copy_(torch.frombuffer(bytearray(Engine.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        eng.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+    if world > 1:  # the per-tick all-gather of committed[]: fused peer stores (default) or ncclAllGather
+        from raftsql_b200 import multi
+
+        multi.attach(eng, dist, args.gather)
 
     # dry run: generate the trace tick by tick on the device (each tick's acks depend on that tick's state),
     # one inbox slot per tick; then rewind the state so the timed run replays exactly these inputs.
@@ -296,7 +294,9 @@ def run_ours(args):
         "dtype": "u64", "data": "synthetic",
         "config": {"workload": "1,048,576 groups x 5 replicas, steady-state append/ack trace (BASELINE configs[2]/[3])",
                    "groups_total": G_TOTAL, "groups_per_gpu": G, "replicas": R, "parallelism": f"groups sharded x{world}",
-                   "collective": "ncclAllGather(committed) per tick" if world > 1 else "none",
+                   "collective": ("none" if world == 1 else
+                                  "all-gather of committed[] per tick, fused into the tick kernel as peer stores over NVLink"
+                                  if args.gather == "fused" else "ncclAllGather(committed) per tick"),
                    "l2": f"inputs larger than L2: {nslots} rotating inbox slots, per-step footprint "
                          f"{(tb['total'] * G) / 1e6:.0f} MB vs 126 MB L2"},
         "group_ticks_per_sec": ticks_per_s * G_TOTAL,
@@ -307,7 +307,11 @@ def run_ours(args):
         "clocks": clocks,
     }
 
-    if rank == 0 and world == 1:
+    fast = os.environ.get("MRQ_BENCH_FAST") == "1"  # profiling runs (ncu): kernels only, no CPU legs
+    if rank == 0 and world == 1 and fast:
+        line["roofline_quorum_kernel"] = bench_quorum_kernel(torch, eng, peak, K, W)
+        line["e2e"] = None
+    elif rank == 0 and world == 1:
         line["roofline_quorum_kernel"] = bench_quorum_kernel(torch, eng, peak, K, W)
         line["e2e"] = bench_e2e(eng, st0, host_ib, K, W)
         # CPU baseline: the oracle port on this box's host cores, bounded sample
@@ -406,6 +410,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
+                    help="N>1: how committed[] is all-gathered each tick")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
