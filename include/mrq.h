@@ -176,14 +176,17 @@ typedef struct mrq_msg {
 int mrq_post_inbox_delta(mrq_engine *e, uint32_t slot, const mrq_msg *msgs, size_t n, int accumulate);
 
 /* Packed dense form for the PCIe-bound host path: one 32-bit word per (sender, group) slot, decoded
- * on the device against the receiver's own state (exact, with an escape to the wide form):
+ * on the device against two per-group BASE columns the host sets with mrq_set_packed_base (so the
+ * decode never depends on engine state the host may be a few ticks behind on).  Exact; anything that
+ * does not fit rides in the `wide` escape list:
  *   bits  0..3   type        bit 4 REJECT
- *   bits  5..6   term code:  0 => term == receiver's current term, 1 => term+1, 2 => term+2,
- *                            3 => escape: the full message is in the `wide` list instead
- *   bits  7..31  payload (25 bits), by type:
- *        MSG_APP_RESP      lag:  index  = last_index - lag   (escape if lag >= 2^25)
- *        MSG_VOTE          bits 7..8 logterm code (0 => == receiver last_term, 1 => +1, 2 => -1... see DESIGN)
- *        MSG_HEARTBEAT     commit = committed + payload
+ *   bits  5..6   term code c: term = base_term[g] + c for c in 0..2; c == 3 => escaped to `wide`
+ *   bits  7..31  payload p (25 bits), by type:
+ *        MSG_APP_RESP      index  = base_index[g] + p
+ *        MSG_HEARTBEAT     commit = base_index[g] + p
+ *        MSG_VOTE          logterm = base_term[g] + (p & 3), index = base_index[g] + (p >> 2)
+ *        MSG_VOTE_RESP / MSG_HEARTBEAT_RESP   p unused
+ *        MSG_APP           always escaped (needs three 64-bit fields)
  * Escaped / wide messages ride in `wide` (n_wide entries) and override their slot.            */
 typedef struct mrq_inbox_packed {
   const uint32_t *word;       /* [R][G] */
@@ -192,6 +195,8 @@ typedef struct mrq_inbox_packed {
   size_t n_wide;
 } mrq_inbox_packed;
 int mrq_post_inbox_packed(mrq_engine *e, uint32_t slot, const mrq_inbox_packed *in);
+/* Dense [G] decode bases for the packed form (NULL keeps the current column).  Blocking. */
+int mrq_set_packed_base(mrq_engine *e, const uint64_t *base_index, const uint64_t *base_term);
 
 /* Proposals only (node.Propose, reference raft.go:211-215): sparse (group, count) pairs added to
  * inbox slot `slot`'s prop_count.                                                             */
@@ -214,13 +219,14 @@ int mrq_tick_idle(mrq_engine *e, uint32_t n);
  * Reads 8R+16 bytes per group, writes 8 when the commit index moves.  Asynchronous.           */
 int mrq_quorum_commit(mrq_engine *e);
 
-/* Which implementation mrq_quorum_commit uses: 0 = 128-bit LDG form (default), 1 = TMA bulk-copy
- * form (replica columns staged through shared memory with cp.async.bulk + mbarrier).          */
+/* Which implementation mrq_quorum_commit uses: 0 = 256-bit LDG form, four groups per thread
+ * (default), 1 = TMA bulk-copy form (replica columns staged through shared memory with
+ * cp.async.bulk + mbarrier), 2 = 128-bit LDG form, two groups per thread.                      */
 int mrq_set_quorum_variant(mrq_engine *e, int variant);
 /* The same kernel over caller-owned DEVICE columns (zero-copy integration; also what bench.py
  * rotates through so every timed launch reads cold HBM): d_match is [R][stride] replica-major,
- * d_committed / d_term_start are [n_groups]; stride must be even and >= n_groups.  Asynchronous
- * on the engine stream.                                                                        */
+ * d_committed / d_term_start are [n_groups]; stride must be a multiple of 4 and >= n_groups and
+ * the columns 32-byte aligned.  Asynchronous on the engine stream.                             */
 int mrq_quorum_commit_ext(mrq_engine *e, const uint64_t *d_match, uint64_t *d_committed, const uint64_t *d_term_start,
                           uint64_t n_groups, uint64_t stride, int variant);
 

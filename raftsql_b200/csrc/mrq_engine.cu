@@ -80,6 +80,7 @@ struct mrq_engine {
   uint64_t *commit_prev = nullptr;  // commit-delta drain base
   uint8_t *delta = nullptr;
   uint64_t *gathered = nullptr;     // [world * G]
+  uint64_t *pk_base_index = nullptr, *pk_base_term = nullptr;  // packed-inbox decode bases
   uint64_t tick_no = 0;
   uint64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -93,7 +94,7 @@ struct mrq_engine {
   uint32_t world = 1, rank = 0, comm_mode = 0;
   uint64_t *peer_gather[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool ipc_attached = false;
-  int quorum_variant = 0;  // 0 = LDG.128, 1 = TMA bulk
+  int quorum_variant = 0;  // 0 = LDG.256 (4 groups/thread), 1 = TMA bulk, 2 = LDG.128
   std::string err;
 };
 
@@ -120,6 +121,23 @@ int fail(mrq_engine *e, int code, const char *fmt, ...) {
   } while (0)
 
 inline unsigned nblocks(uint64_t n, unsigned bs = 256) { return (unsigned)((n + bs - 1) / bs); }
+
+// Launch with programmatic stream serialization (PDL): the grid may start occupying SMs while the previous
+// kernel in the stream drains; the kernel itself waits (griddepcontrol.wait) before touching memory.
+template <typename Arg>
+cudaError_t launch_pdl(void (*kern)(Arg), unsigned grid, unsigned block, size_t smem, cudaStream_t st, const Arg &arg) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, arg);
+}
 
 template <typename T>
 int dalloc(mrq_engine *e, T **p, size_t n) {
@@ -157,9 +175,6 @@ int copy_out(mrq_engine *e, void *host, const void *dev, size_t elem, size_t row
   return MRQ_OK;
 }
 
-template <template <int> class K>
-struct Dispatch;
-
 #define MRQ_DISPATCH_R(R, STMT)  \
   switch (R) {                   \
     case 1: { constexpr int kR = 1; STMT; } break; \
@@ -192,9 +207,10 @@ int launch_tick(mrq_engine *e, const InboxBuf *ib) {
   a.world = (e->comm_mode == 1 && e->ipc_attached) ? e->world : 1;
   a.rank = e->rank;
   for (int p = 0; p < 8; ++p) a.peer_gather[p] = e->peer_gather[p];
-  const unsigned nb = nblocks(e->G);
-  MRQ_DISPATCH_R(e->R, (tick_kernel<kR><<<nb, 256, 0, e->stream>>>(a)));
-  CK(e, cudaGetLastError());
+  const unsigned nb = nblocks(e->G, kTickThreads);
+  cudaError_t lst = cudaErrorInvalidValue;
+  MRQ_DISPATCH_R(e->R, lst = launch_pdl(tick_kernel<kR>, nb, kTickThreads, 0, e->stream, a));
+  CK(e, lst);
   e->launches++;
   e->tick_no++;
   if (e->world > 1 && e->comm_mode == 0 && e->comm) {
@@ -206,6 +222,7 @@ int launch_tick(mrq_engine *e, const InboxBuf *ib) {
 
 constexpr int kTmaTile = 256;
 constexpr int kTmaStages = 4;
+constexpr int kLdg256Threads = 128;
 
 template <int R>
 int launch_quorum_t(mrq_engine *e, const QuorumArgs &a0, int variant, cudaStream_t st, int sm_count) {
@@ -227,20 +244,23 @@ int launch_quorum_t(mrq_engine *e, const QuorumArgs &a0, int variant, cudaStream
     if (grid > ntiles) grid = ntiles;
     QuorumArgs t = a;
     t.G = ntiles * kTmaTile;
-    kern<<<(unsigned)grid, kTmaTile, smem, st>>>(t);
-    CK(e, cudaGetLastError());
+    CK(e, launch_pdl(kern, (unsigned)grid, kTmaTile, smem, st, t));
     if (e) e->launches++;
     done = t.G;
   }
-  if (done < a.G) {  // LDG.128 form (whole range, or the tail the tiled form left)
+  if (done < a.G) {  // an LDG form (whole range, or the tail the tiled form left)
     QuorumArgs t = a;
     t.match = a.match + done;
     t.committed = a.committed + done;
     t.term_start = a.term_start + done;
     t.G = a.G - done;
-    const uint64_t pairs = (t.G + 1) / 2;
-    quorum_kernel_ldg<R><<<nblocks(pairs), 256, 0, st>>>(t);
-    CK(e, cudaGetLastError());
+    if (variant == 2) {
+      const uint64_t pairs = (t.G + 1) / 2;
+      CK(e, launch_pdl(quorum_kernel_ldg<R>, nblocks(pairs), 256, 0, st, t));
+    } else {
+      const uint64_t quads = (t.G + 3) / 4;
+      CK(e, launch_pdl(quorum_kernel_ldg256<R, kLdg256Threads>, nblocks(quads, kLdg256Threads), kLdg256Threads, 0, st, t));
+    }
     if (e) e->launches++;
   }
   return MRQ_OK;
@@ -334,6 +354,8 @@ int mrq_create(const mrq_config *cfg, mrq_engine **out) {
     if ((r = dalloc(e, &e->commit_prev, gs))) return r;
     if ((r = dalloc(e, &e->delta, gs))) return r;
     if ((r = dalloc(e, &e->gathered, gs))) return r;
+    if ((r = dalloc(e, &e->pk_base_index, gs))) return r;
+    if ((r = dalloc(e, &e->pk_base_term, gs))) return r;
     uint32_t nslots = cfg->inbox_slots ? cfg->inbox_slots : 2;
     e->inbox.resize(nslots);
     for (auto &ib : e->inbox) {
@@ -373,7 +395,7 @@ void mrq_destroy(mrq_engine *e) {
       if (p != e->rank && e->peer_gather[p]) cudaIpcCloseMemHandle(e->peer_gather[p]);
   }
   void *ptrs[] = {e->s.term, e->s.meta, e->s.last_index, e->s.last_term, e->s.committed, e->s.term_start, e->s.match,
-                  e->s.out, e->ctr, e->commit_prev, e->delta, e->gathered, e->scratch};
+                  e->s.out, e->ctr, e->commit_prev, e->delta, e->gathered, e->scratch, e->pk_base_index, e->pk_base_term};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (auto &ib : e->inbox) {
@@ -498,6 +520,9 @@ int mrq_import_state(mrq_engine *e, const mrq_state *in) {
     CK(e, cudaGetLastError());
     e->launches++;
   }
+  fix_strict_kernel<<<nblocks(G), 256, 0, e->stream>>>(e->s, G, gs, e->R);
+  CK(e, cudaGetLastError());
+  e->launches++;
   CK(e, cudaStreamSynchronize(e->stream));
   return MRQ_OK;
 }
@@ -573,8 +598,8 @@ int mrq_post_inbox_packed(mrq_engine *e, uint32_t slot, const mrq_inbox_packed *
   MsgRec *d_wide = (MsgRec *)((uint8_t *)e->scratch + wbytes + ((pbytes + 63) / 64) * 64);
   CK(e, cudaMemcpy2DAsync(d_word, e->gs * 4, in->word, e->G * 4, e->G * 4, e->R, cudaMemcpyHostToDevice, e->stream));
   if (in->prop_count8) CK(e, cudaMemcpyAsync(d_prop, in->prop_count8, e->G, cudaMemcpyHostToDevice, e->stream));
-  unpack_inbox_kernel<<<nblocks(e->G), 256, 0, e->stream>>>(e->inbox[slot].view(), e->s, e->gs, e->G, e->R, d_word,
-                                                          in->prop_count8 ? d_prop : nullptr);
+  unpack_inbox_kernel<<<nblocks(e->G), 256, 0, e->stream>>>(e->inbox[slot].view(), e->pk_base_index, e->pk_base_term, e->gs,
+                                                          e->G, e->R, d_word, in->prop_count8 ? d_prop : nullptr);
   CK(e, cudaGetLastError());
   e->launches++;
   if (in->n_wide) {
@@ -584,6 +609,16 @@ int mrq_post_inbox_packed(mrq_engine *e, uint32_t slot, const mrq_inbox_packed *
     CK(e, cudaGetLastError());
     e->launches++;
   }
+  return MRQ_OK;
+}
+
+int mrq_set_packed_base(mrq_engine *e, const uint64_t *base_index, const uint64_t *base_term) {
+  if (!e) return MRQ_E_INVAL;
+  CK(e, cudaSetDevice(e->device));
+  if (e->G == 0) return MRQ_OK;
+  if (base_index) CK(e, cudaMemcpyAsync(e->pk_base_index, base_index, e->G * 8, cudaMemcpyHostToDevice, e->stream));
+  if (base_term) CK(e, cudaMemcpyAsync(e->pk_base_term, base_term, e->G * 8, cudaMemcpyHostToDevice, e->stream));
+  CK(e, cudaStreamSynchronize(e->stream));
   return MRQ_OK;
 }
 
@@ -661,7 +696,7 @@ int mrq_quorum_commit(mrq_engine *e) {
 }
 
 int mrq_set_quorum_variant(mrq_engine *e, int variant) {
-  if (!e || variant < 0 || variant > 1) return MRQ_E_INVAL;
+  if (!e || variant < 0 || variant > 2) return MRQ_E_INVAL;
   e->quorum_variant = variant;
   return MRQ_OK;
 }
@@ -669,7 +704,10 @@ int mrq_set_quorum_variant(mrq_engine *e, int variant) {
 int mrq_quorum_commit_ext(mrq_engine *e, const uint64_t *d_match, uint64_t *d_committed, const uint64_t *d_term_start,
                           uint64_t n_groups, uint64_t stride, int variant) {
   if (!e || !d_match || !d_committed || !d_term_start) return MRQ_E_INVAL;
-  if (stride < n_groups || (stride & 1)) return fail(e, MRQ_E_INVAL, "stride must be even and >= n_groups");
+  if (stride < n_groups || (stride & 3)) return fail(e, MRQ_E_INVAL, "stride must be a multiple of 4 and >= n_groups");
+  if (((uintptr_t)d_match | (uintptr_t)d_committed | (uintptr_t)d_term_start) & 31)
+    return fail(e, MRQ_E_INVAL, "device columns must be 32-byte aligned");
+  if (variant < 0 || variant > 2) return fail(e, MRQ_E_INVAL, "variant outside 0..2");
   CK(e, cudaSetDevice(e->device));
   if (n_groups == 0) return MRQ_OK;
   QuorumArgs a{d_match, d_committed, d_term_start, nullptr, n_groups, stride};

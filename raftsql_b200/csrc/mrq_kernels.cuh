@@ -23,13 +23,15 @@ static constexpr uint64_t kNoGate = 0xFFFFFFFFFFFFFFFFull;  // term_start of a n
 // ---- packed per-group small state ("meta" column, one u64 per group) -----------------------
 //  [0,2) role  [2,6) lead  [6,10) vote  [10,14) self id  [14,26) electionElapsed
 //  [26,38) randomizedElectionTimeout  [38,46) heartbeatElapsed  [46,62) votes (2 bits x 8 slots)
+//  [62] strict: some Progress.Match may exceed lastIndex (an out-of-range ack was seen this leadership)
 struct Meta {
-  uint32_t role, lead, vote, self, elapsed, rto, hb, votes;
+  uint32_t role, lead, vote, self, elapsed, rto, hb, votes, strict;
 };
 __host__ __device__ __forceinline__ uint64_t meta_pack(const Meta &m) {
   return (uint64_t)(m.role & 3u) | ((uint64_t)(m.lead & 15u) << 2) | ((uint64_t)(m.vote & 15u) << 6) |
          ((uint64_t)(m.self & 15u) << 10) | ((uint64_t)(m.elapsed & 0xFFFu) << 14) |
-         ((uint64_t)(m.rto & 0xFFFu) << 26) | ((uint64_t)(m.hb & 0xFFu) << 38) | ((uint64_t)(m.votes & 0xFFFFu) << 46);
+         ((uint64_t)(m.rto & 0xFFFu) << 26) | ((uint64_t)(m.hb & 0xFFu) << 38) |
+         ((uint64_t)(m.votes & 0xFFFFu) << 46) | ((uint64_t)(m.strict & 1u) << 62);
 }
 __host__ __device__ __forceinline__ Meta meta_unpack(uint64_t w) {
   Meta m;
@@ -41,6 +43,7 @@ __host__ __device__ __forceinline__ Meta meta_unpack(uint64_t w) {
   m.rto = (uint32_t)((w >> 26) & 0xFFFu);
   m.hb = (uint32_t)((w >> 38) & 0xFFu);
   m.votes = (uint32_t)((w >> 46) & 0xFFFFu);
+  m.strict = (uint32_t)((w >> 62) & 1u);
   return m;
 }
 
@@ -66,11 +69,17 @@ struct TickArgs {
   // fused peer-store gather (multi-GPU mode 1): committed[g] is stored into every rank's gather buffer
   uint64_t *peer_gather[8];
   uint32_t world, rank;
-  uint64_t *commit_prev;  // optional: previous drain's committed (for commit deltas); unused in the tick
 };
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// Every hot kernel lets the next launch in the stream start filling freed SMs while this grid's tail
+// drains (launch_dependents), and touches global memory only after the previous grid has completed
+// and flushed (wait).  No-ops when the launch did not ask for programmatic serialization.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- cache-hinted accessors ---------------------------------------------------------------------
-// Inbox columns are read exactly once per tick: stream them (evict-first, no L1 allocation).
+// Inbox columns are read exactly once per tick: stream them (read-only path, no L1 allocation).
 __device__ __forceinline__ uint64_t ld_stream(const uint64_t *p) {
   uint64_t v;
   asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
@@ -100,9 +109,8 @@ __device__ __forceinline__ void st_state_u32(uint32_t *p, uint32_t v) {
 }
 
 // ---- q-th largest of R values held in registers (a15: mis[q()-1] after a descending sort) -------
-// Partial selection by bubbling maxima: after pass p the p+1 largest values sit in v[0..p], so q
-// passes leave the q-th largest in v[q-1].  Fully unrolled: every index is a compile-time constant
-// and the values never leave registers.  (R=5, q=3: 9 compare-exchanges.)
+// 64-bit form: partial selection by bubbling maxima (q passes; R=5: 9 compare-exchanges, each
+// 2 ISETP + 4 SEL because sm_100 has no 64-bit integer compare).  Used on the slow path only.
 __device__ __forceinline__ void cswap_desc(uint64_t &hi, uint64_t &lo) {
   const uint64_t a = hi, b = lo;
   const bool sw = a < b;
@@ -110,7 +118,7 @@ __device__ __forceinline__ void cswap_desc(uint64_t &hi, uint64_t &lo) {
   lo = sw ? a : b;
 }
 template <int R>
-__device__ __forceinline__ uint64_t quorum_index(const uint64_t (&m)[R]) {
+__device__ __forceinline__ uint64_t quorum_index64(const uint64_t (&m)[R]) {
   constexpr int Q = R / 2 + 1;  // a7: q() = len(prs)/2 + 1
   uint64_t v[R];
 #pragma unroll
@@ -122,6 +130,63 @@ __device__ __forceinline__ uint64_t quorum_index(const uint64_t (&m)[R]) {
   }
   return v[Q - 1];
 }
+// 32-bit form on single-instruction min/max (VIMNMX.U32): the q-th largest of R uint32 values.
+template <int R>
+__device__ __forceinline__ uint32_t quorum_index32(const uint32_t (&d)[R]) {
+  constexpr int Q = R / 2 + 1;
+  if constexpr (R == 1) {
+    return d[0];
+  } else if constexpr (R == 2) {
+    return min(d[0], d[1]);  // q = 2: the smaller one
+  } else if constexpr (R == 3) {  // median of 3: 4 ops
+    return max(min(d[0], d[1]), min(max(d[0], d[1]), d[2]));
+  } else if constexpr (R == 5) {  // median of 5: 10 ops — drop the min and max of four, median3 with the fifth
+    const uint32_t lo_ab = min(d[0], d[1]), hi_ab = max(d[0], d[1]);
+    const uint32_t lo_cd = min(d[2], d[3]), hi_cd = max(d[2], d[3]);
+    const uint32_t f = max(lo_ab, lo_cd), g = min(hi_ab, hi_cd);
+    return max(min(d[4], f), min(max(d[4], f), g));
+  } else {
+    uint32_t v[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) v[i] = d[i];
+#pragma unroll
+    for (int p = 0; p < Q; ++p) {
+#pragma unroll
+      for (int i = R - 1; i > p; --i) {
+        const uint32_t a = v[i - 1], b = v[i];
+        v[i - 1] = max(a, b);
+        v[i] = min(a, b);
+      }
+    }
+    return v[Q - 1];
+  }
+}
+// mci = q-th largest of match[].  Fast path: order statistics commute with the monotone map
+// x -> max(x - committed, 0), so when every match is within 2^32 of `committed` (above) or below it
+// (clamped to 0: such a value can never be the new commit index) the selection runs on 32-bit
+// deltas; any other value falls back to the exact 64-bit network.  Returns the exact mci whenever
+// mci > committed, and some value <= committed otherwise (callers only test mci > committed).
+// d = max(m - c, 0) if that fits 32 bits; otherwise flags `bad`.  One borrow chain (3 instructions):
+// b = all-ones iff m < c (behind: clamps to 0 whatever the distance), hi != 0 otherwise means too far ahead.
+__device__ __forceinline__ void delta32(uint64_t m, uint64_t c, uint32_t &d, uint32_t &bad) {
+  uint32_t lo, hi, b;
+  asm("sub.cc.u32 %0, %3, %5;\n\t"
+      "subc.cc.u32 %1, %4, %6;\n\t"
+      "subc.u32 %2, 0, 0;"
+      : "=r"(lo), "=r"(hi), "=r"(b)
+      : "r"((uint32_t)m), "r"((uint32_t)(m >> 32)), "r"((uint32_t)c), "r"((uint32_t)(c >> 32)));
+  d = ((b | hi) == 0u) ? lo : 0u;
+  bad |= ~b & hi;
+}
+template <int R>
+__device__ __forceinline__ uint64_t quorum_index(const uint64_t (&m)[R], uint64_t committed) {
+  uint32_t d[R];
+  uint32_t bad = 0;
+#pragma unroll
+  for (int r = 0; r < R; ++r) delta32(m[r], committed, d[r], bad);
+  if (__builtin_expect(bad == 0u, 1)) return committed + quorum_index32<R>(d);
+  return quorum_index64<R>(m);
+}
 
 // ---- one group's state machine, in registers ------------------------------------------------------
 enum : uint32_t {
@@ -132,9 +197,10 @@ template <int R>
 struct Group {
   uint64_t term, last_index, last_term, committed, gate;
   uint64_t match[R];
-  uint32_t role, lead, vote, self, elapsed, rto, hb, votes;
+  uint32_t role, lead, vote, self, elapsed, rto, hb, votes, strict;
   uint32_t out, dirty, ev;  // ev: event bits for the counters
   bool lt_valid;
+  bool pending;             // a Progress.Match rose and maybeCommit() has not been evaluated yet
   // context
   const uint64_t *lt_ptr;
   uint64_t seed, gg, tick_no;
@@ -158,6 +224,31 @@ struct Group {
         dirty |= D_MATCH0 << r;
       }
   }
+  // a15 + a16: mci = q-th largest match; commit iff mci > committed && term(mci) == Term, where for a
+  // leader term(i) == Term  <=>  term_start <= i <= lastIndex.
+  __device__ __forceinline__ bool maybeCommit() {
+    const uint64_t mci = quorum_index<R>(match, committed);
+    if (mci > committed && mci >= gate && mci <= last_index) {
+      committed = mci;
+      dirty |= D_COMMIT;
+      out |= MRQ_OUT_COMMIT_ADVANCED;
+      ev |= EV_COMMIT;
+      return true;
+    }
+    return false;
+  }
+  // upstream runs maybeCommit() after EVERY successful maybeUpdate.  Within a tick match[] only rises, so
+  // the successive quorum indices are non-decreasing and the gate (>= term_start) is monotone in them: as
+  // long as no match exceeds lastIndex, evaluating once after the last update commits exactly what the
+  // sequence of evaluations would have.  (`strict` marks the other case — an out-of-range ack — and
+  // makes every update evaluate immediately, as upstream does.)  Flushed before anything that reads
+  // `committed`, changes role, or appends.
+  __device__ __forceinline__ void flushCommit() {
+    if (pending) {
+      pending = false;
+      if (maybeCommit()) out |= MRQ_OUT_BCAST_APPEND;  // stepLeader: if r.maybeCommit() { r.bcastAppend() }
+    }
+  }
   // a12 / upstream raft.reset(term)
   __device__ __forceinline__ void reset(uint64_t t) {
     if (term != t) {
@@ -172,6 +263,7 @@ struct Group {
     rto = mrq_randomized_timeout(seed, gg, tick_no, et);
   }
   __device__ __forceinline__ void becomeFollower(uint64_t t, uint32_t ld) {
+    flushCommit();
     if (role != MRQ_ROLE_FOLLOWER) {
       out |= MRQ_OUT_STEPPED_DOWN;
       ev |= EV_STEPDOWN;
@@ -184,19 +276,6 @@ struct Group {
       dirty |= D_GATE;
     }
   }
-  // a15 + a16: mci = q-th largest match; commit iff mci > committed && term(mci) == Term, where for a
-  // leader term(i) == Term  <=>  term_start <= i <= lastIndex.
-  __device__ __forceinline__ bool maybeCommit() {
-    const uint64_t mci = quorum_index<R>(match);
-    if (mci > committed && mci >= gate && mci <= last_index) {
-      committed = mci;
-      dirty |= D_COMMIT;
-      out |= MRQ_OUT_COMMIT_ADVANCED;
-      ev |= EV_COMMIT;
-      return true;
-    }
-    return false;
-  }
   // a5: appendEntry(n entries stamped with Term) + self maybeUpdate + maybeCommit
   __device__ __forceinline__ void appendEntry(uint32_t n) {
     last_index += n;
@@ -207,12 +286,15 @@ struct Group {
       dirty |= D_LT;
     }
     setSelfMatch(last_index);
+    pending = false;  // the evaluation below subsumes any deferred one: match only rose since
     maybeCommit();
   }
   __device__ __forceinline__ void becomeLeader() {
     reset(term);
     lead = self;
     role = MRQ_ROLE_LEADER;
+    strict = 0;
+    pending = false;
     out |= MRQ_OUT_BECAME_LEADER;
     ev |= EV_WON;
 #pragma unroll
@@ -272,7 +354,7 @@ struct Group {
     out |= 1u << (MRQ_OUT_ACK_REPLY_SHIFT + r);
   }
 
-  // upstream raft.Step(m) for the message in sender slot r (id r+1); R_ is the compile-time slot so
+  // upstream raft.Step(m) for the message in sender slot R_ (id R_+1); R_ is a compile-time slot so
   // match[] stays in registers.
   template <int R_>
   __device__ __forceinline__ void step(uint32_t ty, uint64_t mterm, uint64_t index, const uint64_t *p_logterm,
@@ -291,9 +373,17 @@ struct Group {
     if (role == MRQ_ROLE_LEADER) {
       if (type == MRQ_MSG_APP_RESP) {  // a14 + a15/a16
         if (!reject && match[R_] < index) {
+          if (index > last_index && !strict) {  // out-of-range ack: from here on evaluate eagerly
+            flushCommit();
+            strict = 1;
+          }
           match[R_] = index;
           dirty |= D_MATCH0 << R_;
-          if (maybeCommit()) out |= MRQ_OUT_BCAST_APPEND;
+          if (strict) {
+            if (maybeCommit()) out |= MRQ_OUT_BCAST_APPEND;
+          } else {
+            pending = true;
+          }
         }
       } else if (type == MRQ_MSG_VOTE) {
         replyVote(R_, true);
@@ -348,7 +438,7 @@ struct Group {
 
   __device__ __forceinline__ void propose(uint32_t n) {  // a5
     if (role == MRQ_ROLE_LEADER) {
-      appendEntry(n);
+      appendEntry(n);  // (also settles a deferred evaluation; BCAST_APPEND is set either way)
       out |= MRQ_OUT_BCAST_APPEND;
     } else if (role == MRQ_ROLE_CANDIDATE || lead == 0) {
       out |= MRQ_OUT_PROP_DROPPED;
@@ -356,6 +446,7 @@ struct Group {
       out |= MRQ_OUT_PROP_FORWARD;
     }
   }
+
   // a3 + a11: Tick()
   __device__ __forceinline__ void tick() {
     if (role == MRQ_ROLE_LEADER) {
@@ -402,10 +493,13 @@ __device__ __forceinline__ void count_events(Counters *c, uint32_t ev) {
 }
 
 // ---- the fused per-tick kernel (a3–a16) ---------------------------------------------------------------
+static constexpr int kTickThreads = 128;  // small CTAs: finer register-file packing (6 x 128 threads at <= 85 regs)
 template <int R>
-__global__ void __launch_bounds__(256) tick_kernel(const TickArgs a) {
+__global__ void __launch_bounds__(kTickThreads, (R <= 5 ? 6 : 5)) tick_kernel(const TickArgs a) {
+  pdl_launch_dependents();
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t ev = 0;
+  pdl_wait();
   if (i < a.G) {
     const bool has_inbox = a.in.type != nullptr;
     // phase 1: group state + the tick's message types
@@ -421,8 +515,8 @@ __global__ void __launch_bounds__(256) tick_kernel(const TickArgs a) {
     const uint32_t nprop = (has_inbox && a.in.prop) ? ld_stream_u32(a.in.prop + i) : 0u;
     const Meta m = meta_unpack(w_meta);
     g.role = m.role; g.lead = m.lead; g.vote = m.vote; g.self = m.self;
-    g.elapsed = m.elapsed; g.rto = m.rto; g.hb = m.hb; g.votes = m.votes;
-    g.out = 0; g.dirty = 0; g.ev = 0; g.lt_valid = false; g.last_term = 0;
+    g.elapsed = m.elapsed; g.rto = m.rto; g.hb = m.hb; g.votes = m.votes; g.strict = m.strict;
+    g.out = 0; g.dirty = 0; g.ev = 0; g.lt_valid = false; g.last_term = 0; g.pending = false;
     g.lt_ptr = a.s.last_term + i;
     g.seed = a.seed; g.gg = a.group_base + i; g.tick_no = a.tick_no;
     g.et = a.election_tick; g.ht = a.heartbeat_tick;
@@ -440,11 +534,12 @@ __global__ void __launch_bounds__(256) tick_kernel(const TickArgs a) {
     // Step every message in sender order, then proposals, then the tick
     StepAll<R, 0>::run(g, ty, mt, mi, a.in, a.gs, i);
     if (nprop) g.propose(nprop);
+    g.flushCommit();
     g.tick();
     // write back what changed
     Meta o;
     o.role = g.role; o.lead = g.lead; o.vote = g.vote; o.self = g.self;
-    o.elapsed = g.elapsed; o.rto = g.rto; o.hb = g.hb; o.votes = g.votes;
+    o.elapsed = g.elapsed; o.rto = g.rto; o.hb = g.hb; o.votes = g.votes; o.strict = g.strict;
     const uint64_t w_new = meta_pack(o);
     if (w_new != w_meta) st_state(a.s.meta + i, w_new);
     if (g.dirty & D_TERM) st_state(a.s.term + i, g.term);
@@ -467,8 +562,7 @@ __global__ void __launch_bounds__(256) tick_kernel(const TickArgs a) {
   if (__any_sync(0xFFFFFFFFu, ev != 0)) count_events(a.ctr, ev);
 }
 
-// ---- K3: the standalone quorum kernel (a15–a16), LDG.128 form ------------------------------------------
-// Two groups per thread: every column is read with one 128-bit load per thread (512 B per warp).
+// ---- K3: the standalone quorum kernel (a15–a16) ------------------------------------------------------------
 // Reads 8R+16 bytes per group (match[R], committed, term_start); writes committed where it moves.
 // Precondition (checked by the fused tick, which has lastIndex in registers): match <= lastIndex.
 struct QuorumArgs {
@@ -479,6 +573,78 @@ struct QuorumArgs {
   uint64_t G, gs;
 };
 
+template <int R>
+__device__ __forceinline__ uint64_t quorum_commit_one(const uint64_t (&m)[R], uint64_t committed, uint64_t gate,
+                                                      bool &moved) {
+  const uint64_t mci = quorum_index<R>(m, committed);
+  moved = mci > committed && mci >= gate;
+  return moved ? mci : committed;
+}
+
+__device__ __forceinline__ void count_moved(Counters *ctr, unsigned nmoved) {
+  if (ctr) {  // warp-shuffle reduction of the "commit advanced" count, one atomic per warp
+    const unsigned tot = __reduce_add_sync(0xFFFFFFFFu, nmoved);
+    if (tot != 0 && (threadIdx.x & 31u) == 0) atomicAdd(&ctr->commits_advanced, (unsigned long long)tot);
+  }
+}
+
+// -- 256-bit form: four groups per thread, every column read with ONE 256-bit load per thread
+//    (LDG.E.256: 1 KB per warp per column), R+2 independent 32-byte loads in flight per thread.
+struct u64x4 {
+  uint64_t v[4];
+};
+__device__ __forceinline__ u64x4 ld_stream_v4(const uint64_t *p) {
+  u64x4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0, %1, %2, %3}, [%4];"
+               : "=l"(r.v[0]), "=l"(r.v[1]), "=l"(r.v[2]), "=l"(r.v[3])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ u64x4 ld_plain_v4(const uint64_t *p) {
+  u64x4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];"
+               : "=l"(r.v[0]), "=l"(r.v[1]), "=l"(r.v[2]), "=l"(r.v[3])
+               : "l"(p));
+  return r;
+}
+
+template <int R, int THREADS>
+__global__ void __launch_bounds__(THREADS) quorum_kernel_ldg256(const QuorumArgs a) {
+  pdl_launch_dependents();
+  const uint64_t i = ((uint64_t)blockIdx.x * THREADS + threadIdx.x) * 4;
+  unsigned nmoved = 0;
+  pdl_wait();
+  if (i + 3 < a.G) {
+    u64x4 mv[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) mv[r] = ld_stream_v4(a.match + (uint64_t)r * a.gs + i);
+    const u64x4 cm = ld_plain_v4(a.committed + i);
+    const u64x4 gt = ld_stream_v4(a.term_start + i);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint64_t m[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) m[r] = mv[r].v[k];
+      bool moved;
+      const uint64_t c = quorum_commit_one<R>(m, cm.v[k], gt.v[k], moved);
+      if (moved) st_state(a.committed + i + k, c);
+      nmoved += moved;
+    }
+  } else {
+    for (uint64_t j = i; j < a.G; ++j) {  // ragged tail (< 4 groups)
+      uint64_t m[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) m[r] = ld_stream(a.match + (uint64_t)r * a.gs + j);
+      bool moved;
+      const uint64_t c = quorum_commit_one<R>(m, ld_state(a.committed + j), ld_stream(a.term_start + j), moved);
+      if (moved) st_state(a.committed + j, c);
+      nmoved += moved;
+    }
+  }
+  count_moved(a.ctr, nmoved);
+}
+
+// -- 128-bit form: two groups per thread.
 __device__ __forceinline__ ulonglong2 ld_stream_v2(const uint64_t *p) {
   ulonglong2 v;
   asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
@@ -491,18 +657,12 @@ __device__ __forceinline__ ulonglong2 ld_plain_v2(const uint64_t *p) {
 }
 
 template <int R>
-__device__ __forceinline__ uint64_t quorum_commit_one(const uint64_t (&m)[R], uint64_t committed, uint64_t gate,
-                                                      bool &moved) {
-  const uint64_t mci = quorum_index<R>(m);
-  moved = mci > committed && mci >= gate;
-  return moved ? mci : committed;
-}
-
-template <int R>
 __global__ void __launch_bounds__(256) quorum_kernel_ldg(const QuorumArgs a) {
+  pdl_launch_dependents();
   const uint64_t pair = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t i = pair * 2;
   unsigned nmoved = 0;
+  pdl_wait();
   if (i + 1 < a.G) {
     ulonglong2 mv[R];
 #pragma unroll
@@ -535,13 +695,10 @@ __global__ void __launch_bounds__(256) quorum_kernel_ldg(const QuorumArgs a) {
     if (mv0) st_state(a.committed + i, c0);
     nmoved = mv0;
   }
-  if (a.ctr) {  // warp-shuffle reduction of the "commit advanced" count, one atomic per warp
-    const unsigned tot = __reduce_add_sync(0xFFFFFFFFu, nmoved);
-    if (tot != 0 && (threadIdx.x & 31u) == 0) atomicAdd(&a.ctr->commits_advanced, (unsigned long long)tot);
-  }
+  count_moved(a.ctr, nmoved);
 }
 
-// ---- K3, TMA form: replica columns staged through shared memory by the bulk-copy engine --------------
+// -- TMA form: replica columns staged through shared memory by the bulk-copy engine.
 // A persistent CTA walks tiles of TILE groups.  For each tile one elected thread issues R+2 1-D bulk
 // copies (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes — UBLKCP in SASS) of
 // TILE*8 bytes each (match[0..R-1], committed, term_start) into one of STAGES shared-memory stages and
@@ -577,17 +734,19 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 
 template <int R, int TILE, int STAGES>
 __global__ void __launch_bounds__(TILE) quorum_kernel_tma(const QuorumArgs a) {
+  pdl_launch_dependents();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int COLS = R + 2;
   uint64_t *tiles = reinterpret_cast<uint64_t *>(smem_raw);                     // [STAGES][COLS][TILE]
   uint64_t *bars = tiles + (size_t)STAGES * COLS * TILE;                        // [STAGES]
-  const uint64_t ntiles = a.G / TILE;  // host guarantees G % TILE == 0 for this path (tail goes to LDG form)
+  const uint64_t ntiles = a.G / TILE;  // host guarantees G % TILE == 0 for this path (tail goes to an LDG form)
   const uint32_t tid = threadIdx.x;
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pdl_wait();
   auto issue = [&](uint64_t tile, int s) {
     uint64_t *dst = tiles + (size_t)s * COLS * TILE;
     const uint64_t base = tile * TILE;
@@ -598,7 +757,6 @@ __global__ void __launch_bounds__(TILE) quorum_kernel_tma(const QuorumArgs a) {
     bulk_g2s(dst + (size_t)(R + 1) * TILE, a.term_start + base, TILE * 8, &bars[s]);
   };
   // prologue: fill the pipeline
-  uint64_t next = blockIdx.x;
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       const uint64_t t = (uint64_t)blockIdx.x + (uint64_t)s * gridDim.x;
@@ -608,7 +766,7 @@ __global__ void __launch_bounds__(TILE) quorum_kernel_tma(const QuorumArgs a) {
   unsigned nmoved = 0;
   int s = 0;
   uint32_t parity = 0;
-  for (uint64_t tile = next; tile < ntiles; tile += gridDim.x) {
+  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     mbar_wait(&bars[s], parity);
     const uint64_t *src = tiles + (size_t)s * COLS * TILE;
     uint64_t m[R];
@@ -630,10 +788,7 @@ __global__ void __launch_bounds__(TILE) quorum_kernel_tma(const QuorumArgs a) {
       parity ^= 1u;
     }
   }
-  if (a.ctr) {
-    const unsigned tot = __reduce_add_sync(0xFFFFFFFFu, nmoved);
-    if (tot != 0 && (tid & 31u) == 0) atomicAdd(&a.ctr->commits_advanced, (unsigned long long)tot);
-  }
+  count_moved(a.ctr, nmoved);
 }
 
 // ---- a14 as a sparse pass: Progress.maybeUpdate for a list of acks -----------------------------------
@@ -673,16 +828,18 @@ __global__ void scatter_props_kernel(uint32_t *prop, uint64_t G, const uint64_t 
   if (groups[k] < G) atomicAdd(prop + groups[k], counts[k]);
 }
 
-// Packed inbox (include/mrq.h mrq_inbox_packed): one 32-bit word per slot, decoded against the
-// receiver's own state into the wide columns.  Exact: anything that does not fit escapes to the wide list.
-__global__ void unpack_inbox_kernel(InboxView in, StateView s, uint64_t gs, uint64_t G, uint32_t R, const uint32_t *word,
-                                    const uint8_t *prop8) {
+// Packed inbox (include/mrq.h mrq_inbox_packed): one 32-bit word per slot, decoded against per-group
+// base columns the host set with mrq_set_packed_base (robust to host/device pipelining: the decode
+// never looks at engine state).  Exact: anything that does not fit escapes to the wide list.
+__global__ void __launch_bounds__(256) unpack_inbox_kernel(InboxView in, const uint64_t *base_index,
+                                                            const uint64_t *base_term, uint64_t gs, uint64_t G,
+                                                            uint32_t R, const uint32_t *word, const uint8_t *prop8) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= G) return;
-  const uint64_t term = s.term[i], li = s.last_index[i], cm = s.committed[i];
+  const uint64_t bi = base_index[i], bt = base_term[i];
   for (uint32_t r = 0; r < R; ++r) {
-    const uint32_t w = word[(uint64_t)r * gs + i];
     const uint64_t o = (uint64_t)r * gs + i;
+    const uint32_t w = word[o];
     const uint32_t type = w & 15u;
     const uint32_t tc = (w >> 5) & 3u;
     const uint64_t pay = w >> 7;
@@ -691,18 +848,15 @@ __global__ void unpack_inbox_kernel(InboxView in, StateView s, uint64_t gs, uint
       continue;
     }
     in.type[o] = (uint8_t)(type | ((w & 16u) ? MRQ_MSG_REJECT : 0u));
-    in.term[o] = term + tc;
+    in.term[o] = bt + tc;
     uint64_t index = 0, logterm = 0, commit = 0;
     if (type == MRQ_MSG_APP_RESP) {
-      index = li - pay;  // lag encoding; host guarantees pay <= li
+      index = bi + pay;
     } else if (type == MRQ_MSG_HEARTBEAT) {
-      commit = cm + pay;
-    } else if (type == MRQ_MSG_VOTE) {
-      // payload: bits 0..1 logterm code vs receiver last_term (0 same, 1 +1, 2 +2), bits 2.. signed-ish
-      // index offset: index = last_index + (pay>>2) - 2^21
-      const uint64_t lt = s.last_term[i];
-      logterm = lt + (pay & 3u);
-      index = li + (pay >> 2) - (1ull << 21);
+      commit = bi + pay;
+    } else if (type == MRQ_MSG_VOTE) {  // payload: bits 0..1 logterm - base_term, bits 2..24 index - base_index
+      logterm = bt + (pay & 3u);
+      index = bi + (pay >> 2);
     }
     in.index[o] = index;
     in.logterm[o] = logterm;
@@ -765,6 +919,8 @@ __global__ void unpack_meta_kernel(const uint64_t *meta, uint64_t G, uint8_t *ro
   for (uint32_t r = 0; r < R; ++r) votes[(uint64_t)r * gs + i] = (uint8_t)((m.votes >> (2 * r)) & 3u);
 }
 
+// Import: small-state columns -> meta.  The strict bit is recomputed from the imported columns
+// (some match above lastIndex) by fix_strict_kernel afterwards.
 __global__ void pack_meta_kernel(uint64_t *meta, uint64_t G, const uint8_t *role, const uint8_t *lead, const uint8_t *self_id,
                                  const uint64_t *vote, const uint16_t *el, const uint16_t *hb, const uint16_t *rto,
                                  const uint8_t *votes, uint64_t gs, uint32_t R) {
@@ -784,6 +940,19 @@ __global__ void pack_meta_kernel(uint64_t *meta, uint64_t G, const uint8_t *role
     m.votes = w;
   }
   meta[i] = meta_pack(m);
+}
+
+__global__ void fix_strict_kernel(StateView s, uint64_t G, uint64_t gs, uint32_t R) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G) return;
+  Meta m = meta_unpack(s.meta[i]);
+  uint32_t strict = 0;
+  if (m.role == MRQ_ROLE_LEADER) {
+    const uint64_t li = s.last_index[i];
+    for (uint32_t r = 0; r < R; ++r) strict |= s.match[(uint64_t)r * gs + i] > li;
+  }
+  m.strict = strict;
+  s.meta[i] = meta_pack(m);
 }
 
 __global__ void init_state_kernel(StateView s, uint64_t G, uint64_t group_base, uint32_t R, uint32_t self_id, uint64_t seed,

@@ -163,6 +163,9 @@ class Engine:
         v.wide, v.n_wide = arr, len(wide)
         self._ck(self.L.mrq_post_inbox_packed(self.h, slot, C.byref(v)))
 
+    def set_packed_base(self, base_index: np.ndarray | None, base_term: np.ndarray | None):
+        self._ck(self.L.mrq_set_packed_base(self.h, _p(base_index, F.u64p), _p(base_term, F.u64p)))
+
     def propose(self, groups, counts, slot: int = 0):
         g = np.ascontiguousarray(groups, dtype=np.uint64)
         c = np.ascontiguousarray(counts, dtype=np.uint32)

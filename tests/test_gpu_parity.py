@@ -120,7 +120,7 @@ def test_config3_steady_state_1Mx5_import_and_tick():
 
 # ---- K3: the standalone quorum kernel ------------------------------------------------------------------
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("R", [1, 2, 3, 4, 5, 6, 7, 8])
 def test_quorum_kernel_vs_oracle_and_numpy(R, variant):
     G = 70001  # odd, not a multiple of the TMA tile: exercises the tiled body and the LDG tail
@@ -153,7 +153,7 @@ def test_quorum_kernel_vs_oracle_and_numpy(R, variant):
     np.testing.assert_array_equal(eng.sync_commits(), want)
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_quorum_kernel_full_size_properties(variant):
     """1,048,576 x 5 (BASELINE configs[2]): q-th largest by an independent numpy sort, monotone, gated,
     idempotent, and linear in a uniform index shift."""
@@ -195,7 +195,7 @@ def test_quorum_ext_on_caller_device_buffers():
     dc = torch.from_numpy(st["committed"].view(np.int64)).cuda()
     dg = torch.from_numpy(st["term_start"].view(np.int64)).cuda()
     with Engine(16, R) as eng:
-        for variant in (0, 1):
+        for variant in (0, 1, 2):
             c = dc.clone()
             torch.cuda.synchronize()
             eng.quorum_commit_ext(dm.data_ptr(), c.data_ptr(), dg.data_ptr(), G, stride, variant)
@@ -245,6 +245,36 @@ def test_sparse_delta_inbox_equals_dense():
         assert_state_equal(eng.export_state(), orc.export(), f"sparse tick {t}")
 
 
+def test_packed_inbox_equals_dense():
+    """The 4-byte-per-slot host form decodes to exactly the wide inbox (escapes included)."""
+    from raftsql_b200.packed import pack_inbox
+
+    G, R = 4000, 7
+    eng, orc, p = _warm(G, R, 26, 60)
+    n_escaped = n_packed = 0
+    for t in range(60, 130):
+        cur = orc.export()
+        ib = orc.gen_trace(_orc_params(p), t)
+        # bases near the group's state; lagging followers' stale acks fall below the base and must escape
+        base_index = np.where(cur["last_index"] > 50, cur["last_index"] - np.uint64(50), 0).astype(np.uint64)
+        base_term = np.where(cur["term"] > 0, cur["term"] - np.uint64(t % 2), 0).astype(np.uint64)
+        word, prop8, wide = pack_inbox(ib, base_index, base_term)
+        n_escaped += len(wide)
+        n_packed += int(((word & 15) != 0).sum()) - len(wide)
+        eng.set_packed_base(base_index, base_term)
+        eng.post_inbox_packed(word, prop8, wide, slot=1)
+        got = eng.read_inbox(1)
+        present = (ib["type"] & 0x0F) != 0
+        np.testing.assert_array_equal(got["type"], ib["type"])
+        for k in ("term", "index", "logterm", "commit"):
+            np.testing.assert_array_equal(got[k][present], ib[k][present], err_msg=k)
+        np.testing.assert_array_equal(got["prop_count"], ib["prop_count"])
+        eng.tick(1)
+        orc.tick(ib)
+        assert_state_equal(eng.export_state(), orc.export(), f"packed tick {t}")
+    assert n_escaped > 100 and n_packed > 10 * n_escaped
+
+
 def test_match_update_then_quorum_equals_step_by_step():
     """a14 as a sparse pass + K3  ==  Step(MsgAppResp) one at a time on the oracle."""
     G, R = 4000, 5
@@ -267,6 +297,54 @@ def test_match_update_then_quorum_equals_step_by_step():
     o = orc.export()
     np.testing.assert_array_equal(eng.sync_commits(), o["committed"])
     np.testing.assert_array_equal(eng.export_state(("match",))["match"], o["match"])
+
+
+@pytest.mark.parametrize("R", [3, 5, 7])
+def test_out_of_range_acks_follow_upstream(R):
+    """Acks beyond the leader's lastIndex (a protocol violation): upstream still records the match, and
+    term() of such an index is 0 so it never commits — but an earlier in-range quorum index in the same
+    tick does.  The engine defers maybeCommit() to once per tick EXCEPT in exactly this case."""
+    G = 6000
+    rng = np.random.default_rng(900 + R)
+    st = leader_state(G, R, rng)
+    eng, orc = Engine(G, R, seed=1), Oracle(G, R, seed=1)
+    eng.import_state(st)
+    orc.import_state(st)
+    for t in range(8):
+        cur = orc.export()
+        ib = empty_inbox(G, R)
+        kind = rng.integers(0, 5, size=(R, G))  # 0 none, 1-2 in-range ack, 3 out-of-range ack, 4 stale ack
+        li = cur["last_index"][None, :]
+        idx = np.where(kind == 3, li + rng.integers(1, 1000, size=(R, G), dtype=np.uint64),
+                       np.where(kind == 4, li - np.uint64(30), li - rng.integers(0, 4, size=(R, G), dtype=np.uint64)))
+        ib["type"][:] = np.where(kind > 0, F.MSG_APP_RESP, 0).astype(np.uint8)
+        ib["term"][:] = np.where(kind > 0, cur["term"][None, :], 0)
+        ib["index"][:] = np.where(kind > 0, idx, 0)
+        ib["prop_count"][:] = rng.integers(0, 3, size=G, dtype=np.uint32)
+        if t == 5:  # a higher-term heartbeat right after the acks: the deferred evaluation must land first
+            ib["type"][R - 1, ::7] = F.MSG_HEARTBEAT
+            ib["term"][R - 1, ::7] = cur["term"][::7] + np.uint64(1)
+            ib["index"][R - 1, ::7] = 0
+        eng.post_inbox_dense(ib)
+        eng.tick()
+        orc.tick(ib)
+        assert_state_equal(eng.export_state(), orc.export(), f"tick {t}")
+        np.testing.assert_array_equal(eng.sync_out(), orc.export()["out"])
+    # the strict marker survives an export/import round trip (it is recomputed from match vs lastIndex)
+    eng2 = Engine(G, R, seed=1)
+    eng2.import_state(eng.export_state())
+    eng2.tick_count = eng.tick_count
+    cur = orc.export()
+    ib = empty_inbox(G, R)
+    ib["type"][0, :] = F.MSG_APP_RESP
+    ib["term"][0, :] = cur["term"]
+    ib["index"][0, :] = cur["last_index"]
+    for e in (eng, eng2):
+        e.post_inbox_dense(ib)
+        e.tick()
+    orc.tick(ib)
+    assert_state_equal(eng.export_state(), orc.export(), "after strict")
+    assert_state_equal(eng2.export_state(), orc.export(), "after strict, re-imported")
 
 
 def test_commit_delta_drain_reconstructs_commits():
