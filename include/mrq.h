@@ -240,7 +240,8 @@ int mrq_sync_commits(mrq_engine *e, uint64_t *committed_out, uint8_t *role_out, 
 /* Per-group output word of the last tick (MRQ_OUT_*). */
 int mrq_sync_out(mrq_engine *e, uint32_t *out_words);
 /* Compact commit drain for the host path: per-group advance of committed since the previous
- * drain, saturated to 255 in a byte (255 => read the full value with mrq_sync_commits).       */
+ * drain, saturated to 255 in a byte.  255 means "read the full value": mrq_sync_commits with a
+ * non-NULL committed_out rebases every group's drain to the values it returns.                 */
 int mrq_sync_commit_deltas(mrq_engine *e, uint8_t *delta_out);
 int mrq_synchronize(mrq_engine *e);
 

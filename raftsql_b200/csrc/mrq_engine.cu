@@ -745,7 +745,11 @@ int mrq_sync_commits(mrq_engine *e, uint64_t *committed_out, uint8_t *role_out, 
   if (!e) return MRQ_E_INVAL;
   CK(e, cudaSetDevice(e->device));
   if (e->G == 0) return MRQ_OK;
-  if (committed_out) CK(e, cudaMemcpyAsync(committed_out, e->s.committed, e->G * 8, cudaMemcpyDeviceToHost, e->stream));
+  if (committed_out) {
+    CK(e, cudaMemcpyAsync(committed_out, e->s.committed, e->G * 8, cudaMemcpyDeviceToHost, e->stream));
+    // a full read rebases the compact drain: the next mrq_sync_commit_deltas counts from these values
+    CK(e, cudaMemcpyAsync(e->commit_prev, e->s.committed, e->G * 8, cudaMemcpyDeviceToDevice, e->stream));
+  }
   if (term_out) CK(e, cudaMemcpyAsync(term_out, e->s.term, e->G * 8, cudaMemcpyDeviceToHost, e->stream));
   if (role_out) {
     mrq_state st;

@@ -24,14 +24,16 @@ static constexpr uint64_t kNoGate = 0xFFFFFFFFFFFFFFFFull;  // term_start of a n
 //  [0,2) role  [2,6) lead  [6,10) vote  [10,14) self id  [14,26) electionElapsed
 //  [26,38) randomizedElectionTimeout  [38,46) heartbeatElapsed  [46,62) votes (2 bits x 8 slots)
 //  [62] strict: some Progress.Match may exceed lastIndex (an out-of-range ack was seen this leadership)
+//  [63] ltok:   the stored last_term equals term (always true for a leader after its first append) — lets
+//               the steady-state path skip the last_term column entirely
 struct Meta {
-  uint32_t role, lead, vote, self, elapsed, rto, hb, votes, strict;
+  uint32_t role, lead, vote, self, elapsed, rto, hb, votes, strict, ltok;
 };
 __host__ __device__ __forceinline__ uint64_t meta_pack(const Meta &m) {
   return (uint64_t)(m.role & 3u) | ((uint64_t)(m.lead & 15u) << 2) | ((uint64_t)(m.vote & 15u) << 6) |
          ((uint64_t)(m.self & 15u) << 10) | ((uint64_t)(m.elapsed & 0xFFFu) << 14) |
          ((uint64_t)(m.rto & 0xFFFu) << 26) | ((uint64_t)(m.hb & 0xFFu) << 38) |
-         ((uint64_t)(m.votes & 0xFFFFu) << 46) | ((uint64_t)(m.strict & 1u) << 62);
+         ((uint64_t)(m.votes & 0xFFFFu) << 46) | ((uint64_t)(m.strict & 1u) << 62) | ((uint64_t)(m.ltok & 1u) << 63);
 }
 __host__ __device__ __forceinline__ Meta meta_unpack(uint64_t w) {
   Meta m;
@@ -44,6 +46,7 @@ __host__ __device__ __forceinline__ Meta meta_unpack(uint64_t w) {
   m.hb = (uint32_t)((w >> 38) & 0xFFu);
   m.votes = (uint32_t)((w >> 46) & 0xFFFFu);
   m.strict = (uint32_t)((w >> 62) & 1u);
+  m.ltok = (uint32_t)((w >> 63) & 1u);
   return m;
 }
 
@@ -197,7 +200,7 @@ template <int R>
 struct Group {
   uint64_t term, last_index, last_term, committed, gate;
   uint64_t match[R];
-  uint32_t role, lead, vote, self, elapsed, rto, hb, votes, strict;
+  uint32_t role, lead, vote, self, elapsed, rto, hb, votes, strict, ltok;
   uint32_t out, dirty, ev;  // ev: event bits for the counters
   bool lt_valid;
   bool pending;             // a Progress.Match rose and maybeCommit() has not been evaluated yet
@@ -211,7 +214,7 @@ struct Group {
 
   __device__ __forceinline__ uint64_t lastTerm() {  // raftLog.lastTerm(), loaded on first use
     if (!lt_valid) {
-      last_term = ld_state(lt_ptr);
+      last_term = ltok ? term : ld_state(lt_ptr);
       lt_valid = true;
     }
     return last_term;
@@ -254,6 +257,7 @@ struct Group {
     if (term != t) {
       term = t;
       vote = 0;
+      ltok = 0;  // every existing entry carries a smaller term
       dirty |= D_TERM;
     }
     lead = 0;
@@ -280,11 +284,12 @@ struct Group {
   __device__ __forceinline__ void appendEntry(uint32_t n) {
     last_index += n;
     dirty |= D_LI;
-    if (!lt_valid || last_term != term) {
+    if (!ltok && (!lt_valid || last_term != term)) {
       last_term = term;
       lt_valid = true;
       dirty |= D_LT;
     }
+    ltok = 1;
     setSelfMatch(last_index);
     pending = false;  // the evaluation below subsumes any deferred one: match only rose since
     maybeCommit();
@@ -345,6 +350,7 @@ struct Group {
         lt_valid = true;
         dirty |= D_LT;
       }
+      ltok = logterm == term;
       commitTo(commit);
     }
     out |= 1u << (MRQ_OUT_ACK_REPLY_SHIFT + r);
@@ -513,33 +519,66 @@ __global__ void __launch_bounds__(kTickThreads, (R <= 5 ? 6 : 5)) tick_kernel(co
 #pragma unroll
     for (int r = 0; r < R; ++r) ty[r] = has_inbox ? ld_stream_u8(a.in.type + (uint64_t)r * a.gs + i) : 0u;
     const uint32_t nprop = (has_inbox && a.in.prop) ? ld_stream_u32(a.in.prop + i) : 0u;
+    // Progress.Match rides in the first wave of loads too (it is only meaningful for leaders, but waiting
+    // for `role` would serialise a second round trip in front of the common case)
+#pragma unroll
+    for (int r = 0; r < R; ++r) g.match[r] = ld_state(a.s.match + (uint64_t)r * a.gs + i);
     const Meta m = meta_unpack(w_meta);
     g.role = m.role; g.lead = m.lead; g.vote = m.vote; g.self = m.self;
-    g.elapsed = m.elapsed; g.rto = m.rto; g.hb = m.hb; g.votes = m.votes; g.strict = m.strict;
+    g.elapsed = m.elapsed; g.rto = m.rto; g.hb = m.hb; g.votes = m.votes; g.strict = m.strict; g.ltok = m.ltok;
     g.out = 0; g.dirty = 0; g.ev = 0; g.lt_valid = false; g.last_term = 0; g.pending = false;
     g.lt_ptr = a.s.last_term + i;
     g.seed = a.seed; g.gg = a.group_base + i; g.tick_no = a.tick_no;
     g.et = a.election_tick; g.ht = a.heartbeat_tick;
-    // phase 2: Progress.Match (leaders only) and the messages' term / index
-    const bool was_leader = g.role == MRQ_ROLE_LEADER;
-#pragma unroll
-    for (int r = 0; r < R; ++r) g.match[r] = was_leader ? ld_state(a.s.match + (uint64_t)r * a.gs + i) : 0ull;
+    // phase 2: the present messages' term / index
     uint64_t mt[R], mi[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
+      if ((uint32_t)(r + 1) == g.self) ty[r] = 0;  // a node does not message itself
       const bool present = (ty[r] & MRQ_MSG_TYPE_MASK) != 0;
       mt[r] = present ? ld_stream(a.in.term + (uint64_t)r * a.gs + i) : 0ull;
       mi[r] = present ? ld_stream(a.in.index + (uint64_t)r * a.gs + i) : 0ull;
     }
-    // Step every message in sender order, then proposals, then the tick
-    StepAll<R, 0>::run(g, ty, mt, mi, a.in, a.gs, i);
-    if (nprop) g.propose(nprop);
-    g.flushCommit();
+    // Steady state — a leader whose inbox holds nothing but accepted, same-term, in-range MsgAppResp — is
+    // the overwhelmingly common tick.  It needs none of the role machinery: merge the acks (a14), append
+    // the proposals (a5), evaluate the quorum once (a15/a16, see flushCommit), run the leader's timers.
+    // Everything else takes the general per-message path below; both produce identical state.
+    bool fast = g.role == MRQ_ROLE_LEADER && !g.strict && g.ltok;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      fast = fast && (ty[r] == 0u || (ty[r] == MRQ_MSG_APP_RESP && mt[r] == g.term && mi[r] <= g.last_index));
+    if (fast) {
+      bool changed = false;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (ty[r] != 0u && g.match[r] < mi[r]) {
+          g.match[r] = mi[r];
+          g.dirty |= D_MATCH0 << r;
+          changed = true;
+        }
+      if (nprop) {
+        g.last_index += nprop;
+        g.dirty |= D_LI;
+        g.setSelfMatch(g.last_index);
+        g.out |= MRQ_OUT_BCAST_APPEND;
+        changed = true;
+      }
+      if (changed && g.maybeCommit()) g.out |= MRQ_OUT_BCAST_APPEND;
+    } else {
+      if (g.role != MRQ_ROLE_LEADER) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) g.match[r] = 0ull;  // not a leader: Progress is rebuilt by becomeLeader
+      }
+      // Step every message in sender order, then proposals
+      StepAll<R, 0>::run(g, ty, mt, mi, a.in, a.gs, i);
+      if (nprop) g.propose(nprop);
+      g.flushCommit();
+    }
     g.tick();
     // write back what changed
     Meta o;
     o.role = g.role; o.lead = g.lead; o.vote = g.vote; o.self = g.self;
-    o.elapsed = g.elapsed; o.rto = g.rto; o.hb = g.hb; o.votes = g.votes; o.strict = g.strict;
+    o.elapsed = g.elapsed; o.rto = g.rto; o.hb = g.hb; o.votes = g.votes; o.strict = g.strict; o.ltok = g.ltok;
     const uint64_t w_new = meta_pack(o);
     if (w_new != w_meta) st_state(a.s.meta + i, w_new);
     if (g.dirty & D_TERM) st_state(a.s.term + i, g.term);
@@ -952,6 +991,7 @@ __global__ void fix_strict_kernel(StateView s, uint64_t G, uint64_t gs, uint32_t
     for (uint32_t r = 0; r < R; ++r) strict |= s.match[(uint64_t)r * gs + i] > li;
   }
   m.strict = strict;
+  m.ltok = s.last_term[i] == s.term[i];
   s.meta[i] = meta_pack(m);
 }
 
@@ -963,6 +1003,7 @@ __global__ void init_state_kernel(StateView s, uint64_t G, uint64_t group_base, 
   m.role = MRQ_ROLE_FOLLOWER;
   m.self = self_id ? self_id : (uint32_t)((group_base + i) % R) + 1u;
   m.rto = mrq_randomized_timeout(seed, group_base + i, 0, election_tick);  // newRaft(): becomeFollower -> reset()
+  m.ltok = 1;  // term 0, empty log: lastTerm() == Term
   s.meta[i] = meta_pack(m);
   s.term_start[i] = kNoGate;
 }

@@ -359,7 +359,7 @@ def test_commit_delta_drain_reconstructs_commits():
         sat = d == 255
         base[~sat] += d[~sat].astype(np.uint64)
         np.testing.assert_array_equal(base[~sat], full[~sat])
-        base[sat] = base[sat]  # saturated groups keep their base until read in full
+        base[sat] = full[sat]  # 255 = "read in full"; the full read rebases the drain
     assert (base > 0).mean() > 0.5
 
 
