@@ -213,6 +213,11 @@ int mrq_clear_inbox(mrq_engine *e, uint32_t slot);
 int mrq_tick(mrq_engine *e, uint32_t slot);
 /* n ticks with an empty inbox (timers only). */
 int mrq_tick_idle(mrq_engine *e, uint32_t n);
+/* How mrq_tick is launched: 0 (default) = a lean fast kernel for the ticks that need no role machinery
+ * (steady-state leaders, quiet / heart-beaten followers) + a general kernel over the compacted list of
+ * the remaining groups; 1 = one general kernel over every group.  Both give identical results; mode 1
+ * exists for differential testing.                                                             */
+int mrq_set_tick_mode(mrq_engine *e, int mode);
 
 /* The standalone quorum kernel (K3; SURVEY §8a rows a15–a16): for every leader group,
  * mci = q-th largest of match[0..R-1][g]; committed = mci iff mci > committed && mci >= term_start.

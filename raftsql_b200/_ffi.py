@@ -114,6 +114,7 @@ SIGNATURES = {
     "mrq_clear_inbox": (C.c_int, [_EP, C.c_uint32]),
     "mrq_tick": (C.c_int, [_EP, C.c_uint32]),
     "mrq_tick_idle": (C.c_int, [_EP, C.c_uint32]),
+    "mrq_set_tick_mode": (C.c_int, [_EP, C.c_int]),
     "mrq_quorum_commit": (C.c_int, [_EP]),
     "mrq_set_quorum_variant": (C.c_int, [_EP, C.c_int]),
     "mrq_quorum_commit_ext": (C.c_int, [_EP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int]),

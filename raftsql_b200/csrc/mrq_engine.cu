@@ -81,6 +81,10 @@ struct mrq_engine {
   uint8_t *delta = nullptr;
   uint64_t *gathered = nullptr;     // [world * G]
   uint64_t *pk_base_index = nullptr, *pk_base_term = nullptr;  // packed-inbox decode bases
+  uint32_t *slow_list = nullptr;    // [gs] groups left to the slow kernel this tick
+  unsigned *slow_count = nullptr;   // [2] double-buffered list length
+  uint32_t slow_parity = 0;
+  int tick_mode = 0;                // 0 = fast + slow kernels, 1 = single general kernel
   uint64_t tick_no = 0;
   uint64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -188,6 +192,8 @@ int copy_out(mrq_engine *e, void *host, const void *dev, size_t elem, size_t row
     default: break;              \
   }
 
+int g_sm_count = 148;
+
 int launch_tick(mrq_engine *e, const InboxBuf *ib) {
   if (e->G == 0) {
     e->tick_no++;
@@ -207,11 +213,25 @@ int launch_tick(mrq_engine *e, const InboxBuf *ib) {
   a.world = (e->comm_mode == 1 && e->ipc_attached) ? e->world : 1;
   a.rank = e->rank;
   for (int p = 0; p < 8; ++p) a.peer_gather[p] = e->peer_gather[p];
+  a.slow_list = e->slow_list;
+  a.slow_count = e->slow_count + (e->slow_parity & 1u);
+  a.slow_count_next = e->slow_count + ((e->slow_parity + 1u) & 1u);
   const unsigned nb = nblocks(e->G, kTickThreads);
   cudaError_t lst = cudaErrorInvalidValue;
-  MRQ_DISPATCH_R(e->R, lst = launch_pdl(tick_kernel<kR>, nb, kTickThreads, 0, e->stream, a));
-  CK(e, lst);
-  e->launches++;
+  if (e->tick_mode == 1) {  // single launch, every group through the general path (differential testing)
+    MRQ_DISPATCH_R(e->R, lst = launch_pdl(tick_general_kernel<kR>, nb, kTickThreads, 0, e->stream, a));
+    CK(e, lst);
+    e->launches++;
+  } else {
+    MRQ_DISPATCH_R(e->R, lst = launch_pdl(tick_fast_kernel<kR>, nb, kTickThreads, 0, e->stream, a));
+    CK(e, lst);
+    unsigned nslow = (unsigned)g_sm_count * 6u;
+    if (nslow > nb) nslow = nb;
+    MRQ_DISPATCH_R(e->R, lst = launch_pdl(tick_slow_kernel<kR>, nslow, kTickThreads, 0, e->stream, a));
+    CK(e, lst);
+    e->launches += 2;
+    e->slow_parity ^= 1u;
+  }
   e->tick_no++;
   if (e->world > 1 && e->comm_mode == 0 && e->comm) {
     int st = g_nccl.AllGather(e->s.committed, e->gathered, (size_t)e->G, kNcclUint64, e->comm, e->stream);
@@ -266,7 +286,6 @@ int launch_quorum_t(mrq_engine *e, const QuorumArgs &a0, int variant, cudaStream
   return MRQ_OK;
 }
 
-int g_sm_count = 148;
 
 int launch_quorum(mrq_engine *e, const QuorumArgs &a, int variant) {
   int rc = MRQ_E_INVAL;
@@ -310,6 +329,7 @@ int mrq_create(const mrq_config *cfg, mrq_engine **out) {
   if (cfg->self_id > cfg->n_replicas) return fail(nullptr, MRQ_E_INVAL, "self_id %u > n_replicas", cfg->self_id);
   if (cfg->election_tick < 1 || cfg->election_tick > 2047) return fail(nullptr, MRQ_E_INVAL, "election_tick outside 1..2047");
   if (cfg->heartbeat_tick < 1 || cfg->heartbeat_tick > 255) return fail(nullptr, MRQ_E_INVAL, "heartbeat_tick outside 1..255");
+  if (cfg->n_groups >= (1ull << 32)) return fail(nullptr, MRQ_E_INVAL, "n_groups must be below 2^32 per engine (shard across engines)");
   int ndev = 0;
   cudaError_t st = cudaGetDeviceCount(&ndev);
   if (st != cudaSuccess || ndev == 0)
@@ -356,6 +376,8 @@ int mrq_create(const mrq_config *cfg, mrq_engine **out) {
     if ((r = dalloc(e, &e->gathered, gs))) return r;
     if ((r = dalloc(e, &e->pk_base_index, gs))) return r;
     if ((r = dalloc(e, &e->pk_base_term, gs))) return r;
+    if ((r = dalloc(e, &e->slow_list, gs))) return r;
+    if ((r = dalloc(e, &e->slow_count, 2))) return r;
     uint32_t nslots = cfg->inbox_slots ? cfg->inbox_slots : 2;
     e->inbox.resize(nslots);
     for (auto &ib : e->inbox) {
@@ -395,7 +417,7 @@ void mrq_destroy(mrq_engine *e) {
       if (p != e->rank && e->peer_gather[p]) cudaIpcCloseMemHandle(e->peer_gather[p]);
   }
   void *ptrs[] = {e->s.term, e->s.meta, e->s.last_index, e->s.last_term, e->s.committed, e->s.term_start, e->s.match,
-                  e->s.out, e->ctr, e->commit_prev, e->delta, e->gathered, e->scratch, e->pk_base_index, e->pk_base_term};
+                  e->s.out, e->ctr, e->commit_prev, e->delta, e->gathered, e->scratch, e->pk_base_index, e->pk_base_term, e->slow_list, e->slow_count};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (auto &ib : e->inbox) {
@@ -693,6 +715,12 @@ int mrq_quorum_commit(mrq_engine *e) {
   if (e->G == 0) return MRQ_OK;
   QuorumArgs a{e->s.match, e->s.committed, e->s.term_start, e->ctr, e->G, e->gs};
   return launch_quorum(e, a, e->quorum_variant);
+}
+
+int mrq_set_tick_mode(mrq_engine *e, int mode) {
+  if (!e || mode < 0 || mode > 1) return MRQ_E_INVAL;
+  e->tick_mode = mode;
+  return MRQ_OK;
 }
 
 int mrq_set_quorum_variant(mrq_engine *e, int variant) {

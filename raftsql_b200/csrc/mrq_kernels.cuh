@@ -72,6 +72,9 @@ struct TickArgs {
   // fused peer-store gather (multi-GPU mode 1): committed[g] is stored into every rank's gather buffer
   uint64_t *peer_gather[8];
   uint32_t world, rank;
+  // fast/slow split: groups the fast kernel leaves untouched are listed here for the slow kernel
+  uint32_t *slow_list;
+  unsigned *slow_count, *slow_count_next;
 };
 
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------------
@@ -498,15 +501,12 @@ __device__ __forceinline__ void count_events(Counters *c, uint32_t ev) {
   }
 }
 
-// ---- the fused per-tick kernel (a3–a16) ---------------------------------------------------------------
-static constexpr int kTickThreads = 128;  // small CTAs: finer register-file packing (6 x 128 threads at <= 85 regs)
+// ---- the general per-group tick: every message through the full state machine (a3–a16) ------------------
+static constexpr int kTickThreads = 128;
 template <int R>
-__global__ void __launch_bounds__(kTickThreads, (R <= 5 ? 6 : 5)) tick_kernel(const TickArgs a) {
-  pdl_launch_dependents();
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ uint32_t general_group_tick(const TickArgs &a, const uint64_t i) {
   uint32_t ev = 0;
-  pdl_wait();
-  if (i < a.G) {
+  {
     const bool has_inbox = a.in.type != nullptr;
     // phase 1: group state + the tick's message types
     const uint64_t w_meta = ld_state(a.s.meta + i);
@@ -539,41 +539,14 @@ __global__ void __launch_bounds__(kTickThreads, (R <= 5 ? 6 : 5)) tick_kernel(co
       mt[r] = present ? ld_stream(a.in.term + (uint64_t)r * a.gs + i) : 0ull;
       mi[r] = present ? ld_stream(a.in.index + (uint64_t)r * a.gs + i) : 0ull;
     }
-    // Steady state — a leader whose inbox holds nothing but accepted, same-term, in-range MsgAppResp — is
-    // the overwhelmingly common tick.  It needs none of the role machinery: merge the acks (a14), append
-    // the proposals (a5), evaluate the quorum once (a15/a16, see flushCommit), run the leader's timers.
-    // Everything else takes the general per-message path below; both produce identical state.
-    bool fast = g.role == MRQ_ROLE_LEADER && !g.strict && g.ltok;
+    if (g.role != MRQ_ROLE_LEADER) {
 #pragma unroll
-    for (int r = 0; r < R; ++r)
-      fast = fast && (ty[r] == 0u || (ty[r] == MRQ_MSG_APP_RESP && mt[r] == g.term && mi[r] <= g.last_index));
-    if (fast) {
-      bool changed = false;
-#pragma unroll
-      for (int r = 0; r < R; ++r)
-        if (ty[r] != 0u && g.match[r] < mi[r]) {
-          g.match[r] = mi[r];
-          g.dirty |= D_MATCH0 << r;
-          changed = true;
-        }
-      if (nprop) {
-        g.last_index += nprop;
-        g.dirty |= D_LI;
-        g.setSelfMatch(g.last_index);
-        g.out |= MRQ_OUT_BCAST_APPEND;
-        changed = true;
-      }
-      if (changed && g.maybeCommit()) g.out |= MRQ_OUT_BCAST_APPEND;
-    } else {
-      if (g.role != MRQ_ROLE_LEADER) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) g.match[r] = 0ull;  // not a leader: Progress is rebuilt by becomeLeader
-      }
-      // Step every message in sender order, then proposals
-      StepAll<R, 0>::run(g, ty, mt, mi, a.in, a.gs, i);
-      if (nprop) g.propose(nprop);
-      g.flushCommit();
+      for (int r = 0; r < R; ++r) g.match[r] = 0ull;  // not a leader: Progress is rebuilt by becomeLeader
     }
+    // Step every message in sender order, then proposals, then the tick
+    StepAll<R, 0>::run(g, ty, mt, mi, a.in, a.gs, i);
+    if (nprop) g.propose(nprop);
+    g.flushCommit();
     g.tick();
     // write back what changed
     Meta o;
@@ -598,6 +571,180 @@ __global__ void __launch_bounds__(kTickThreads, (R <= 5 ? 6 : 5)) tick_kernel(co
     }
     ev = g.ev;
   }
+  return ev;
+}
+
+// ---- the tick, as two launches ------------------------------------------------------------------------------
+// (1) tick_fast_kernel: one thread per group, for the ticks that need none of the role machinery —
+//       * a leader whose inbox holds nothing but accepted, same-term, in-range MsgAppResp (steady state):
+//         merge the acks (a14), append the proposals (a5), evaluate the quorum once (a15/a16), leader timers;
+//       * a follower that hears nothing, or only a same-term MsgHeartbeat from its leader: election timer,
+//         electionElapsed = 0, commitTo(m.Commit);
+//     lean (no state machine inlined: small code, few registers, high occupancy).  Any other group is left
+//     UNTOUCHED and its index appended to the slow list (one warp-aggregated atomic per warp).
+// (2) tick_slow_kernel: grid-strides over the slow list and runs general_group_tick on each entry.
+// A group is handled by exactly one of the two, and both are exact, so the pair equals the single kernel.
+template <int R>
+__global__ void __launch_bounds__(kTickThreads, (R <= 5 ? 8 : (R == 6 ? 7 : 6))) tick_fast_kernel(const TickArgs a) {
+  pdl_launch_dependents();
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t ev = 0;
+  bool slow = false;
+  pdl_wait();
+  if (i < a.G) {
+    const bool has_inbox = a.in.type != nullptr;
+    // one wave of independent loads: packed small state, the u64 state columns, Progress.Match, message types
+    const uint64_t w_meta = ld_state(a.s.meta + i);
+    const uint64_t term = ld_state(a.s.term + i);
+    uint64_t last_index = ld_state(a.s.last_index + i);
+    uint64_t committed = ld_state(a.s.committed + i);
+    const uint64_t gate = ld_state(a.s.term_start + i);
+    uint32_t ty[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) ty[r] = has_inbox ? ld_stream_u8(a.in.type + (uint64_t)r * a.gs + i) : 0u;
+    const uint32_t nprop = (has_inbox && a.in.prop) ? ld_stream_u32(a.in.prop + i) : 0u;
+    uint64_t match[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) match[r] = ld_state(a.s.match + (uint64_t)r * a.gs + i);
+    Meta m = meta_unpack(w_meta);
+    // second wave: term + (index | commit) of the messages that are present
+    uint64_t mt[R], mx[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if ((uint32_t)(r + 1) == m.self) ty[r] = 0;  // a node does not message itself
+      const bool present = ty[r] != 0u;
+      const uint64_t *px = (ty[r] == MRQ_MSG_HEARTBEAT ? a.in.commit : a.in.index) + (uint64_t)r * a.gs + i;
+      mt[r] = present ? ld_stream(a.in.term + (uint64_t)r * a.gs + i) : 0ull;
+      mx[r] = present ? ld_stream(px) : 0ull;
+    }
+    uint32_t out = 0;
+    uint32_t dirty = 0;
+    if (m.role == MRQ_ROLE_LEADER) {
+      bool ok = !m.strict && m.ltok;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        ok = ok && (ty[r] == 0u || (ty[r] == MRQ_MSG_APP_RESP && mt[r] == term && mx[r] <= last_index));
+      slow = !ok;
+      if (ok) {
+        bool changed = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (ty[r] != 0u && match[r] < mx[r]) {  // Progress.maybeUpdate
+            match[r] = mx[r];
+            dirty |= D_MATCH0 << r;
+            changed = true;
+          }
+        if (nprop) {  // appendEntry: lastTerm already equals Term (ltok), self Match = lastIndex
+          last_index += nprop;
+          dirty |= D_LI;
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if ((uint32_t)(r + 1) == m.self) {
+              match[r] = last_index;
+              dirty |= D_MATCH0 << r;
+            }
+          out |= MRQ_OUT_BCAST_APPEND;
+          changed = true;
+        }
+        if (changed) {  // maybeCommit, once (see Group::flushCommit for why once is exact)
+          const uint64_t mci = quorum_index<R>(match, committed);
+          if (mci > committed && mci >= gate && mci <= last_index) {
+            committed = mci;
+            dirty |= D_COMMIT;
+            out |= MRQ_OUT_COMMIT_ADVANCED | MRQ_OUT_BCAST_APPEND;
+            ev |= Group<R>::EV_COMMIT;
+          }
+        }
+        // tickHeartbeat
+        ++m.hb;
+        ++m.elapsed;
+        if (m.elapsed >= a.election_tick) m.elapsed = 0;
+        if (m.hb >= a.heartbeat_tick) {
+          m.hb = 0;
+          out |= MRQ_OUT_BCAST_HEARTBEAT;
+        }
+      }
+    } else if (m.role == MRQ_ROLE_FOLLOWER) {
+      bool ok = nprop == 0;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        ok = ok && (ty[r] == 0u || (ty[r] == MRQ_MSG_HEARTBEAT && (uint32_t)(r + 1) == m.lead && mt[r] == term &&
+                                    mx[r] <= last_index));
+      // the election timer must not fire this tick (campaign() is the slow path's business)
+      bool heard = false;
+#pragma unroll
+      for (int r = 0; r < R; ++r) heard = heard || ty[r] != 0u;
+      ok = ok && ((heard ? 1u : m.elapsed + 1u) < m.rto);
+      slow = !ok;
+      if (ok) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (ty[r] != 0u) {  // stepFollower MsgHeartbeat: electionElapsed = 0, lead = From, commitTo, reply
+            if (committed < mx[r]) {
+              committed = mx[r];
+              dirty |= D_COMMIT;
+              out |= MRQ_OUT_COMMIT_ADVANCED;
+              ev |= Group<R>::EV_COMMIT;
+            }
+            out |= 1u << (MRQ_OUT_ACK_REPLY_SHIFT + r);
+          }
+        m.elapsed = heard ? 1u : m.elapsed + 1u;  // reset by the heartbeat, then this tick's increment
+      }
+    } else {
+      slow = true;
+    }
+    if (!slow) {
+      const uint64_t w_new = meta_pack(m);
+      if (w_new != w_meta) st_state(a.s.meta + i, w_new);
+      if (dirty & D_LI) st_state(a.s.last_index + i, last_index);
+      if (dirty & D_COMMIT) st_state(a.s.committed + i, committed);
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (dirty & (D_MATCH0 << r)) st_state(a.s.match + (uint64_t)r * a.gs + i, match[r]);
+      st_state_u32(a.s.out + i, out);
+      if (a.world > 1) {  // fused all-gather: store the commit index straight into every rank's buffer
+#pragma unroll 1
+        for (uint32_t p = 0; p < a.world; ++p) a.peer_gather[p][(uint64_t)a.rank * a.G + i] = committed;
+      }
+    }
+  }
+  // hand the groups this kernel did not touch to the slow kernel: one atomic per warp
+  const unsigned smask = __ballot_sync(0xFFFFFFFFu, slow);
+  if (smask != 0) {
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(a.slow_count, (unsigned)__popc(smask));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (slow) a.slow_list[base + __popc(smask & ((1u << lane) - 1u))] = (uint32_t)i;
+  }
+  if (__any_sync(0xFFFFFFFFu, ev != 0)) count_events(a.ctr, ev);
+}
+
+template <int R>
+__global__ void __launch_bounds__(kTickThreads, (R <= 5 ? 6 : 5)) tick_slow_kernel(const TickArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const unsigned n = *a.slow_count;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.slow_count_next = 0;  // the next tick's fast kernel starts from zero
+  // whole warps iterate together so the warp-aggregated event counting stays converged
+  const unsigned stride = gridDim.x * blockDim.x;
+  const unsigned rounds = (n + stride - 1) / stride;
+  unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  for (unsigned it = 0; it < rounds; ++it, k += stride) {
+    uint32_t ev = 0;
+    if (k < n) ev = general_group_tick<R>(a, (uint64_t)a.slow_list[k]);
+    if (__any_sync(0xFFFFFFFFu, ev != 0)) count_events(a.ctr, ev);
+  }
+}
+
+// single-launch form (every group through the general path): kept for differential testing of the pair above
+template <int R>
+__global__ void __launch_bounds__(kTickThreads, (R <= 5 ? 6 : 5)) tick_general_kernel(const TickArgs a) {
+  pdl_launch_dependents();
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_wait();
+  uint32_t ev = 0;
+  if (i < a.G) ev = general_group_tick<R>(a, i);
   if (__any_sync(0xFFFFFFFFu, ev != 0)) count_events(a.ctr, ev);
 }
 

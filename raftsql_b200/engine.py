@@ -192,6 +192,9 @@ class Engine:
     def tick_idle(self, n: int = 1):
         self._ck(self.L.mrq_tick_idle(self.h, n))
 
+    def set_tick_mode(self, mode: int):
+        self._ck(self.L.mrq_set_tick_mode(self.h, mode))
+
     def quorum_commit(self):
         self._ck(self.L.mrq_quorum_commit(self.h))
 

@@ -79,6 +79,63 @@ def test_fixed_self_id_and_group_base():
     run_trace_parity(2048, 3, 2, 150, seed=9, group_base=1 << 33)
 
 
+def _follower_heavy_params():
+    """Leaders get deposed by higher-term heartbeats and then keep hearing from that leader: most groups end
+    up as followers receiving same-term heartbeats (the follower half of the fast kernel)."""
+    p = preset_trace(5)
+    p.churn_65536, p.p_heartbeat_256, p.p_grant_256, p.p_reject_256 = 600, 235, 150, 60
+    return p
+
+
+@pytest.mark.parametrize("R", [3, 5, 7])
+def test_follower_heartbeat_trace(R):
+    G, T = 6000, 260
+    p = _follower_heavy_params()
+    eng, orc = Engine(G, R, seed=41), Oracle(G, R, seed=41)
+    for t in range(T):
+        eng.gen_trace(p, t)
+        ib = eng.read_inbox()
+        eng.tick()
+        orc.tick(ib)
+        if t % 4 == 0 or t == T - 1:
+            assert_state_equal(eng.export_state(), orc.export(), f"tick {t}")
+            np.testing.assert_array_equal(eng.sync_out(), orc.export()["out"])
+    s = orc.export()
+    assert ((s["role"] == 0) & (s["lead"] != 0)).mean() > 0.3  # plenty of followers with a live leader
+    assert eng.counters()["errors"] == 0 and orc.errors == 0
+
+
+@pytest.mark.parametrize("cfg_no,R", [(2, 3), (5, 5), (5, 7), (3, 5)])
+def test_split_launch_equals_single_general_kernel(cfg_no, R):
+    """mrq_set_tick_mode: fast + slow kernels (default) vs one general kernel over every group."""
+    G, T = 20000, 150
+    p = preset_trace(cfg_no) if cfg_no != 3 else _follower_heavy_params()
+    a, b = Engine(G, R, seed=7), Engine(G, R, seed=7)
+    b.set_tick_mode(1)
+    if cfg_no == 3:
+        st = leader_state(G, R, np.random.default_rng(1))
+        a.import_state(st)
+        b.import_state(st)
+    for t in range(T):
+        a.gen_trace(p, t)
+        ib = a.read_inbox()
+        b.post_inbox_dense(ib)
+        a.tick()
+        b.tick()
+        if t % 10 == 0 or t == T - 1:
+            sa, sb = a.export_state(), b.export_state()
+            lead = sa["role"] == LEADER
+            for k in sa:
+                if k == "match":
+                    np.testing.assert_array_equal(sa[k][:, lead], sb[k][:, lead], err_msg=f"tick {t} match")
+                else:
+                    np.testing.assert_array_equal(sa[k], sb[k], err_msg=f"tick {t} {k}")
+            np.testing.assert_array_equal(a.sync_out(), b.sync_out())
+    ca, cb = a.counters(), b.counters()
+    for k in ("campaigns", "elections_won", "step_downs", "commits_advanced", "votes_granted", "errors"):
+        assert ca[k] == cb[k], k
+
+
 def test_zero_groups():
     with Engine(0, 3) as eng:
         eng.tick_idle(3)
