@@ -310,7 +310,7 @@ int mrq_ipc_attach(mrq_engine *e, const uint8_t *handles, uint32_t rank, uint32_
 #define MRQ_PTR_GATHERED 8
 void *mrq_device_ptr(mrq_engine *e, int which);
 void *mrq_stream(mrq_engine *e);
-/* Element stride between replica rows of the device's replica-major arrays (G rounded up to 64). */
+/* Element stride between replica rows of the device's replica-major arrays (G rounded up to 128). */
 uint64_t mrq_group_stride(const mrq_engine *e);
 /* Page-locked host memory for asynchronous posts / drains (cudaHostAlloc / cudaFreeHost). */
 void *mrq_alloc_pinned(size_t bytes);

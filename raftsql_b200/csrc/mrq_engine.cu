@@ -340,8 +340,8 @@ int mrq_create(const mrq_config *cfg, mrq_engine **out) {
   if (!e) return fail(nullptr, MRQ_E_NOMEM, "out of host memory");
   e->cfg = *cfg;
   e->G = cfg->n_groups;
-  e->gs = ((e->G + 63) / 64) * 64;
-  if (e->gs == 0) e->gs = 64;
+  e->gs = ((e->G + 127) / 128) * 128;  // column stride: a multiple of the tick CTA size (kTickThreads)
+  if (e->gs == 0) e->gs = 128;
   e->R = cfg->n_replicas;
   e->device = cfg->device;
   int rc = MRQ_OK;
@@ -370,7 +370,7 @@ int mrq_create(const mrq_config *cfg, mrq_engine **out) {
     if ((r = dalloc(e, &e->s.term_start, gs))) return r;
     if ((r = dalloc(e, &e->s.match, gs * e->R))) return r;
     if ((r = dalloc(e, &e->s.out, gs))) return r;
-    if ((r = dalloc(e, &e->ctr, 1))) return r;
+    if ((r = dalloc(e, &e->ctr, kCtrShards))) return r;
     if ((r = dalloc(e, &e->commit_prev, gs))) return r;
     if ((r = dalloc(e, &e->delta, gs))) return r;
     if ((r = dalloc(e, &e->gathered, gs))) return r;
@@ -812,9 +812,18 @@ int mrq_sync_commit_deltas(mrq_engine *e, uint8_t *delta_out) {
 int mrq_get_counters(mrq_engine *e, mrq_counters *out) {
   if (!e || !out) return MRQ_E_INVAL;
   CK(e, cudaSetDevice(e->device));
-  Counters c;
-  CK(e, cudaMemcpyAsync(&c, e->ctr, sizeof c, cudaMemcpyDeviceToHost, e->stream));
+  Counters shards[kCtrShards];
+  CK(e, cudaMemcpyAsync(shards, e->ctr, sizeof shards, cudaMemcpyDeviceToHost, e->stream));
   CK(e, cudaStreamSynchronize(e->stream));
+  Counters c{};
+  for (int k = 0; k < kCtrShards; ++k) {
+    c.campaigns += shards[k].campaigns;
+    c.elections_won += shards[k].elections_won;
+    c.step_downs += shards[k].step_downs;
+    c.commits_advanced += shards[k].commits_advanced;
+    c.votes_granted += shards[k].votes_granted;
+    c.errors += shards[k].errors;
+  }
   out->ticks = e->tick_no;
   out->kernel_launches = e->launches;
   out->campaigns = c.campaigns;

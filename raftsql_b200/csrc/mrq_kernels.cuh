@@ -60,7 +60,11 @@ struct InboxView {  // one inbox slot, replica-major with stride `gs`
   uint64_t *term, *index, *logterm, *commit;
   uint32_t *prop;
 };
-struct Counters {  // device-side mirror of mrq_counters' event counts
+// Device-side event counts.  Sharded: in steady state every group commits every tick, so one counter would
+// take one same-address atomic per warp (tens of thousands per launch, serialised in one L2 slice).  CTAs
+// spread over kCtrShards copies, each on its own 128-byte line; mrq_get_counters sums them.
+static constexpr int kCtrShards = 64;
+struct alignas(128) Counters {
   unsigned long long campaigns, elections_won, step_downs, commits_advanced, votes_granted, errors;
 };
 struct TickArgs {
@@ -492,7 +496,8 @@ struct StepAll<R, R> {
 };
 
 __device__ __forceinline__ void count_events(Counters *c, uint32_t ev) {
-  // warp-aggregate: one ballot per event class, lane 0 adds the popcount
+  // warp-aggregate: one ballot per event class, lane 0 adds the popcount to this CTA's shard
+  c += blockIdx.x & (kCtrShards - 1);
   const unsigned lane = threadIdx.x & 31u;
 #pragma unroll
   for (int b = 0; b < 6; ++b) {
@@ -591,7 +596,11 @@ __global__ void __launch_bounds__(kTickThreads, (R <= 5 ? 8 : (R == 6 ? 7 : 6)))
   uint32_t ev = 0;
   bool slow = false;
   pdl_wait();
-  if (i < a.G) {
+  // Every lane runs the same straight-line code (columns are padded to a multiple of the CTA size, so the
+  // lanes past G read zero padding); `valid` only gates stores and the slow-list append.  That keeps the
+  // warp collectives below on a full, converged warp.
+  const bool valid = i < a.G;
+  {
     const bool has_inbox = a.in.type != nullptr;
     // one wave of independent loads: packed small state, the u64 state columns, Progress.Match, message types
     const uint64_t w_meta = ld_state(a.s.meta + i);
@@ -693,14 +702,22 @@ __global__ void __launch_bounds__(kTickThreads, (R <= 5 ? 8 : (R == 6 ? 7 : 6)))
     } else {
       slow = true;
     }
-    if (!slow) {
-      const uint64_t w_new = meta_pack(m);
-      if (w_new != w_meta) st_state(a.s.meta + i, w_new);
-      if (dirty & D_LI) st_state(a.s.last_index + i, last_index);
-      if (dirty & D_COMMIT) st_state(a.s.committed + i, committed);
+    // Write-back is decided per WARP, not per lane: if any lane of the warp changed a column, every lane
+    // this kernel owns rewrites it (unchanged lanes store the value they loaded).  Whole 32-byte sectors
+    // are written, so L2 never has to fetch-and-merge partially written sectors from HBM.
+    const uint64_t w_new = meta_pack(m);
+    slow = slow && valid;
+    const bool mine = valid && !slow;
+    if (!mine) ev = 0;
+    uint32_t wdirty = mine ? (dirty | (w_new != w_meta ? D_TERM : 0u)) : 0u;  // D_TERM bit reused: "meta changed"
+    wdirty = __reduce_or_sync(0xFFFFFFFFu, wdirty);
+    if (mine) {
+      if (wdirty & D_TERM) st_state(a.s.meta + i, w_new);
+      if (wdirty & D_LI) st_state(a.s.last_index + i, last_index);
+      if (wdirty & D_COMMIT) st_state(a.s.committed + i, committed);
 #pragma unroll
       for (int r = 0; r < R; ++r)
-        if (dirty & (D_MATCH0 << r)) st_state(a.s.match + (uint64_t)r * a.gs + i, match[r]);
+        if (wdirty & (D_MATCH0 << r)) st_state(a.s.match + (uint64_t)r * a.gs + i, match[r]);
       st_state_u32(a.s.out + i, out);
       if (a.world > 1) {  // fused all-gather: store the commit index straight into every rank's buffer
 #pragma unroll 1
@@ -770,7 +787,8 @@ __device__ __forceinline__ uint64_t quorum_commit_one(const uint64_t (&m)[R], ui
 __device__ __forceinline__ void count_moved(Counters *ctr, unsigned nmoved) {
   if (ctr) {  // warp-shuffle reduction of the "commit advanced" count, one atomic per warp
     const unsigned tot = __reduce_add_sync(0xFFFFFFFFu, nmoved);
-    if (tot != 0 && (threadIdx.x & 31u) == 0) atomicAdd(&ctr->commits_advanced, (unsigned long long)tot);
+    if (tot != 0 && (threadIdx.x & 31u) == 0)
+      atomicAdd(&ctr[blockIdx.x & (kCtrShards - 1)].commits_advanced, (unsigned long long)tot);
   }
 }
 
