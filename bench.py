@@ -409,56 +409,69 @@ def bench_e2e(eng, st0, host_ib, K, W):
     wide = {"value": min(steps, n) / el_w, "h2d_bytes_per_step": sum(a.nbytes for a in host_ib[0].values()),
             "d2h_bytes_per_step": G * 8, "api": "mrq_post_inbox_dense + mrq_tick + mrq_sync_commits"}
 
-    # -- packed form: 4 B per slot from pinned host memory, 1 B per group commit-advance drain ----------
-    base_index = (st0["last_index"] - np.uint64(8192)).astype(np.uint64)
-    base_term = st0["term"].copy()
-    eng.set_packed_base(base_index, base_term)
-    words, props = [], []
-    for ib in host_ib:  # the host's message builder would emit this form directly; encoding is not timed
-        w, p8, esc = pack_inbox(ib, base_index, base_term)
-        assert not esc, "steady-state trace should need no escapes"
-        pw, pp = PinnedArray(w.shape, np.uint32), PinnedArray((G,), np.uint8)
-        pw.array[:] = w
-        pp.array[:] = p8
-        words.append(pw)
-        props.append(pp)
-    delta = PinnedArray((G,), np.uint8)
+    # -- packed forms from pinned host memory, 1 B per group commit-advance drain ---------------------
+    # Per step: H2D of that tick's packed inbox (on the engine's copy stream), the tick, D2H of the
+    # commit advances, host waits for THAT step's result.  The post of tick k+1 is issued while tick k
+    # runs, so the PCIe copy — the bound of this path — overlaps the kernels and the drain.
+    from raftsql_b200.packed import pack_inbox16
+
     L, h = eng.L, eng.h
-    views = []
-    for pw, pp in zip(words, props):
-        v = F.InboxPacked()
-        v.word = C.cast(pw.ptr, F.u32p)
-        v.prop_count8 = C.cast(pp.ptr, F.u8p)
-        v.wide, v.n_wide = None, 0
-        views.append(v)
+    delta = PinnedArray((G,), np.uint8)
     dptr = C.cast(delta.ptr, F.u8p)
+    results, pinned = {}, [delta]
+    for bits, packer, back in ((32, pack_inbox, 8192), (16, pack_inbox16, 1024)):
+        base_index = (st0["last_index"] - np.uint64(back)).astype(np.uint64)
+        base_term = st0["term"].copy()
+        views, h2d = [], 0
+        for ib in host_ib:  # the host's message builder would emit this form directly; encoding is not timed
+            w, p8, esc = packer(ib, base_index, base_term)
+            assert not esc, "steady-state trace should need no escapes"
+            pw, pp = PinnedArray(w.shape, w.dtype), PinnedArray((G,), np.uint8)
+            pw.array[:] = w
+            pp.array[:] = p8
+            pinned += [pw, pp]
+            v = F.InboxPacked()
+            v.word, v.prop_count8 = pw.ptr, C.cast(pp.ptr, F.u8p)
+            v.wide, v.n_wide, v.word_bits = None, 0, bits
+            views.append(v)
+            h2d = int(pw.nbytes + pp.nbytes)
 
-    def run_packed(nsteps, accumulate):
-        eng.import_state(st0)
-        eng.tick_count = 0
-        eng.sync_commit_deltas()  # rebase the drain on the imported state
-        base = eng.sync_commits().copy()
-        acc = np.zeros(G, np.uint64)
-        t0 = time.perf_counter()
-        for k in range(nsteps):
-            rc = L.mrq_post_inbox_packed(h, k % 2, C.byref(views[k % n]))
-            rc |= L.mrq_tick(h, k % 2)
-            rc |= L.mrq_sync_commit_deltas(h, dptr)  # blocking: the step's result is on the host
-            assert rc == 0
-            if accumulate:  # reconstruct commit indices from the per-tick advances (checking run only)
-                assert delta.array.max() < 255
-                acc += delta.array
-        return time.perf_counter() - t0, base + acc
+        def run_packed(nsteps, accumulate):
+            eng.import_state(st0)
+            eng.tick_count = 0
+            eng.set_packed_base(base_index, base_term)
+            base = eng.sync_commits().copy()  # a full read also rebases the delta drain
+            acc = np.zeros(G, np.uint64)
+            t0 = time.perf_counter()
+            rc = L.mrq_post_inbox_packed(h, 0, C.byref(views[0]))
+            for k in range(nsteps):
+                rc |= L.mrq_tick(h, k % 2)
+                rc |= L.mrq_drain_commit_deltas(h, dptr)
+                if k + 1 < nsteps:  # next tick's inbox starts copying underneath this tick
+                    rc |= L.mrq_post_inbox_packed(h, (k + 1) % 2, C.byref(views[(k + 1) % n]))
+                rc |= L.mrq_drain_wait(h)  # this step's result is on the host
+                assert rc == 0
+                if accumulate:  # reconstruct commit indices from the per-tick advances (checking run only)
+                    assert delta.array.max() < 255
+                    acc += delta.array
+            el = time.perf_counter() - t0
+            eng.synchronize()
+            return el, base + acc
 
-    run_packed(3, False)
-    _, commits_check = run_packed(min(steps, n), True)
-    same = bool(np.array_equal(commits_check, commits_wide)) and bool(np.array_equal(commits_check, eng.sync_commits()))
-    el_p, _ = run_packed(steps, False)
-    res = {"value": steps / el_p, "unit": "ticks/s", "h2d_bytes_per_step": int(words[0].nbytes + props[0].nbytes),
-           "d2h_bytes_per_step": int(delta.nbytes), "steps": steps,
-           "api": "mrq_post_inbox_packed (pinned, 4 B/slot) + mrq_tick + mrq_sync_commit_deltas (1 B/group)",
-           "packed_equals_wide": same, "wide_form": wide}
-    for a in words + props + [delta]:
+        run_packed(3, False)
+        _, commits_check = run_packed(min(steps, n), True)
+        same = bool(np.array_equal(commits_check, commits_wide)) and bool(np.array_equal(commits_check, eng.sync_commits()))
+        el_p, _ = run_packed(steps, False)
+        results[bits] = {"value": steps / el_p, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(delta.nbytes),
+                         "equals_wide_form": same, "h2d_GBps": h2d * steps / el_p / 1e9}
+    best = max(results, key=lambda b: results[b]["value"])
+    res = {"value": results[best]["value"], "unit": "ticks/s", "h2d_bytes_per_step": results[best]["h2d_bytes_per_step"],
+           "d2h_bytes_per_step": results[best]["d2h_bytes_per_step"], "steps": steps,
+           "api": f"mrq_post_inbox_packed (pinned, {best}-bit words, copy stream) + mrq_tick + "
+                  "mrq_drain_commit_deltas/mrq_drain_wait (1 B/group)",
+           "packed_equals_wide": all(r["equals_wide_form"] for r in results.values()),
+           "packed32": results[32], "packed16": results[16], "wide_form": wide}
+    for a in pinned:
         a.free()
     return res
 

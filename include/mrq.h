@@ -187,12 +187,24 @@ int mrq_post_inbox_delta(mrq_engine *e, uint32_t slot, const mrq_msg *msgs, size
  *        MSG_VOTE          logterm = base_term[g] + (p & 3), index = base_index[g] + (p >> 2)
  *        MSG_VOTE_RESP / MSG_HEARTBEAT_RESP   p unused
  *        MSG_APP           always escaped (needs three 64-bit fields)
- * Escaped / wide messages ride in `wide` (n_wide entries) and override their slot.            */
+ * Escaped / wide messages ride in `wide` (n_wide entries) and override their slot.
+ *
+ * 16-bit form (word_bits = 16; `word` then points at uint16_t[R][G]): bits 0..2 kind (0 none, 1 ack,
+ * 2 ack|REJECT, 3 vote-resp grant, 4 vote-resp REJECT, 5 heartbeat, 6 heartbeat-resp, 7 escaped),
+ * bits 3..4 term code as above, bits 5..15 payload p (ack index / heartbeat commit = base_index[g] + p).
+ * MSG_VOTE and MSG_APP always escape.
+ *
+ * ASYNCHRONOUS: the copies run on the engine's copy stream so that the next tick's H2D overlaps the
+ * current tick; `word`, `prop_count8` and `wide` should be page-locked (mrq_alloc_pinned) and must stay
+ * valid and unmodified until a blocking call (mrq_sync_* / mrq_synchronize) made after the mrq_tick
+ * that consumes the slot has returned.                                                         */
 typedef struct mrq_inbox_packed {
-  const uint32_t *word;       /* [R][G] */
+  const void *word;           /* [R][G] uint32_t (word_bits 32 or 0) or uint16_t (word_bits 16) */
   const uint8_t *prop_count8; /* [G] proposals (0..255) or NULL */
   const mrq_msg *wide;        /* escape list */
   size_t n_wide;
+  uint32_t word_bits;         /* 0 or 32: 32-bit words; 16: 16-bit words */
+  uint32_t reserved;
 } mrq_inbox_packed;
 int mrq_post_inbox_packed(mrq_engine *e, uint32_t slot, const mrq_inbox_packed *in);
 /* Dense [G] decode bases for the packed form (NULL keeps the current column).  Blocking. */
@@ -248,6 +260,11 @@ int mrq_sync_out(mrq_engine *e, uint32_t *out_words);
  * drain, saturated to 255 in a byte.  255 means "read the full value": mrq_sync_commits with a
  * non-NULL committed_out rebases every group's drain to the values it returns.                 */
 int mrq_sync_commit_deltas(mrq_engine *e, uint8_t *delta_out);
+/* The same drain, split for pipelining hosts: mrq_drain_commit_deltas enqueues it (the destination must
+ * be page-locked) and returns; mrq_drain_wait blocks until THAT drain has landed — not until the stream
+ * is idle, so an mrq_post_inbox_packed issued in between keeps copying underneath.             */
+int mrq_drain_commit_deltas(mrq_engine *e, uint8_t *delta_out_pinned);
+int mrq_drain_wait(mrq_engine *e);
 int mrq_synchronize(mrq_engine *e);
 
 /* ---- synthetic vote/append traces, generated on the device (include/mrq_trace.h) -------- */

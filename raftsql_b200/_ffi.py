@@ -77,7 +77,8 @@ class Msg(C.Structure):
 
 
 class InboxPacked(C.Structure):
-    _fields_ = [("word", u32p), ("prop_count8", u8p), ("wide", C.POINTER(Msg)), ("n_wide", C.c_size_t)]
+    _fields_ = [("word", C.c_void_p), ("prop_count8", u8p), ("wide", C.POINTER(Msg)), ("n_wide", C.c_size_t),
+                ("word_bits", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class TraceParams(C.Structure):
@@ -122,6 +123,8 @@ SIGNATURES = {
     "mrq_sync_commits": (C.c_int, [_EP, u64p, u8p, u64p]),
     "mrq_sync_out": (C.c_int, [_EP, u32p]),
     "mrq_sync_commit_deltas": (C.c_int, [_EP, u8p]),
+    "mrq_drain_commit_deltas": (C.c_int, [_EP, u8p]),
+    "mrq_drain_wait": (C.c_int, [_EP]),
     "mrq_synchronize": (C.c_int, [_EP]),
     "mrq_gen_trace": (C.c_int, [_EP, C.c_uint32, C.POINTER(TraceParams), C.c_uint64]),
     "mrq_read_inbox": (C.c_int, [_EP, C.c_uint32, C.POINTER(InboxOut)]),

@@ -58,6 +58,13 @@ struct NcclApi {
 NcclApi g_nccl;
 constexpr int kNcclUint64 = 5;  // ncclDataType_t::ncclUint64
 
+struct PackedStage {
+  void *buf = nullptr;
+  size_t bytes = 0;
+  cudaEvent_t copied = nullptr, consumed = nullptr;
+  bool used = false;
+};
+
 struct InboxBuf {
   uint8_t *type = nullptr;
   uint64_t *term = nullptr, *index = nullptr, *logterm = nullptr, *commit = nullptr;
@@ -81,6 +88,9 @@ struct mrq_engine {
   uint8_t *delta = nullptr;
   uint64_t *gathered = nullptr;     // [world * G]
   uint64_t *pk_base_index = nullptr, *pk_base_term = nullptr;  // packed-inbox decode bases
+  cudaEvent_t drain_done = nullptr;    // mrq_drain_commit_deltas / mrq_drain_wait
+  cudaStream_t copy_stream = nullptr;  // H2D of packed inboxes, overlapped with the tick stream
+  std::vector<PackedStage> pk_stage;   // one staging buffer per inbox slot
   uint32_t *slow_list = nullptr;    // [gs] groups left to the slow kernel this tick
   unsigned *slow_count = nullptr;   // [2] double-buffered list length
   uint32_t slow_parity = 0;
@@ -411,6 +421,16 @@ void mrq_destroy(mrq_engine *e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->drain_done) cudaEventDestroy(e->drain_done);
+  if (e->copy_stream) {
+    cudaStreamSynchronize(e->copy_stream);
+    cudaStreamDestroy(e->copy_stream);
+  }
+  for (auto &sg : e->pk_stage) {
+    if (sg.buf) cudaFree(sg.buf);
+    if (sg.copied) cudaEventDestroy(sg.copied);
+    if (sg.consumed) cudaEventDestroy(sg.consumed);
+  }
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
   if (e->ipc_attached) {
     for (uint32_t p = 0; p < e->world; ++p)
@@ -613,24 +633,57 @@ int mrq_post_inbox_packed(mrq_engine *e, uint32_t slot, const mrq_inbox_packed *
   if (!in || !in->word) return fail(e, MRQ_E_INVAL, "null packed inbox");
   CK(e, cudaSetDevice(e->device));
   if (e->G == 0) return MRQ_OK;
-  const size_t wbytes = e->gs * e->R * 4, pbytes = e->gs, xbytes = in->n_wide * sizeof(mrq_msg);
-  if ((r = ensure_scratch(e, wbytes + pbytes + xbytes + 256))) return r;
-  uint32_t *d_word = (uint32_t *)e->scratch;
-  uint8_t *d_prop = (uint8_t *)e->scratch + wbytes;
-  MsgRec *d_wide = (MsgRec *)((uint8_t *)e->scratch + wbytes + ((pbytes + 63) / 64) * 64);
-  CK(e, cudaMemcpy2DAsync(d_word, e->gs * 4, in->word, e->G * 4, e->G * 4, e->R, cudaMemcpyHostToDevice, e->stream));
-  if (in->prop_count8) CK(e, cudaMemcpyAsync(d_prop, in->prop_count8, e->G, cudaMemcpyHostToDevice, e->stream));
-  unpack_inbox_kernel<<<nblocks(e->G), 256, 0, e->stream>>>(e->inbox[slot].view(), e->pk_base_index, e->pk_base_term, e->gs,
-                                                          e->G, e->R, d_word, in->prop_count8 ? d_prop : nullptr);
+  const uint32_t bits = in->word_bits ? in->word_bits : 32u;
+  if (bits != 16u && bits != 32u) return fail(e, MRQ_E_INVAL, "word_bits must be 16 or 32");
+  if (in->n_wide && !in->wide) return fail(e, MRQ_E_INVAL, "n_wide > 0 but wide == NULL");
+  const size_t wsz = bits / 8;
+  const size_t wbytes = ((e->gs * e->R * wsz + 255) / 256) * 256, pbytes = ((e->gs + 255) / 256) * 256;
+  const size_t xbytes = in->n_wide * sizeof(mrq_msg);
+  // The copy runs on its own stream into a per-slot staging buffer, so the H2D of the NEXT tick's inbox
+  // overlaps this tick's kernels and drain; events order copy -> unpack (main stream) -> reuse of the stage.
+  if (e->pk_stage.size() < e->inbox.size()) e->pk_stage.resize(e->inbox.size());
+  PackedStage &sg = e->pk_stage[slot];
+  if (!e->copy_stream) CK(e, cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  if (!sg.copied) {
+    CK(e, cudaEventCreateWithFlags(&sg.copied, cudaEventDisableTiming));
+    CK(e, cudaEventCreateWithFlags(&sg.consumed, cudaEventDisableTiming));
+  }
+  const size_t need = wbytes + pbytes + xbytes + 256;
+  if (need > sg.bytes) {
+    CK(e, cudaStreamSynchronize(e->stream));
+    CK(e, cudaStreamSynchronize(e->copy_stream));
+    if (sg.buf) CK(e, cudaFree(sg.buf));
+    sg.buf = nullptr;
+    sg.bytes = 0;
+    CK(e, cudaMalloc(&sg.buf, need + (1u << 16)));
+    sg.bytes = need + (1u << 16);
+    sg.used = false;
+  }
+  uint8_t *d_word = (uint8_t *)sg.buf;
+  uint8_t *d_prop = d_word + wbytes;
+  MsgRec *d_wide = (MsgRec *)(d_word + wbytes + pbytes);
+  if (sg.used) CK(e, cudaStreamWaitEvent(e->copy_stream, sg.consumed, 0));
+  CK(e, cudaMemcpy2DAsync(d_word, e->gs * wsz, in->word, e->G * wsz, e->G * wsz, e->R, cudaMemcpyHostToDevice, e->copy_stream));
+  if (in->prop_count8) CK(e, cudaMemcpyAsync(d_prop, in->prop_count8, e->G, cudaMemcpyHostToDevice, e->copy_stream));
+  if (in->n_wide) CK(e, cudaMemcpyAsync(d_wide, in->wide, xbytes, cudaMemcpyHostToDevice, e->copy_stream));
+  CK(e, cudaEventRecord(sg.copied, e->copy_stream));
+  CK(e, cudaStreamWaitEvent(e->stream, sg.copied, 0));
+  if (bits == 32u) {
+    unpack_inbox_kernel<<<nblocks(e->G), 256, 0, e->stream>>>(e->inbox[slot].view(), e->pk_base_index, e->pk_base_term, e->gs,
+                                                            e->G, e->R, (const uint32_t *)d_word, in->prop_count8 ? d_prop : nullptr);
+  } else {
+    unpack16_inbox_kernel<<<nblocks(e->G), 256, 0, e->stream>>>(e->inbox[slot].view(), e->pk_base_index, e->pk_base_term, e->gs,
+                                                              e->G, e->R, (const uint16_t *)d_word, in->prop_count8 ? d_prop : nullptr);
+  }
   CK(e, cudaGetLastError());
   e->launches++;
   if (in->n_wide) {
-    if (!in->wide) return fail(e, MRQ_E_INVAL, "n_wide > 0 but wide == NULL");
-    CK(e, cudaMemcpyAsync(d_wide, in->wide, xbytes, cudaMemcpyHostToDevice, e->stream));
     scatter_msgs_kernel<<<nblocks(in->n_wide), 256, 0, e->stream>>>(e->inbox[slot].view(), e->gs, e->G, e->R, d_wide, in->n_wide);
     CK(e, cudaGetLastError());
     e->launches++;
   }
+  CK(e, cudaEventRecord(sg.consumed, e->stream));
+  sg.used = true;
   return MRQ_OK;
 }
 
@@ -806,6 +859,28 @@ int mrq_sync_commit_deltas(mrq_engine *e, uint8_t *delta_out) {
   e->launches++;
   CK(e, cudaMemcpyAsync(delta_out, e->delta, e->G, cudaMemcpyDeviceToHost, e->stream));
   CK(e, cudaStreamSynchronize(e->stream));
+  return MRQ_OK;
+}
+
+int mrq_drain_commit_deltas(mrq_engine *e, uint8_t *delta_out_pinned) {
+  if (!e || !delta_out_pinned) return MRQ_E_INVAL;
+  CK(e, cudaSetDevice(e->device));
+  if (!e->drain_done) CK(e, cudaEventCreateWithFlags(&e->drain_done, cudaEventDisableTiming));
+  if (e->G) {
+    commit_delta_kernel<<<nblocks(e->G), 256, 0, e->stream>>>(e->s.committed, e->commit_prev, e->delta, e->G);
+    CK(e, cudaGetLastError());
+    e->launches++;
+    CK(e, cudaMemcpyAsync(delta_out_pinned, e->delta, e->G, cudaMemcpyDeviceToHost, e->stream));
+  }
+  CK(e, cudaEventRecord(e->drain_done, e->stream));
+  return MRQ_OK;
+}
+
+int mrq_drain_wait(mrq_engine *e) {
+  if (!e) return MRQ_E_INVAL;
+  if (!e->drain_done) return fail(e, MRQ_E_STATE, "mrq_drain_wait without mrq_drain_commit_deltas");
+  CK(e, cudaSetDevice(e->device));
+  CK(e, cudaEventSynchronize(e->drain_done));
   return MRQ_OK;
 }
 

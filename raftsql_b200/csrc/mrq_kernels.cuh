@@ -1053,18 +1053,54 @@ __global__ void __launch_bounds__(256) unpack_inbox_kernel(InboxView in, const u
     }
     in.type[o] = (uint8_t)(type | ((w & 16u) ? MRQ_MSG_REJECT : 0u));
     in.term[o] = bt + tc;
-    uint64_t index = 0, logterm = 0, commit = 0;
+    // only the columns Step() reads for this type are written (index: acks/votes; commit: heartbeats)
     if (type == MRQ_MSG_APP_RESP) {
-      index = bi + pay;
+      in.index[o] = bi + pay;
     } else if (type == MRQ_MSG_HEARTBEAT) {
-      commit = bi + pay;
+      in.commit[o] = bi + pay;
     } else if (type == MRQ_MSG_VOTE) {  // payload: bits 0..1 logterm - base_term, bits 2..24 index - base_index
-      logterm = bt + (pay & 3u);
-      index = bi + (pay >> 2);
+      in.logterm[o] = bt + (pay & 3u);
+      in.index[o] = bi + (pay >> 2);
+    } else {
+      in.index[o] = 0;
     }
-    in.index[o] = index;
-    in.logterm[o] = logterm;
-    in.commit[o] = commit;
+  }
+  if (in.prop) in.prop[i] = prop8 ? prop8[i] : 0u;
+}
+
+// 16-bit form: bits 0..2 kind (0 none, 1 ack, 2 ack|reject, 3 vote-resp grant, 4 vote-resp reject,
+// 5 heartbeat, 6 heartbeat-resp, 7 escaped), bits 3..4 term code (term = base_term + c, c in 0..2; 3 = escaped),
+// bits 5..15 payload p: ack index / heartbeat commit = base_index + p.  MsgVote / MsgApp always escape.
+__global__ void __launch_bounds__(256) unpack16_inbox_kernel(InboxView in, const uint64_t *base_index,
+                                                              const uint64_t *base_term, uint64_t gs, uint64_t G,
+                                                              uint32_t R, const uint16_t *word, const uint8_t *prop8) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G) return;
+  const uint64_t bi = base_index[i], bt = base_term[i];
+  for (uint32_t r = 0; r < R; ++r) {
+    const uint64_t o = (uint64_t)r * gs + i;
+    const uint32_t w = word[o];
+    const uint32_t kind = w & 7u;
+    const uint32_t tc = (w >> 3) & 3u;
+    const uint64_t pay = w >> 5;
+    if (kind == 0 || kind == 7u || tc == 3u) {
+      in.type[o] = 0;
+      continue;
+    }
+    in.term[o] = bt + tc;
+    if (kind <= 2u) {
+      in.type[o] = (uint8_t)(MRQ_MSG_APP_RESP | (kind == 2u ? MRQ_MSG_REJECT : 0u));
+      in.index[o] = bi + pay;
+    } else if (kind <= 4u) {
+      in.type[o] = (uint8_t)(MRQ_MSG_VOTE_RESP | (kind == 4u ? MRQ_MSG_REJECT : 0u));
+      in.index[o] = 0;
+    } else if (kind == 5u) {
+      in.type[o] = MRQ_MSG_HEARTBEAT;
+      in.commit[o] = bi + pay;
+    } else {
+      in.type[o] = MRQ_MSG_HEARTBEAT_RESP;
+      in.index[o] = 0;
+    }
   }
   if (in.prop) in.prop[i] = prop8 ? prop8[i] : 0u;
 }

@@ -153,8 +153,13 @@ class Engine:
         self._ck(self.L.mrq_post_inbox_delta(self.h, slot, arr, len(msgs), int(accumulate)))
 
     def post_inbox_packed(self, word: np.ndarray, prop8: np.ndarray | None = None, wide=(), slot: int = 0):
+        """word: uint32 or uint16 [R][G] (raftsql_b200.packed.pack_inbox / pack_inbox16).  The copy is
+        asynchronous: this convenience wrapper synchronises before returning so numpy temporaries are safe;
+        hosts that pipeline call mrq_post_inbox_packed directly with pinned buffers (see bench.py)."""
+        assert word.dtype in (np.uint32, np.uint16) and word.flags["C_CONTIGUOUS"]
         v = F.InboxPacked()
-        v.word, v.prop_count8 = _p(word, F.u32p), _p(prop8, F.u8p)
+        v.word, v.prop_count8 = word.ctypes.data, _p(prop8, F.u8p)
+        v.word_bits = 16 if word.dtype == np.uint16 else 32
         arr = (F.Msg * max(1, len(wide)))()
         for i, m in enumerate(wide):
             g, frm, ty, term, index, logterm, commit = m
@@ -162,6 +167,7 @@ class Engine:
             arr[i].term, arr[i].index, arr[i].logterm, arr[i].commit = term, index, logterm, commit
         v.wide, v.n_wide = arr, len(wide)
         self._ck(self.L.mrq_post_inbox_packed(self.h, slot, C.byref(v)))
+        self.synchronize()
 
     def set_packed_base(self, base_index: np.ndarray | None, base_term: np.ndarray | None):
         self._ck(self.L.mrq_set_packed_base(self.h, _p(base_index, F.u64p), _p(base_term, F.u64p)))

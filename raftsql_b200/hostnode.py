@@ -200,6 +200,7 @@ class HostNode:
         self.inflight: list[bytes] = []      # proposals posted to the engine this tick
         self.next = [1] * (npeers + 1)       # Progress.Next per peer id (leader only)
         self.behind: set[int] = set()        # peers whose heartbeat response showed Match < lastIndex
+        self.backlog: list[Message] = []     # inbound messages deferred to the next tick (one per sender per tick)
         self.applied = 0                     # highest index handed to the commit stream
         self.term = self.vote = self.commit = 0
         self.role, self.lead = F.ROLE_FOLLOWER, 0
@@ -235,12 +236,21 @@ class HostNode:
     def step_tick(self) -> list[bytes]:
         """Inbound messages -> engine inbox; proposals; one engine tick; Ready handling.  Returns the payloads
         newly committed by this tick, in log order (what goes to commitC)."""
-        inbound = self.tr.drain(self.id)
+        inbound = self.backlog + self.tr.drain(self.id)
+        self.backlog = []
         eng_msgs, app_replies = [], {}
+        seen_from: set[int] = set()
         for m in inbound:
             if m.type == MsgProp:  # a follower forwarded client proposals to us
                 self.pending.extend(d for (_, d) in m.entries)
                 continue
+            # the engine inbox holds ONE message per sender per tick (include/mrq.h): a second message
+            # from the same peer (say MsgApp then MsgHeartbeat when two of its ticks land in one of ours)
+            # waits for the next tick, in order
+            if m.frm in seen_from:
+                self.backlog.append(m)
+                continue
+            seen_from.add(m.frm)
             if m.type == F.MSG_APP:
                 rec = self._resolve_append(m, app_replies)
                 if rec is not None:

@@ -58,6 +58,46 @@ def pack_inbox(ib: dict, base_index: np.ndarray, base_term: np.ndarray):
     return np.ascontiguousarray(word), prop8, wide
 
 
+PAYLOAD16_MAX = (1 << 11) - 1
+
+
+def pack_inbox16(ib: dict, base_index: np.ndarray, base_term: np.ndarray):
+    """The 2-byte-per-slot form (include/mrq.h, word_bits = 16): acks, vote responses, heartbeats and
+    heartbeat responses within 2047 of the base; MsgVote, MsgApp and anything out of range escape."""
+    ty = ib["type"]
+    Rr, G = ty.shape
+    kind = (ty & F.MSG_TYPE_MASK).astype(np.uint32)
+    rej = (ty & F.MSG_REJECT) != 0
+    bt, bi = base_term[None, :], base_index[None, :]
+    term, index, commit = ib["term"], ib["index"], ib["commit"]
+    present = kind != 0
+    tc = term - bt
+    is_ack, is_vr = kind == F.MSG_APP_RESP, kind == F.MSG_VOTE_RESP
+    is_hb, is_hr = kind == F.MSG_HEARTBEAT, kind == F.MSG_HEARTBEAT_RESP
+    d_idx, d_cm = index - bi, commit - bi
+    ok = present & (tc <= np.uint64(2)) & (is_ack | is_vr | is_hb | is_hr)
+    ok &= ~(is_ack & (d_idx > np.uint64(PAYLOAD16_MAX)))
+    ok &= ~(is_hb & (d_cm > np.uint64(PAYLOAD16_MAX)))
+    code = np.zeros((Rr, G), np.uint32)
+    code = np.where(is_ack, np.where(rej, 2, 1), code)
+    code = np.where(is_vr, np.where(rej, 4, 3), code)
+    code = np.where(is_hb, 5, code)
+    code = np.where(is_hr, 6, code)
+    pay = np.where(is_ack, d_idx, np.where(is_hb, d_cm, 0)).astype(np.uint32)
+    word = np.where(ok, code | (tc.astype(np.uint32) << 3) | (pay << 5), 0)
+    esc = present & ~ok
+    word = np.where(esc, 7, word).astype(np.uint16)
+    wide = [(int(g), int(r) + 1, int(ty[r, g]), int(term[r, g]), int(index[r, g]), int(ib["logterm"][r, g]),
+             int(commit[r, g])) for r, g in zip(*np.nonzero(esc))]
+    prop = ib.get("prop_count")
+    prop8 = None
+    if prop is not None:
+        if prop.max(initial=0) > 255:
+            raise ValueError("packed inbox carries at most 255 proposals per group per tick")
+        prop8 = prop.astype(np.uint8)
+    return np.ascontiguousarray(word), prop8, wide
+
+
 class PinnedArray:
     """A numpy array over page-locked host memory from mrq_alloc_pinned (asynchronous H2D / D2H)."""
 
