@@ -223,6 +223,10 @@ int mrq_clear_inbox(mrq_engine *e, uint32_t slot);
  * engine stream.  The fused sm_100a kernel covers SURVEY §8a rows a3–a16.  If a communicator is
  * attached (mrq_comm_init), the tick also all-gathers committed[] across ranks.               */
 int mrq_tick(mrq_engine *e, uint32_t slot);
+/* n ticks in one call, tick k consuming inbox slot slots[k].  The launch sequence for a slot list is
+ * captured into a CUDA graph on first use and replayed afterwards (launch-bound regimes: small shards,
+ * many GPUs).  Same results as n mrq_tick calls.                                               */
+int mrq_tick_many(mrq_engine *e, const uint32_t *slots, uint32_t n);
 /* n ticks with an empty inbox (timers only). */
 int mrq_tick_idle(mrq_engine *e, uint32_t n);
 /* How mrq_tick is launched: 0 (default) = a lean fast kernel for the ticks that need no role machinery

@@ -114,6 +114,7 @@ SIGNATURES = {
     "mrq_propose": (C.c_int, [_EP, C.c_uint32, u64p, u32p, C.c_size_t]),
     "mrq_clear_inbox": (C.c_int, [_EP, C.c_uint32]),
     "mrq_tick": (C.c_int, [_EP, C.c_uint32]),
+    "mrq_tick_many": (C.c_int, [_EP, u32p, C.c_uint32]),
     "mrq_tick_idle": (C.c_int, [_EP, C.c_uint32]),
     "mrq_set_tick_mode": (C.c_int, [_EP, C.c_int]),
     "mrq_quorum_commit": (C.c_int, [_EP]),

@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
 #include <string>
 #include <vector>
 
@@ -94,6 +95,11 @@ struct mrq_engine {
   uint32_t *slow_list = nullptr;    // [gs] groups left to the slow kernel this tick
   unsigned *slow_count = nullptr;   // [2] double-buffered list length
   uint32_t slow_parity = 0;
+  uint64_t *tickbuf = nullptr;      // [2] device-resident tick number (current / next), see TickArgs
+  uint32_t tick_parity = 0;
+  bool gather_prime = false;        // next tick stores the high words of every commit index to the peers
+  bool graphs_disabled = false;
+  std::map<std::string, cudaGraphExec_t> graphs;  // mrq_tick_many: one executable graph per slot sequence
   int tick_mode = 0;                // 0 = fast + slow kernels, 1 = single general kernel
   uint64_t tick_no = 0;
   uint64_t launches = 0;
@@ -217,12 +223,19 @@ int launch_tick(mrq_engine *e, const InboxBuf *ib) {
   a.gs = e->gs;
   a.group_base = e->cfg.group_base;
   a.seed = e->cfg.seed;
-  a.tick_no = e->tick_no;
+  a.tick_cur = e->tickbuf + (e->tick_parity & 1u);
+  a.tick_next = e->tickbuf + ((e->tick_parity + 1u) & 1u);
   a.election_tick = e->cfg.election_tick;
   a.heartbeat_tick = e->cfg.heartbeat_tick;
   a.world = (e->comm_mode == 1 && e->ipc_attached) ? e->world : 1;
   a.rank = e->rank;
-  for (int p = 0; p < 8; ++p) a.peer_gather[p] = e->peer_gather[p];
+  a.gather_prime = e->gather_prime ? 1u : 0u;
+  for (uint32_t p = 0; p < 8; ++p) {
+    a.peer_lo[p] = reinterpret_cast<uint32_t *>(e->peer_gather[p]);
+    a.peer_hi[p] = a.peer_lo[p] ? a.peer_lo[p] + (size_t)e->world * e->G : nullptr;
+  }
+  if (a.world > 1) e->gather_prime = false;
+  e->tick_parity ^= 1u;
   a.slow_list = e->slow_list;
   a.slow_count = e->slow_count + (e->slow_parity & 1u);
   a.slow_count_next = e->slow_count + ((e->slow_parity + 1u) & 1u);
@@ -388,6 +401,7 @@ int mrq_create(const mrq_config *cfg, mrq_engine **out) {
     if ((r = dalloc(e, &e->pk_base_term, gs))) return r;
     if ((r = dalloc(e, &e->slow_list, gs))) return r;
     if ((r = dalloc(e, &e->slow_count, 2))) return r;
+    if ((r = dalloc(e, &e->tickbuf, 2))) return r;
     uint32_t nslots = cfg->inbox_slots ? cfg->inbox_slots : 2;
     e->inbox.resize(nslots);
     for (auto &ib : e->inbox) {
@@ -437,7 +451,8 @@ void mrq_destroy(mrq_engine *e) {
       if (p != e->rank && e->peer_gather[p]) cudaIpcCloseMemHandle(e->peer_gather[p]);
   }
   void *ptrs[] = {e->s.term, e->s.meta, e->s.last_index, e->s.last_term, e->s.committed, e->s.term_start, e->s.match,
-                  e->s.out, e->ctr, e->commit_prev, e->delta, e->gathered, e->scratch, e->pk_base_index, e->pk_base_term, e->slow_list, e->slow_count};
+                  e->s.out, e->ctr, e->commit_prev, e->delta, e->gathered, e->scratch, e->pk_base_index, e->pk_base_term, e->slow_list, e->slow_count, e->tickbuf};
+  for (auto &kv : e->graphs) cudaGraphExecDestroy(kv.second);
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (auto &ib : e->inbox) {
@@ -455,7 +470,15 @@ void mrq_destroy(mrq_engine *e) {
 uint64_t mrq_tick_count(const mrq_engine *e) { return e ? e->tick_no : 0; }
 int mrq_set_tick_count(mrq_engine *e, uint64_t t) {
   if (!e) return MRQ_E_INVAL;
+  CK(e, cudaSetDevice(e->device));
   e->tick_no = t;
+  // also normalise the double-buffer parities, so that a slot sequence replayed after a rewind hits the
+  // same captured graph (mrq_tick_many keys its graphs by parity)
+  e->tick_parity = 0;
+  e->slow_parity = 0;
+  CK(e, cudaMemcpyAsync(e->tickbuf, &e->tick_no, 8, cudaMemcpyHostToDevice, e->stream));
+  CK(e, cudaMemsetAsync(e->slow_count, 0, 2 * sizeof(unsigned), e->stream));
+  CK(e, cudaStreamSynchronize(e->stream));
   return MRQ_OK;
 }
 void *mrq_stream(mrq_engine *e) { return e ? (void *)e->stream : nullptr; }
@@ -752,6 +775,71 @@ int mrq_tick(mrq_engine *e, uint32_t slot) {
   return launch_tick(e, &e->inbox[slot]);
 }
 
+// n ticks in one call.  The launch sequence for a given slot list is captured once into a CUDA graph (the
+// tick number and the slow-list length live in device memory, double-buffered by tick parity, so a replay
+// needs no per-launch host arguments) and replayed afterwards: the per-tick host cost drops from two
+// cudaLaunchKernelEx calls to a fraction of one graph launch.
+int mrq_tick_many(mrq_engine *e, const uint32_t *slots, uint32_t n) {
+  if (!e) return MRQ_E_INVAL;
+  if (n == 0) return MRQ_OK;
+  if (!slots) return fail(e, MRQ_E_INVAL, "null slot list");
+  for (uint32_t k = 0; k < n; ++k) {
+    int r = check_slot(e, slots[k]);
+    if (r) return r;
+  }
+  CK(e, cudaSetDevice(e->device));
+  const bool nccl_gather = e->world > 1 && e->comm_mode == 0 && e->comm;
+  const bool can_graph = n >= 2 && !e->graphs_disabled && !nccl_gather && !e->gather_prime && e->G > 0;
+  if (!can_graph) {
+    for (uint32_t k = 0; k < n; ++k) {
+      int r = launch_tick(e, &e->inbox[slots[k]]);
+      if (r) return r;
+    }
+    return MRQ_OK;
+  }
+  std::string key((const char *)slots, (size_t)n * sizeof(uint32_t));
+  key.push_back((char)('0' + (e->tick_parity & 1u)));
+  key.push_back((char)('0' + (e->slow_parity & 1u)));
+  key.push_back((char)('0' + e->tick_mode));
+  key.push_back((char)('0' + ((e->comm_mode == 1 && e->ipc_attached) ? e->world : 1)));
+  const uint64_t tick0 = e->tick_no, launches0 = e->launches;
+  const uint32_t tp0 = e->tick_parity, sp0 = e->slow_parity;
+  auto it = e->graphs.find(key);
+  if (it == e->graphs.end()) {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    bool ok = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    int rc = MRQ_OK;
+    if (ok) {
+      for (uint32_t k = 0; k < n && rc == MRQ_OK; ++k) rc = launch_tick(e, &e->inbox[slots[k]]);
+      ok = cudaStreamEndCapture(e->stream, &graph) == cudaSuccess && rc == MRQ_OK && graph != nullptr;
+    }
+    // capture recorded the launches without running them: rewind the host-side bookkeeping
+    const uint64_t per_tick = n ? (e->launches - launches0) / n : 0;
+    e->tick_no = tick0;
+    e->launches = launches0;
+    e->tick_parity = tp0;
+    e->slow_parity = sp0;
+    if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {  // no graph support for this sequence: fall back to plain launches from now on
+      cudaGetLastError();
+      e->graphs_disabled = true;
+      return mrq_tick_many(e, slots, n);
+    }
+    (void)per_tick;
+    it = e->graphs.emplace(key, exec).first;
+  }
+  CK(e, cudaGraphLaunch(it->second, e->stream));
+  e->tick_no = tick0 + n;
+  e->launches = launches0 + (uint64_t)n * (e->tick_mode == 1 ? 1u : 2u);
+  if (n & 1u) {
+    e->tick_parity = tp0 ^ 1u;
+    if (e->tick_mode != 1) e->slow_parity = sp0 ^ 1u;
+  }
+  return MRQ_OK;
+}
+
 int mrq_tick_idle(mrq_engine *e, uint32_t n) {
   if (!e) return MRQ_E_INVAL;
   CK(e, cudaSetDevice(e->device));
@@ -963,6 +1051,7 @@ int mrq_comm_set_mode(mrq_engine *e, uint32_t mode) {
   if (!e || mode > 1) return MRQ_E_INVAL;
   if (mode == 1 && !e->ipc_attached) return fail(e, MRQ_E_STATE, "peer-store gather needs mrq_ipc_attach first");
   e->comm_mode = mode;
+  if (mode == 1) e->gather_prime = true;  // (re)publish the high words on the next tick
   return MRQ_OK;
 }
 
@@ -999,13 +1088,23 @@ int mrq_ipc_attach(mrq_engine *e, const uint8_t *handles, uint32_t rank, uint32_
   e->world = world;
   e->rank = rank;
   e->ipc_attached = true;
+  e->gather_prime = true;  // the first tick publishes the high words of every commit index
   return MRQ_OK;
 }
 
 int mrq_sync_gathered(mrq_engine *e, uint64_t *gathered_out) {
   if (!e || !gathered_out) return MRQ_E_INVAL;
   CK(e, cudaSetDevice(e->device));
-  CK(e, cudaMemcpyAsync(gathered_out, e->gathered, (size_t)e->world * e->G * 8, cudaMemcpyDeviceToHost, e->stream));
+  const size_t n = (size_t)e->world * e->G;
+  if (e->comm_mode == 1 && e->ipc_attached) {
+    // peer-store layout: low words [n] then high words [n]; stitch them back into 64-bit indices
+    std::vector<uint32_t> tmp(2 * n);
+    CK(e, cudaMemcpyAsync(tmp.data(), e->gathered, n * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    for (size_t k = 0; k < n; ++k) gathered_out[k] = ((uint64_t)tmp[n + k] << 32) | tmp[k];
+    return MRQ_OK;
+  }
+  CK(e, cudaMemcpyAsync(gathered_out, e->gathered, n * 8, cudaMemcpyDeviceToHost, e->stream));
   CK(e, cudaStreamSynchronize(e->stream));
   return MRQ_OK;
 }

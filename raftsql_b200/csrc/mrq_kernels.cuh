@@ -71,11 +71,17 @@ struct TickArgs {
   StateView s;
   InboxView in;  // in.type == nullptr: idle tick (timers only)
   Counters *ctr;
-  uint64_t G, gs, group_base, seed, tick_no;
+  uint64_t G, gs, group_base, seed;
+  // The tick number lives in device memory so that a sequence of ticks can be replayed as a CUDA graph:
+  // tick t reads tick_cur (written during tick t-1) and its first kernel writes tick_next = tick_cur + 1.
+  const uint64_t *tick_cur;
+  uint64_t *tick_next;
   uint32_t election_tick, heartbeat_tick;
-  // fused peer-store gather (multi-GPU mode 1): committed[g] is stored into every rank's gather buffer
-  uint64_t *peer_gather[8];
-  uint32_t world, rank;
+  // Fused peer-store all-gather (multi-GPU mode 1): the commit index of every group this rank owns is stored
+  // straight into every rank's gather buffer over NVLink.  To halve the bytes on the wire the buffer is split
+  // into low words (stored every tick) and high words (stored only when they change, or when priming).
+  uint32_t *peer_lo[8], *peer_hi[8];
+  uint32_t world, rank, gather_prime;
   // fast/slow split: groups the fast kernel leaves untouched are listed here for the slow kernel
   uint32_t *slow_list;
   unsigned *slow_count, *slow_count_next;
@@ -533,7 +539,8 @@ __device__ __forceinline__ uint32_t general_group_tick(const TickArgs &a, const 
     g.elapsed = m.elapsed; g.rto = m.rto; g.hb = m.hb; g.votes = m.votes; g.strict = m.strict; g.ltok = m.ltok;
     g.out = 0; g.dirty = 0; g.ev = 0; g.lt_valid = false; g.last_term = 0; g.pending = false;
     g.lt_ptr = a.s.last_term + i;
-    g.seed = a.seed; g.gg = a.group_base + i; g.tick_no = a.tick_no;
+    g.seed = a.seed; g.gg = a.group_base + i; g.tick_no = *a.tick_cur;
+    const uint64_t committed0 = g.committed;
     g.et = a.election_tick; g.ht = a.heartbeat_tick;
     // phase 2: the present messages' term / index
     uint64_t mt[R], mi[R];
@@ -572,7 +579,11 @@ __device__ __forceinline__ uint32_t general_group_tick(const TickArgs &a, const 
     st_state_u32(a.s.out + i, g.out);
     if (a.world > 1) {  // fused all-gather: store the commit index straight into every rank's buffer
 #pragma unroll 1
-      for (uint32_t p = 0; p < a.world; ++p) a.peer_gather[p][(uint64_t)a.rank * a.G + i] = g.committed;
+      for (uint32_t p = 0; p < a.world; ++p) {
+        a.peer_lo[p][(uint64_t)a.rank * a.G + i] = (uint32_t)g.committed;
+        if (a.gather_prime || (g.committed >> 32) != (committed0 >> 32))
+          a.peer_hi[p][(uint64_t)a.rank * a.G + i] = (uint32_t)(g.committed >> 32);
+      }
     }
     ev = g.ev;
   }
@@ -600,6 +611,7 @@ __global__ void __launch_bounds__(kTickThreads, (R <= 5 ? 8 : (R == 6 ? 7 : 6)))
   // lanes past G read zero padding); `valid` only gates stores and the slow-list append.  That keeps the
   // warp collectives below on a full, converged warp.
   const bool valid = i < a.G;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.tick_next = *a.tick_cur + 1;  // the next tick's number
   {
     const bool has_inbox = a.in.type != nullptr;
     // one wave of independent loads: packed small state, the u64 state columns, Progress.Match, message types
@@ -607,6 +619,7 @@ __global__ void __launch_bounds__(kTickThreads, (R <= 5 ? 8 : (R == 6 ? 7 : 6)))
     const uint64_t term = ld_state(a.s.term + i);
     uint64_t last_index = ld_state(a.s.last_index + i);
     uint64_t committed = ld_state(a.s.committed + i);
+    const uint64_t committed0 = committed;
     const uint64_t gate = ld_state(a.s.term_start + i);
     uint32_t ty[R];
 #pragma unroll
@@ -721,7 +734,11 @@ __global__ void __launch_bounds__(kTickThreads, (R <= 5 ? 8 : (R == 6 ? 7 : 6)))
       st_state_u32(a.s.out + i, out);
       if (a.world > 1) {  // fused all-gather: store the commit index straight into every rank's buffer
 #pragma unroll 1
-        for (uint32_t p = 0; p < a.world; ++p) a.peer_gather[p][(uint64_t)a.rank * a.G + i] = committed;
+        for (uint32_t p = 0; p < a.world; ++p) {
+          a.peer_lo[p][(uint64_t)a.rank * a.G + i] = (uint32_t)committed;
+          if (a.gather_prime || (committed >> 32) != (committed0 >> 32))
+            a.peer_hi[p][(uint64_t)a.rank * a.G + i] = (uint32_t)(committed >> 32);
+        }
       }
     }
   }
@@ -760,6 +777,7 @@ __global__ void __launch_bounds__(kTickThreads, (R <= 5 ? 6 : 5)) tick_general_k
   pdl_launch_dependents();
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   pdl_wait();
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.tick_next = *a.tick_cur + 1;
   uint32_t ev = 0;
   if (i < a.G) ev = general_group_tick<R>(a, i);
   if (__any_sync(0xFFFFFFFFu, ev != 0)) count_events(a.ctr, ev);

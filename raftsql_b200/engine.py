@@ -195,6 +195,10 @@ class Engine:
     def tick(self, slot: int = 0):
         self._ck(self.L.mrq_tick(self.h, slot))
 
+    def tick_many(self, slots):
+        s = np.ascontiguousarray(slots, dtype=np.uint32)
+        self._ck(self.L.mrq_tick_many(self.h, _p(s, F.u32p), len(s)))
+
     def tick_idle(self, n: int = 1):
         self._ck(self.L.mrq_tick_idle(self.h, n))
 

@@ -136,6 +136,48 @@ def test_split_launch_equals_single_general_kernel(cfg_no, R):
         assert ca[k] == cb[k], k
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_tick_many_graph_replay_equals_single_ticks(mode):
+    """mrq_tick_many (CUDA-graph replay of a slot sequence) == the same ticks launched one by one, including a
+    second replay of the cached graph and a rewind (set_tick_count normalises the graph parities)."""
+    G, R, S = 30000, 5, 7
+    p = preset_trace(5)
+    a, b = Engine(G, R, seed=3, inbox_slots=S), Engine(G, R, seed=3, inbox_slots=S)
+    a.set_tick_mode(mode)
+    b.set_tick_mode(mode)
+    for t in range(40):  # get past the first elections
+        a.gen_trace(p, t)
+        b.post_inbox_dense(a.read_inbox())
+        a.tick()
+        b.tick()
+    snap, tick0 = a.export_state(), a.tick_count
+    for rep in range(3):
+        for s in range(S):  # S inboxes generated from a's evolving state, mirrored into b's slots
+            a.gen_trace(p, 100 + rep * S + s, slot=s)
+            b.post_inbox_dense(a.read_inbox(s), slot=s)
+            a.tick(s)
+        b.tick_many(list(range(S)))
+        sa, sb = a.export_state(), b.export_state()
+        lead = sa["role"] == LEADER
+        for k in sa:
+            if k == "match":
+                np.testing.assert_array_equal(sa[k][:, lead], sb[k][:, lead], err_msg=f"rep {rep} match")
+            else:
+                np.testing.assert_array_equal(sa[k], sb[k], err_msg=f"rep {rep} {k}")
+        assert a.tick_count == b.tick_count
+    # rewind both and replay the last slot sequence: the cached graph must still be valid
+    for e in (a, b):
+        e.import_state(snap)
+        e.tick_count = tick0
+    for s in range(S):
+        a.tick(s)
+    b.tick_many(list(range(S)))
+    sa, sb = a.export_state(), b.export_state()
+    for k in ("term", "committed", "last_index", "role", "votes", "randomized_timeout", "election_elapsed"):
+        np.testing.assert_array_equal(sa[k], sb[k], err_msg=f"after rewind {k}")
+    assert a.counters()["commits_advanced"] == b.counters()["commits_advanced"]
+
+
 def test_zero_groups():
     with Engine(0, 3) as eng:
         eng.tick_idle(3)
