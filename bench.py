@@ -222,6 +222,7 @@ def run_ours(args):
     nslots = min(K + W, MAX_SLOTS)
 
     eng = Engine(G, R, seed=SEED, group_base=base, device=dev, inbox_slots=nslots)
+    eng.set_graph_mode({"off": 0, "on": 1, "auto": 2}[args.graph])
     st0 = steady_state(G, R, base, SEED)
     eng.import_state(st0)
     p = preset_trace(3)
@@ -496,6 +497,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
                     help="N>1: how committed[] is all-gathered each tick")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="CUDA-graph replay of the tick sequence (auto: only for small shards)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

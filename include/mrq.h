@@ -227,6 +227,9 @@ int mrq_tick(mrq_engine *e, uint32_t slot);
  * captured into a CUDA graph on first use and replayed afterwards (launch-bound regimes: small shards,
  * many GPUs).  Same results as n mrq_tick calls.                                               */
 int mrq_tick_many(mrq_engine *e, const uint32_t *slots, uint32_t n);
+/* Whether mrq_tick_many replays CUDA graphs: 0 never (plain launches), 1 always, 2 (default) only when
+ * the engine holds few enough groups that the host launch rate, not the kernels, bounds the tick rate. */
+int mrq_set_graph_mode(mrq_engine *e, int mode);
 /* n ticks with an empty inbox (timers only). */
 int mrq_tick_idle(mrq_engine *e, uint32_t n);
 /* How mrq_tick is launched: 0 (default) = a lean fast kernel for the ticks that need no role machinery

@@ -99,6 +99,7 @@ struct mrq_engine {
   uint32_t tick_parity = 0;
   bool gather_prime = false;        // next tick stores the high words of every commit index to the peers
   bool graphs_disabled = false;
+  int graph_mode = 2;               // mrq_set_graph_mode: 0 never, 1 always, 2 auto (small shards only)
   std::map<std::string, cudaGraphExec_t> graphs;  // mrq_tick_many: one executable graph per slot sequence
   int tick_mode = 0;                // 0 = fast + slow kernels, 1 = single general kernel
   uint64_t tick_no = 0;
@@ -209,6 +210,7 @@ int copy_out(mrq_engine *e, void *host, const void *dev, size_t elem, size_t row
   }
 
 int g_sm_count = 148;
+constexpr uint64_t kGraphAutoMaxGroups = 200000;
 
 int launch_tick(mrq_engine *e, const InboxBuf *ib) {
   if (e->G == 0) {
@@ -789,7 +791,10 @@ int mrq_tick_many(mrq_engine *e, const uint32_t *slots, uint32_t n) {
   }
   CK(e, cudaSetDevice(e->device));
   const bool nccl_gather = e->world > 1 && e->comm_mode == 0 && e->comm;
-  const bool can_graph = n >= 2 && !e->graphs_disabled && !nccl_gather && !e->gather_prime && e->G > 0;
+  // graph_mode: 0 never, 1 always, 2 (default) only for small shards, where the host's launch rate rather than
+  // the kernels bounds the tick rate (measured on B200: at 1M groups per GPU PDL stream launches are faster)
+  const bool want_graph = e->graph_mode == 1 || (e->graph_mode == 2 && e->G <= kGraphAutoMaxGroups);
+  const bool can_graph = want_graph && n >= 2 && !e->graphs_disabled && !nccl_gather && !e->gather_prime && e->G > 0;
   if (!can_graph) {
     for (uint32_t k = 0; k < n; ++k) {
       int r = launch_tick(e, &e->inbox[slots[k]]);
@@ -856,6 +861,12 @@ int mrq_quorum_commit(mrq_engine *e) {
   if (e->G == 0) return MRQ_OK;
   QuorumArgs a{e->s.match, e->s.committed, e->s.term_start, e->ctr, e->G, e->gs};
   return launch_quorum(e, a, e->quorum_variant);
+}
+
+int mrq_set_graph_mode(mrq_engine *e, int mode) {
+  if (!e || mode < 0 || mode > 2) return MRQ_E_INVAL;
+  e->graph_mode = mode;
+  return MRQ_OK;
 }
 
 int mrq_set_tick_mode(mrq_engine *e, int mode) {
