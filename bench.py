@@ -115,6 +115,16 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
+def ncu_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu summary (bench.py never
+    runs under a profiler itself)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[kernel]
+        return int(t["dram_read_bytes"]) + int(t["dram_write_bytes"])
+    except Exception:
+        return None
+
+
 def measured_peak_gbs() -> tuple[float, str]:
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -223,6 +233,8 @@ def run_ours(args):
 
     eng = Engine(G, R, seed=SEED, group_base=base, device=dev, inbox_slots=nslots)
     eng.set_graph_mode({"off": 0, "on": 1, "auto": 2}[args.graph])
+    if args.tick_mode is not None:
+        eng.set_tick_mode(args.tick_mode)
     st0 = steady_state(G, R, base, SEED)
     eng.import_state(st0)
     p = preset_trace(3)
@@ -314,8 +326,10 @@ def run_ours(args):
         "group_ticks_per_sec": ticks_per_s * G_TOTAL,
         "roofline": {"bound": "hbm", "kernel": "tick_fast_kernel<5> (+ tick_slow_kernel<5> over the slow list, empty on this trace)",
                      "achieved": tick_gbs, "peak": peak, "unit": "GB/s",
-                     "frac": tick_gbs / peak, "traffic": None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_group": tb},
+                     "frac": tick_gbs / peak, "traffic": ncu_traffic("tick_fast_kernel<5>") if world == 1 else None,
+                     "traffic_source": "profiles/r01_traffic.json (ncu --set full, cold cache, isolated launch)",
+                     "peak_source": peak_src, "algorithmic_bytes_per_group": tb,
+                     "algorithmic_bytes_per_launch": tb["total"] * G},
         "gpu_launches": launches_timed,
         "clocks": clocks,
     }
@@ -334,16 +348,19 @@ def run_ours(args):
                                     "sample": f"{n} full ticks over all {G_TOTAL} groups x {R} replicas in {el:.1f} s on {nt} threads"}
         except Exception as ex:  # the baseline must never take the GPU numbers down with it
             line["cpu_baseline"] = {"value": None, "unit": "ticks/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
-    elif rank == 0:
-        line["e2e"] = None
     if world > 1:
         # correctness of the gather on every rank: it must equal the concatenation of all shards' commits
         mine = torch.from_numpy(eng.sync_commits().view(np.int64)).cuda()
         allc = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(allc, mine)
         g = eng.sync_gathered().view(np.int64)
-        ok = bool(np.array_equal(g, torch.cat(allc).cpu().numpy()))
-        line["gather_check"] = ok
+        ok = torch.tensor([int(np.array_equal(g, torch.cat(allc).cpu().numpy()))], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        line["gather_check"] = bool(ok.item())
+        # end to end at N GPUs: every rank ships its shard's packed inbox over its own PCIe link each tick
+        e2e = bench_e2e(eng, st0, host_ib, K, W, dist=dist, torch=torch)
+        if rank == 0:
+            line["e2e"] = e2e
     if rank == 0:
         print(json.dumps(line))
     eng.close()
@@ -389,14 +406,15 @@ def bench_quorum_kernel(torch, eng, peak, K, W):
         out[name] = {"us_per_launch": per * 1e3, "achieved": gbs, "frac": gbs / peak, "launches": len(timed)}
     best = max(out, key=lambda k: out[k]["achieved"])
     return {"bound": "hbm", "kernel": f"quorum_kernel ({best})", "achieved": out[best]["achieved"], "peak": peak,
-            "unit": "GB/s", "frac": out[best]["frac"], "traffic": None,
+            "unit": "GB/s", "frac": out[best]["frac"], "traffic": ncu_traffic("quorum_kernel_ldg<5>"),
             "algorithmic_bytes_per_group": quorum_bytes_per_group(R), "variants": out,
             "cold": f"{len(sets)} distinct column sets ({quorum_bytes_per_group(R) * G / 1e6:.1f} MB each), L2 flushed before timing"}
 
 
-def bench_e2e(eng, st0, host_ib, K, W):
+def bench_e2e(eng, st0, host_ib, K, W, dist=None, torch=None):
     """The same tick through the C-ABI with HOST buffers: per step H2D of that tick's inbox, the tick, and a
-    D2H drain of the commit indices — all inside the timed region."""
+    D2H drain of the commit indices — all inside the timed region.  With `dist`, every rank runs its shard and
+    the elapsed time is the max over ranks (barrier on both sides)."""
     import ctypes as C
 
     from raftsql_b200 import _ffi as F
@@ -406,16 +424,28 @@ def bench_e2e(eng, st0, host_ib, K, W):
     G, Rr = eng.G, eng.R
     steps = K
 
+    def sync_all():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # -- wide form (33 B per slot, pageable numpy arrays): the straightforward host path ----------------
     def run_wide(nsteps, timed):
         eng.import_state(st0)
         eng.tick_count = 0
+        sync_all()
         t0 = time.perf_counter()
         for k in range(nsteps):
             eng.post_inbox_dense(host_ib[k % n], slot=k % 2)
             eng.tick(k % 2)
             c = eng.sync_commits()
-        return (time.perf_counter() - t0), c
+        return max_over_ranks(time.perf_counter() - t0), c
 
     run_wide(2, False)
     el_w, commits_wide = run_wide(min(steps, n), True)
@@ -455,6 +485,7 @@ def bench_e2e(eng, st0, host_ib, K, W):
             eng.set_packed_base(base_index, base_term)
             base = eng.sync_commits().copy()  # a full read also rebases the delta drain
             acc = np.zeros(G, np.uint64)
+            sync_all()
             t0 = time.perf_counter()
             rc = L.mrq_post_inbox_packed(h, 0, C.byref(views[0]))
             for k in range(nsteps):
@@ -467,7 +498,7 @@ def bench_e2e(eng, st0, host_ib, K, W):
                 if accumulate:  # reconstruct commit indices from the per-tick advances (checking run only)
                     assert delta.array.max() < 255
                     acc += delta.array
-            el = time.perf_counter() - t0
+            el = max_over_ranks(time.perf_counter() - t0)
             eng.synchronize()
             return el, base + acc
 
@@ -475,8 +506,9 @@ def bench_e2e(eng, st0, host_ib, K, W):
         _, commits_check = run_packed(min(steps, n), True)
         same = bool(np.array_equal(commits_check, commits_wide)) and bool(np.array_equal(commits_check, eng.sync_commits()))
         el_p, _ = run_packed(steps, False)
-        results[bits] = {"value": steps / el_p, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(delta.nbytes),
-                         "equals_wide_form": same, "h2d_GBps": h2d * steps / el_p / 1e9}
+        ws = 1 if dist is None else dist.get_world_size()  # bytes are whole-job figures (all ranks)
+        results[bits] = {"value": steps / el_p, "h2d_bytes_per_step": h2d * ws, "d2h_bytes_per_step": int(delta.nbytes) * ws,
+                         "equals_wide_form": same, "h2d_GBps_per_gpu": h2d * steps / el_p / 1e9}
     best = max(results, key=lambda b: results[b]["value"])
     res = {"value": results[best]["value"], "unit": "ticks/s", "h2d_bytes_per_step": results[best]["h2d_bytes_per_step"],
            "d2h_bytes_per_step": results[best]["d2h_bytes_per_step"], "steps": steps,
@@ -497,6 +529,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
                     help="N>1: how committed[] is all-gathered each tick")
+    ap.add_argument("--tick-mode", type=int, default=None, choices=[0, 2],
+                    help="0: fast + slow kernels, 2: single fused launch (default: the engine's)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="CUDA-graph replay of the tick sequence (auto: only for small shards)")
     args = ap.parse_args()

@@ -232,10 +232,11 @@ int mrq_tick_many(mrq_engine *e, const uint32_t *slots, uint32_t n);
 int mrq_set_graph_mode(mrq_engine *e, int mode);
 /* n ticks with an empty inbox (timers only). */
 int mrq_tick_idle(mrq_engine *e, uint32_t n);
-/* How mrq_tick is launched: 0 (default) = a lean fast kernel for the ticks that need no role machinery
+/* How mrq_tick is launched: 0 = a lean fast kernel for the ticks that need no role machinery
  * (steady-state leaders, quiet / heart-beaten followers) + a general kernel over the compacted list of
- * the remaining groups; 1 = one general kernel over every group.  Both give identical results; mode 1
- * exists for differential testing.                                                             */
+ * the remaining groups (two launches); 2 = one launch doing both (each CTA compacts its stragglers in
+ * shared memory and runs the general path on them); 1 = one general kernel over every group
+ * (differential testing).  All give identical results.                                          */
 int mrq_set_tick_mode(mrq_engine *e, int mode);
 
 /* The standalone quorum kernel (K3; SURVEY §8a rows a15–a16): for every leader group,

@@ -247,6 +247,10 @@ int launch_tick(mrq_engine *e, const InboxBuf *ib) {
     MRQ_DISPATCH_R(e->R, lst = launch_pdl(tick_general_kernel<kR>, nb, kTickThreads, 0, e->stream, a));
     CK(e, lst);
     e->launches++;
+  } else if (e->tick_mode == 2) {  // single launch: fast tick + in-CTA general path for the stragglers
+    MRQ_DISPATCH_R(e->R, lst = launch_pdl(tick_fused_kernel<kR>, nb, kTickThreads, 0, e->stream, a));
+    CK(e, lst);
+    e->launches++;
   } else {
     MRQ_DISPATCH_R(e->R, lst = launch_pdl(tick_fast_kernel<kR>, nb, kTickThreads, 0, e->stream, a));
     CK(e, lst);
@@ -837,10 +841,10 @@ int mrq_tick_many(mrq_engine *e, const uint32_t *slots, uint32_t n) {
   }
   CK(e, cudaGraphLaunch(it->second, e->stream));
   e->tick_no = tick0 + n;
-  e->launches = launches0 + (uint64_t)n * (e->tick_mode == 1 ? 1u : 2u);
+  e->launches = launches0 + (uint64_t)n * (e->tick_mode == 0 ? 2u : 1u);
   if (n & 1u) {
     e->tick_parity = tp0 ^ 1u;
-    if (e->tick_mode != 1) e->slow_parity = sp0 ^ 1u;
+    if (e->tick_mode == 0) e->slow_parity = sp0 ^ 1u;
   }
   return MRQ_OK;
 }
@@ -870,7 +874,7 @@ int mrq_set_graph_mode(mrq_engine *e, int mode) {
 }
 
 int mrq_set_tick_mode(mrq_engine *e, int mode) {
-  if (!e || mode < 0 || mode > 1) return MRQ_E_INVAL;
+  if (!e || mode < 0 || mode > 2) return MRQ_E_INVAL;
   e->tick_mode = mode;
   return MRQ_OK;
 }

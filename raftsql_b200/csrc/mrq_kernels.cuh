@@ -600,18 +600,13 @@ __device__ __forceinline__ uint32_t general_group_tick(const TickArgs &a, const 
 //     UNTOUCHED and its index appended to the slow list (one warp-aggregated atomic per warp).
 // (2) tick_slow_kernel: grid-strides over the slow list and runs general_group_tick on each entry.
 // A group is handled by exactly one of the two, and both are exact, so the pair equals the single kernel.
+// The fast per-group tick.  Sets `slow` (and touches nothing) when the group needs the general path.
 template <int R>
-__global__ void __launch_bounds__(kTickThreads, (R <= 5 ? 8 : (R == 6 ? 7 : 6))) tick_fast_kernel(const TickArgs a) {
-  pdl_launch_dependents();
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t ev = 0;
-  bool slow = false;
-  pdl_wait();
+__device__ __forceinline__ void fast_group_tick(const TickArgs &a, const uint64_t i, bool &slow, uint32_t &ev) {
   // Every lane runs the same straight-line code (columns are padded to a multiple of the CTA size, so the
   // lanes past G read zero padding); `valid` only gates stores and the slow-list append.  That keeps the
   // warp collectives below on a full, converged warp.
   const bool valid = i < a.G;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *a.tick_next = *a.tick_cur + 1;  // the next tick's number
   {
     const bool has_inbox = a.in.type != nullptr;
     // one wave of independent loads: packed small state, the u64 state columns, Progress.Match, message types
@@ -742,6 +737,17 @@ __global__ void __launch_bounds__(kTickThreads, (R <= 5 ? 8 : (R == 6 ? 7 : 6)))
       }
     }
   }
+}
+
+template <int R>
+__global__ void __launch_bounds__(kTickThreads, (R <= 5 ? 8 : (R == 6 ? 7 : 6))) tick_fast_kernel(const TickArgs a) {
+  pdl_launch_dependents();
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t ev = 0;
+  bool slow = false;
+  pdl_wait();
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.tick_next = *a.tick_cur + 1;  // the next tick's number
+  fast_group_tick<R>(a, i, slow, ev);
   // hand the groups this kernel did not touch to the slow kernel: one atomic per warp
   const unsigned smask = __ballot_sync(0xFFFFFFFFu, slow);
   if (smask != 0) {
@@ -768,6 +774,41 @@ __global__ void __launch_bounds__(kTickThreads, (R <= 5 ? 6 : 5)) tick_slow_kern
     uint32_t ev = 0;
     if (k < n) ev = general_group_tick<R>(a, (uint64_t)a.slow_list[k]);
     if (__any_sync(0xFFFFFFFFu, ev != 0)) count_events(a.ctr, ev);
+  }
+}
+
+// Single-launch form of the same split: every lane runs the fast tick; the CTA then compacts the few lanes
+// that need the general path into shared memory and runs general_group_tick on them with converged warps.
+// One launch per tick instead of two (the second launch costs ~3 us even on an empty list, which matters
+// once a GPU's shard is small), at the price of the general path's register budget for the whole kernel.
+template <int R>
+__global__ void __launch_bounds__(kTickThreads, (R <= 5 ? 6 : 5)) tick_fused_kernel(const TickArgs a) {
+  __shared__ uint32_t s_list[kTickThreads];
+  __shared__ unsigned s_n;
+  pdl_launch_dependents();
+  const uint64_t base = (uint64_t)blockIdx.x * blockDim.x;
+  uint32_t ev = 0;
+  bool slow = false;
+  if (threadIdx.x == 0) s_n = 0;
+  pdl_wait();
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.tick_next = *a.tick_cur + 1;
+  fast_group_tick<R>(a, base + threadIdx.x, slow, ev);
+  __syncthreads();
+  const unsigned smask = __ballot_sync(0xFFFFFFFFu, slow);
+  if (smask != 0) {  // warp-aggregated append to the CTA's list
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned pos = 0;
+    if (lane == 0) pos = atomicAdd(&s_n, (unsigned)__popc(smask));
+    pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+    if (slow) s_list[pos + __popc(smask & ((1u << lane) - 1u))] = threadIdx.x;
+  }
+  __syncthreads();
+  const unsigned n = s_n;
+  if (__any_sync(0xFFFFFFFFu, ev != 0)) count_events(a.ctr, ev);
+  if (n != 0) {  // CTA-uniform
+    uint32_t ev2 = 0;
+    if (threadIdx.x < n) ev2 = general_group_tick<R>(a, base + s_list[threadIdx.x]);
+    if (__any_sync(0xFFFFFFFFu, ev2 != 0)) count_events(a.ctr, ev2);
   }
 }
 

@@ -105,12 +105,15 @@ def test_follower_heartbeat_trace(R):
     assert eng.counters()["errors"] == 0 and orc.errors == 0
 
 
+@pytest.mark.parametrize("mode", [0, 2])
 @pytest.mark.parametrize("cfg_no,R", [(2, 3), (5, 5), (5, 7), (3, 5)])
-def test_split_launch_equals_single_general_kernel(cfg_no, R):
-    """mrq_set_tick_mode: fast + slow kernels (default) vs one general kernel over every group."""
+def test_split_launch_equals_single_general_kernel(cfg_no, R, mode):
+    """mrq_set_tick_mode: fast + slow kernels (0) / the fused single launch (2) vs one general kernel over
+    every group (1)."""
     G, T = 20000, 150
     p = preset_trace(cfg_no) if cfg_no != 3 else _follower_heavy_params()
     a, b = Engine(G, R, seed=7), Engine(G, R, seed=7)
+    a.set_tick_mode(mode)
     b.set_tick_mode(1)
     if cfg_no == 3:
         st = leader_state(G, R, np.random.default_rng(1))
@@ -136,7 +139,7 @@ def test_split_launch_equals_single_general_kernel(cfg_no, R):
         assert ca[k] == cb[k], k
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_tick_many_graph_replay_equals_single_ticks(mode):
     """mrq_tick_many (CUDA-graph replay of a slot sequence) == the same ticks launched one by one, including a
     second replay of the cached graph and a rewind (set_tick_count normalises the graph parities)."""
