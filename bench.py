@@ -235,6 +235,8 @@ def run_ours(args):
     eng.set_graph_mode({"off": 0, "on": 1, "auto": 2}[args.graph])
     if args.tick_mode is not None:
         eng.set_tick_mode(args.tick_mode)
+    if args.l2 is not None:
+        eng.set_l2_policy(args.l2)
     st0 = steady_state(G, R, base, SEED)
     eng.import_state(st0)
     p = preset_trace(3)
@@ -261,6 +263,10 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def run_ticks(n, first_slot):
+        if os.environ.get("MRQ_BENCH_PYLOOP") == "1":  # development switch: one mrq_tick call per tick
+            for k in range(n):
+                eng.tick((first_slot + k) % nslots)
+            return
         # n ticks in one C call; the launch sequence for a slot list is a CUDA graph after its first use
         eng.tick_many([(first_slot + k) % nslots for k in range(n)])
 
@@ -531,6 +537,8 @@ def main():
                     help="N>1: how committed[] is all-gathered each tick")
     ap.add_argument("--tick-mode", type=int, default=None, choices=[0, 2],
                     help="0: fast + slow kernels, 2: single fused launch (default: the engine's)")
+    ap.add_argument("--l2", type=int, default=None, choices=[0, 1],
+                    help="L2 residency hints of the tick kernel (default: the engine's, on)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="CUDA-graph replay of the tick sequence (auto: only for small shards)")
     args = ap.parse_args()

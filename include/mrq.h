@@ -230,6 +230,10 @@ int mrq_tick_many(mrq_engine *e, const uint32_t *slots, uint32_t n);
 /* Whether mrq_tick_many replays CUDA graphs: 0 never (plain launches), 1 always, 2 (default) only when
  * the engine holds few enough groups that the host launch rate, not the kernels, bounds the tick rate. */
 int mrq_set_graph_mode(mrq_engine *e, int mode);
+/* L2 residency hints of the tick kernel (default on): inbox columns are loaded evict-first, state columns
+ * loaded / stored evict-last, so that a shard whose state fits the 126 MB L2 keeps it on-chip from tick to
+ * tick and HBM carries (mostly) the inbox.  Results are unaffected; 0 turns the hints off.       */
+int mrq_set_l2_policy(mrq_engine *e, int on);
 /* n ticks with an empty inbox (timers only). */
 int mrq_tick_idle(mrq_engine *e, uint32_t n);
 /* How mrq_tick is launched: 0 = a lean fast kernel for the ticks that need no role machinery

@@ -116,6 +116,7 @@ SIGNATURES = {
     "mrq_tick": (C.c_int, [_EP, C.c_uint32]),
     "mrq_tick_many": (C.c_int, [_EP, u32p, C.c_uint32]),
     "mrq_set_graph_mode": (C.c_int, [_EP, C.c_int]),
+    "mrq_set_l2_policy": (C.c_int, [_EP, C.c_int]),
     "mrq_tick_idle": (C.c_int, [_EP, C.c_uint32]),
     "mrq_set_tick_mode": (C.c_int, [_EP, C.c_int]),
     "mrq_quorum_commit": (C.c_int, [_EP]),

@@ -100,6 +100,7 @@ struct mrq_engine {
   bool gather_prime = false;        // next tick stores the high words of every commit index to the peers
   bool graphs_disabled = false;
   int graph_mode = 2;               // mrq_set_graph_mode: 0 never, 1 always, 2 auto (small shards only)
+  int l2_policy = 1;                // mrq_set_l2_policy: keep state L2-resident, stream the inbox
   std::map<std::string, cudaGraphExec_t> graphs;  // mrq_tick_many: one executable graph per slot sequence
   int tick_mode = 0;                // 0 = fast + slow kernels, 1 = single general kernel
   uint64_t tick_no = 0;
@@ -152,11 +153,12 @@ cudaError_t launch_pdl(void (*kern)(Arg), unsigned grid, unsigned block, size_t 
   cfg.blockDim = dim3(block);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
+  static const bool no_pdl = getenv("MRQ_NO_PDL") != nullptr;  // development switch
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = no_pdl ? 0 : 1;
   return cudaLaunchKernelEx(&cfg, kern, arg);
 }
 
@@ -232,6 +234,7 @@ int launch_tick(mrq_engine *e, const InboxBuf *ib) {
   a.world = (e->comm_mode == 1 && e->ipc_attached) ? e->world : 1;
   a.rank = e->rank;
   a.gather_prime = e->gather_prime ? 1u : 0u;
+  a.l2_policy = e->l2_policy ? 1u : 0u;
   for (uint32_t p = 0; p < 8; ++p) {
     a.peer_lo[p] = reinterpret_cast<uint32_t *>(e->peer_gather[p]);
     a.peer_hi[p] = a.peer_lo[p] ? a.peer_lo[p] + (size_t)e->world * e->G : nullptr;
@@ -865,6 +868,12 @@ int mrq_quorum_commit(mrq_engine *e) {
   if (e->G == 0) return MRQ_OK;
   QuorumArgs a{e->s.match, e->s.committed, e->s.term_start, e->ctr, e->G, e->gs};
   return launch_quorum(e, a, e->quorum_variant);
+}
+
+int mrq_set_l2_policy(mrq_engine *e, int on) {
+  if (!e || on < 0 || on > 1) return MRQ_E_INVAL;
+  e->l2_policy = on;
+  return MRQ_OK;
 }
 
 int mrq_set_graph_mode(mrq_engine *e, int mode) {

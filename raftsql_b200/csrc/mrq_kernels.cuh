@@ -82,6 +82,7 @@ struct TickArgs {
   // into low words (stored every tick) and high words (stored only when they change, or when priming).
   uint32_t *peer_lo[8], *peer_hi[8];
   uint32_t world, rank, gather_prime;
+  uint32_t l2_policy;  // 1: inbox evict-first / state evict-last hints in the fast kernel (see l2_policy())
   // fast/slow split: groups the fast kernel leaves untouched are listed here for the slow kernel
   uint32_t *slow_list;
   unsigned *slow_count, *slow_count_next;
@@ -122,6 +123,49 @@ __device__ __forceinline__ void st_state(uint64_t *p, uint64_t v) {
 }
 __device__ __forceinline__ void st_state_u32(uint32_t *p, uint32_t v) {
   asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- L2 residency policy --------------------------------------------------------------------------------
+// At the headline shape the engine state (~92 MB) nearly fits B200's 126 MB L2, while every tick also streams
+// ~70 MB of inbox through it exactly once.  Left alone the stream evicts the state and each tick re-reads it
+// from HBM.  With cache-hinted accesses (createpolicy + .L2::cache_hint; the policy rides in the memory
+// descriptor, no extra instructions) the inbox is marked evict-first and the state evict-last, so state
+// columns stay on-chip from one tick to the next and HBM mostly carries the inbox.
+__device__ __forceinline__ uint64_t l2_policy(uint32_t kind) {  // 0 normal, 1 evict-first, 2 evict-last
+  uint64_t p;
+  if (kind == 1u)
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  else if (kind == 2u)
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  else
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t ld_stream_p(const uint64_t *p, uint64_t pol) {
+  uint64_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_stream_u8_p(const uint8_t *p, uint64_t pol) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_stream_u32_p(const uint32_t *p, uint64_t pol) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ uint64_t ld_state_p(const uint64_t *p, uint64_t pol) {
+  uint64_t v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_state_p(uint64_t *p, uint64_t v, uint64_t pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_state_u32_p(uint32_t *p, uint32_t v, uint64_t pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
 }
 
 // ---- q-th largest of R values held in registers (a15: mis[q()-1] after a descending sort) -------
@@ -607,22 +651,24 @@ __device__ __forceinline__ void fast_group_tick(const TickArgs &a, const uint64_
   // lanes past G read zero padding); `valid` only gates stores and the slow-list append.  That keeps the
   // warp collectives below on a full, converged warp.
   const bool valid = i < a.G;
+  const uint64_t pol_stream = l2_policy(a.l2_policy ? 1u : 0u);  // inbox, out word: read/written once per tick
+  const uint64_t pol_keep = l2_policy(a.l2_policy ? 2u : 0u);    // state columns: reused by the next tick
   {
     const bool has_inbox = a.in.type != nullptr;
     // one wave of independent loads: packed small state, the u64 state columns, Progress.Match, message types
-    const uint64_t w_meta = ld_state(a.s.meta + i);
-    const uint64_t term = ld_state(a.s.term + i);
-    uint64_t last_index = ld_state(a.s.last_index + i);
-    uint64_t committed = ld_state(a.s.committed + i);
+    const uint64_t w_meta = ld_state_p(a.s.meta + i, pol_keep);
+    const uint64_t term = ld_state_p(a.s.term + i, pol_keep);
+    uint64_t last_index = ld_state_p(a.s.last_index + i, pol_keep);
+    uint64_t committed = ld_state_p(a.s.committed + i, pol_keep);
     const uint64_t committed0 = committed;
-    const uint64_t gate = ld_state(a.s.term_start + i);
+    const uint64_t gate = ld_state_p(a.s.term_start + i, pol_keep);
     uint32_t ty[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) ty[r] = has_inbox ? ld_stream_u8(a.in.type + (uint64_t)r * a.gs + i) : 0u;
-    const uint32_t nprop = (has_inbox && a.in.prop) ? ld_stream_u32(a.in.prop + i) : 0u;
+    for (int r = 0; r < R; ++r) ty[r] = has_inbox ? ld_stream_u8_p(a.in.type + (uint64_t)r * a.gs + i, pol_stream) : 0u;
+    const uint32_t nprop = (has_inbox && a.in.prop) ? ld_stream_u32_p(a.in.prop + i, pol_stream) : 0u;
     uint64_t match[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) match[r] = ld_state(a.s.match + (uint64_t)r * a.gs + i);
+    for (int r = 0; r < R; ++r) match[r] = ld_state_p(a.s.match + (uint64_t)r * a.gs + i, pol_keep);
     Meta m = meta_unpack(w_meta);
     // second wave: term + (index | commit) of the messages that are present
     uint64_t mt[R], mx[R];
@@ -631,8 +677,8 @@ __device__ __forceinline__ void fast_group_tick(const TickArgs &a, const uint64_
       if ((uint32_t)(r + 1) == m.self) ty[r] = 0;  // a node does not message itself
       const bool present = ty[r] != 0u;
       const uint64_t *px = (ty[r] == MRQ_MSG_HEARTBEAT ? a.in.commit : a.in.index) + (uint64_t)r * a.gs + i;
-      mt[r] = present ? ld_stream(a.in.term + (uint64_t)r * a.gs + i) : 0ull;
-      mx[r] = present ? ld_stream(px) : 0ull;
+      mt[r] = present ? ld_stream_p(a.in.term + (uint64_t)r * a.gs + i, pol_stream) : 0ull;
+      mx[r] = present ? ld_stream_p(px, pol_stream) : 0ull;
     }
     uint32_t out = 0;
     uint32_t dirty = 0;
@@ -720,13 +766,13 @@ __device__ __forceinline__ void fast_group_tick(const TickArgs &a, const uint64_
     uint32_t wdirty = mine ? (dirty | (w_new != w_meta ? D_TERM : 0u)) : 0u;  // D_TERM bit reused: "meta changed"
     wdirty = __reduce_or_sync(0xFFFFFFFFu, wdirty);
     if (mine) {
-      if (wdirty & D_TERM) st_state(a.s.meta + i, w_new);
-      if (wdirty & D_LI) st_state(a.s.last_index + i, last_index);
-      if (wdirty & D_COMMIT) st_state(a.s.committed + i, committed);
+      if (wdirty & D_TERM) st_state_p(a.s.meta + i, w_new, pol_keep);
+      if (wdirty & D_LI) st_state_p(a.s.last_index + i, last_index, pol_keep);
+      if (wdirty & D_COMMIT) st_state_p(a.s.committed + i, committed, pol_keep);
 #pragma unroll
       for (int r = 0; r < R; ++r)
-        if (wdirty & (D_MATCH0 << r)) st_state(a.s.match + (uint64_t)r * a.gs + i, match[r]);
-      st_state_u32(a.s.out + i, out);
+        if (wdirty & (D_MATCH0 << r)) st_state_p(a.s.match + (uint64_t)r * a.gs + i, match[r], pol_keep);
+      st_state_u32_p(a.s.out + i, out, pol_stream);
       if (a.world > 1) {  // fused all-gather: store the commit index straight into every rank's buffer
 #pragma unroll 1
         for (uint32_t p = 0; p < a.world; ++p) {

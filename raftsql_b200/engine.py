@@ -199,6 +199,9 @@ class Engine:
         s = np.ascontiguousarray(slots, dtype=np.uint32)
         self._ck(self.L.mrq_tick_many(self.h, _p(s, F.u32p), len(s)))
 
+    def set_l2_policy(self, on: int):
+        self._ck(self.L.mrq_set_l2_policy(self.h, on))
+
     def set_graph_mode(self, mode: int):
         self._ck(self.L.mrq_set_graph_mode(self.h, mode))
 

@@ -77,13 +77,21 @@ void run(const char *name, unsigned long long *rd, unsigned long long *wr, size_
 
 int main(int argc, char **argv) {
   const size_t n = argc > 1 ? strtoull(argv[1], 0, 10) : (size_t)1 << 22;
-  const size_t stride = n + 64;
+  const size_t pad = argc > 2 ? strtoull(argv[2], 0, 10) : 64;  // column skew in 8-byte elements
+  const size_t stride = n + pad;
+  printf("--- stride = n + %zu elements\n", pad);
   unsigned long long *rd, *wr;
   cudaMalloc(&rd, stride * 8 * 28);
   cudaMalloc(&wr, stride * 8 * 12);
   cudaMemset(rd, 1, stride * 8 * 28);
   cudaMemset(wr, 0, stride * 8 * 12);
   const int it = 20;
+  if (argc > 3) {  // short form: only the tick-like and K3-like patterns
+    run<7, 0, 2, 1, 256>("K3-like 7r v2", rd, wr, n, stride, it);
+    run<20, 8, 1, 2, 128>("20r 8w 2-phase (tick-like)", rd, wr, n, stride, it);
+    run<12, 8, 1, 1, 128>("12r 8w", rd, wr, n, stride, it);
+    return 0;
+  }
   run<7, 0, 1, 1, 256>("K3-like 7r", rd, wr, n, stride, it);
   run<7, 0, 2, 1, 256>("K3-like 7r v2", rd, wr, n, stride, it);
   run<1, 1, 2, 1, 256>("copy 1r1w v2", rd, wr, n, stride, it);
