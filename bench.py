@@ -295,12 +295,6 @@ def run_ours(args):
     barrier()
     c1 = eng.counters()
     launches = c1["kernel_launches"] - c0["kernel_launches"]  # our kernels launched inside the timed region
-    # keep the GPU busy a little longer so the clock sampler sees load even for short K
-    t_end = time.time() + 0.6
-    while time.time() < t_end:
-        run_ticks(8, 0)
-        eng.synchronize()
-    clocks = sampler.finish()
     if dist is not None:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -310,6 +304,14 @@ def run_ours(args):
         launches_all = int(lt.item())
     else:
         launches_all = launches
+    # keep the GPU busy ~0.5 s more so the clock sampler sees it under this load even for short K.  The
+    # repeat count is derived from the max-over-ranks time, so EVERY rank issues the same number of ticks
+    # (a per-tick collective would deadlock on a time-based loop).
+    reps = max(4, min(4000, int(0.5 / max(1e-6, 8 * ms / K * 1e-3))))
+    for _ in range(reps):
+        run_ticks(8, 0)
+    eng.synchronize()
+    clocks = sampler.finish()
     launches_timed = launches_all
     ticks_per_s = K / (ms / 1e3)
     peak, peak_src = measured_peak_gbs()

@@ -212,7 +212,9 @@ int copy_out(mrq_engine *e, void *host, const void *dev, size_t elem, size_t row
   }
 
 int g_sm_count = 148;
-constexpr uint64_t kGraphAutoMaxGroups = 200000;
+// Measured on B200 (bench.py, 1,048,576 x 5 sharded): graph replay wins at 524,288 groups per GPU and below
+// (N=2: 51.5k vs 43.2k ticks/s; N=4: 72.3k vs 60.0k; N=8: 81.8k vs 63.8k) and loses at 1,048,576 (40.9 vs 37.5 us).
+constexpr uint64_t kGraphAutoMaxGroups = 600000;
 
 int launch_tick(mrq_engine *e, const InboxBuf *ib) {
   if (e->G == 0) {
