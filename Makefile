@@ -1,20 +1,35 @@
-# Builds libmrq.so (the C-ABI engine, sm_100a only) in-tree and the CPU oracle (test infrastructure).
+# Builds, in-tree: libmrq.so (the C-ABI engine, sm_100a only), libraftpipe.so (the C++ host side above the
+# C-ABI: channels, host node, WAL, NewRaftPipe), the CPU oracle (test infrastructure) and the C++ scenario test.
 NVCC ?= /usr/local/cuda/bin/nvcc
+CXX ?= g++
 ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wextra -Xptxas -v
+CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -Wextra -pthread
+ROOT := $(abspath .)
 LIB := raftsql_b200/libmrq.so
+HOSTLIB := raftsql_b200/libraftpipe.so
 SRC := raftsql_b200/csrc/mrq_engine.cu
 HDR := raftsql_b200/csrc/mrq_kernels.cuh include/mrq.h include/mrq_trace.h
+HOSTSRC := raftsql_b200/csrc/host/hostnode.cpp raftsql_b200/csrc/host/raftpipe.cpp
+HOSTHDR := raftsql_b200/csrc/host/chan.hpp raftsql_b200/csrc/host/hostnode.hpp raftsql_b200/csrc/host/raftpipe.hpp include/mrq.h
+CPPTEST := tests/cpp/raftpipe_test
 
-all: $(LIB) oracle
+all: $(LIB) $(HOSTLIB) oracle $(CPPTEST)
 
 $(LIB): $(SRC) $(HDR)
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(SRC) -ldl 2> build_ptxas.log || (cat build_ptxas.log; exit 1)
 
+$(HOSTLIB): $(HOSTSRC) $(HOSTHDR) $(LIB)
+	$(CXX) $(CXXFLAGS) -shared -o $@ $(HOSTSRC) -L$(ROOT)/raftsql_b200 -lmrq -Wl,-rpath,'$$ORIGIN'
+
 oracle:
 	$(MAKE) -C oracle liboracle.so
 
+$(CPPTEST): tests/cpp/raftpipe_test.cpp $(HOSTLIB) oracle
+	$(CXX) $(CXXFLAGS) -o $@ tests/cpp/raftpipe_test.cpp -L$(ROOT)/raftsql_b200 -lraftpipe -lmrq -L$(ROOT)/oracle -loracle \
+	  -Wl,-rpath,$(ROOT)/raftsql_b200 -Wl,-rpath,$(ROOT)/oracle
+
 clean:
-	rm -f $(LIB) build_ptxas.log
+	rm -f $(LIB) $(HOSTLIB) $(CPPTEST) build_ptxas.log
 	$(MAKE) -C oracle clean
 .PHONY: all oracle clean

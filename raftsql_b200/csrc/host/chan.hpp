@@ -1,0 +1,76 @@
+// chan.hpp — a Go channel for the C++ host side: unbuffered rendezvous by default, close(), `recv(v)`
+// returning false once closed and drained.  The reference's seam is three such channels
+// (reference raftpipe.go:3-7; all unbuffered: raft.go:65-66, server/main.go:30).
+#pragma once
+
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <stdexcept>
+
+namespace raftsql {
+
+struct ChanClosed : std::runtime_error {
+  ChanClosed() : std::runtime_error("send on closed channel") {}
+};
+
+template <class T>
+class Chan {
+ public:
+  explicit Chan(size_t buffered = 0) : cap_(buffered) {}
+
+  // Blocks until a receiver has taken the value (unbuffered) or there is room (buffered).
+  // `stop`, when given, aborts the wait: `select { case ch <- v: case <-stopc: }` (reference raft.go:89-93).
+  bool send(T v, const std::atomic<bool> *stop = nullptr) {
+    std::unique_lock<std::mutex> lk(mu_);
+    if (closed_) throw ChanClosed();
+    q_.push_back(std::move(v));
+    const unsigned long my = ++sent_;
+    cv_.notify_all();
+    if (cap_ && q_.size() <= cap_) return true;
+    while (taken_ < my) {
+      if (closed_) throw ChanClosed();
+      if (stop && stop->load()) return false;
+      cv_.wait_for(lk, std::chrono::milliseconds(20));
+    }
+    return true;
+  }
+
+  // false: closed and drained.  timeout_ms < 0: wait for ever; on timeout throws std::runtime_error.
+  bool recv(T &out, long timeout_ms = -1) {
+    std::unique_lock<std::mutex> lk(mu_);
+    auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(timeout_ms < 0 ? 0 : timeout_ms);
+    while (q_.empty()) {
+      if (closed_) return false;
+      if (timeout_ms >= 0 && std::chrono::steady_clock::now() >= deadline) throw std::runtime_error("recv timed out");
+      cv_.wait_for(lk, std::chrono::milliseconds(20));
+    }
+    out = std::move(q_.front());
+    q_.pop_front();
+    ++taken_;
+    cv_.notify_all();
+    return true;
+  }
+
+  void close() {
+    std::lock_guard<std::mutex> lk(mu_);
+    closed_ = true;
+    cv_.notify_all();
+  }
+  bool closed() {
+    std::lock_guard<std::mutex> lk(mu_);
+    return closed_;
+  }
+
+ private:
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<T> q_;
+  size_t cap_;
+  bool closed_ = false;
+  unsigned long sent_ = 0, taken_ = 0;
+};
+
+}  // namespace raftsql

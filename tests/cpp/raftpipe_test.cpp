@@ -1,0 +1,199 @@
+// raftpipe_test.cpp — scenario tests for the C++ host side (raftsql_b200/csrc/host/): the seam's channel
+// protocol, a 3-node in-process cluster, and stop / restart with WAL replay — the C++ counterpart of
+// tests/test_plumbing.py, which restates the reference's raftsql_test.go:92-171 at the raftPipe level.
+//
+//   raftpipe_test oracle <tmpdir>     consensus core = the CPU oracle (TEST ONLY: this file lives under tests/)
+//   raftpipe_test engine <tmpdir>     consensus core = the GPU engine through the C-ABI (needs a B200)
+#include <sys/stat.h>
+
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <thread>
+
+#include "../../include/mrq.h"
+#include "../../oracle/raft_oracle.h"
+#include "../../raftsql_b200/csrc/host/raftpipe.hpp"
+
+using namespace raftsql;
+
+namespace {
+
+// TEST-ONLY core: the oracle wearing the Core interface (one group, dense inbox of R slots).
+class OracleCore : public Core {
+ public:
+  OracleCore(uint32_t npeers, uint32_t id) : R_(npeers) {
+    e_ = orc_create(1, npeers, 0, 10, 1, 0x5EED + id, id);
+    if (!e_) throw std::runtime_error("orc_create failed");
+  }
+  ~OracleCore() override { orc_destroy(e_); }
+  void import_hardstate(uint64_t term, uint64_t vote, uint64_t committed, uint64_t last_index, uint64_t last_term) override {
+    orc_import(e_, &term, &vote, &committed, &last_index, &last_term, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+               nullptr, nullptr, nullptr);
+  }
+  CoreState tick(const std::vector<CoreMsg> &msgs, uint32_t nprop) override {
+    std::vector<uint8_t> type(R_, 0);
+    std::vector<uint64_t> term(R_, 0), index(R_, 0), logterm(R_, 0), commit(R_, 0);
+    for (const CoreMsg &m : msgs) {
+      const uint32_t r = m.from - 1;
+      type[r] = (uint8_t)m.type;
+      term[r] = m.term;
+      index[r] = m.index;
+      logterm[r] = m.logterm;
+      commit[r] = m.commit;
+    }
+    orc_tick(e_, type.data(), term.data(), index.data(), logterm.data(), commit.data(), &nprop, 1);
+    CoreState s;
+    s.match.resize(R_);
+    uint8_t role = 0, lead = 0;
+    orc_export(e_, &s.term, &s.vote, &s.committed, &s.last_index, &s.last_term, nullptr, s.match.data(), &role, &lead, nullptr,
+               nullptr, nullptr, nullptr, nullptr, &s.out);
+    s.role = role;
+    s.lead = lead;
+    return s;
+  }
+
+ private:
+  orc_engine *e_;
+  uint32_t R_;
+};
+
+int failures = 0;
+#define CHECK(cond, ...)                                   \
+  do {                                                     \
+    if (!(cond)) {                                         \
+      std::printf("FAIL %s:%d: ", __FILE__, __LINE__);     \
+      std::printf(__VA_ARGS__);                            \
+      std::printf("\n");                                   \
+      ++failures;                                          \
+    }                                                      \
+  } while (0)
+
+struct Collector {  // drains a CommitC on its own thread, like db.go's readCommits
+  std::shared_ptr<CommitChan> ch;
+  std::thread th;
+  std::mutex mu;
+  std::vector<std::string> got;
+  std::atomic<int> nils{0};
+  explicit Collector(std::shared_ptr<CommitChan> c) : ch(std::move(c)) {
+    th = std::thread([this]() {
+      std::shared_ptr<std::string> v;
+      while (ch->recv(v)) {
+        if (!v) {
+          ++nils;
+          continue;
+        }
+        std::lock_guard<std::mutex> lk(mu);
+        got.push_back(*v);
+      }
+    });
+  }
+  ~Collector() {
+    if (th.joinable()) th.join();
+  }
+  size_t size() {
+    std::lock_guard<std::mutex> lk(mu);
+    return got.size();
+  }
+  std::vector<std::string> snapshot() {
+    std::lock_guard<std::mutex> lk(mu);
+    return got;
+  }
+  bool wait_for(size_t n, int ms = 30000) {
+    for (int t = 0; t < ms / 5; ++t) {
+      if (size() >= n) return true;
+      std::this_thread::sleep_for(std::chrono::milliseconds(5));
+    }
+    return false;
+  }
+};
+
+RaftPipeOptions options(const std::string &core, const std::string &dir, int id, std::shared_ptr<LocalTransport> tr, double tick) {
+  RaftPipeOptions o;
+  o.tick_seconds = tick;
+  o.waldir = dir + "/raftsql-" + std::to_string(id);
+  o.transport = std::move(tr);
+  if (core == "oracle")
+    o.core_factory = [](uint32_t n, uint32_t i) { return std::unique_ptr<Core>(new OracleCore(n, i)); };
+  return o;
+}
+
+void test_single_node(const std::string &core, const std::string &dir) {
+  std::vector<std::string> peers = {"http://127.0.0.1:9021"};  // server/main.go:25 default
+  auto proposeC = std::make_shared<StrChan>();
+  auto rp = NewRaftPipe(1, peers, proposeC, options(core, dir + "/single", 1, std::make_shared<LocalTransport>(), 0.005));
+  std::shared_ptr<std::string> first;
+  CHECK(rp->CommitC->recv(first, 20000) && !first, "the first value on CommitC must be the nil sentinel");
+  Collector col(rp->CommitC);
+  for (int i = 0; i < 20; ++i) proposeC->send("entry-" + std::to_string(i));
+  CHECK(col.wait_for(20), "20 proposals must commit (got %zu)", col.size());
+  auto got = col.snapshot();
+  for (int i = 0; i < 20 && i < (int)got.size(); ++i) CHECK(got[i] == "entry-" + std::to_string(i), "order broken at %d: %s", i, got[i].c_str());
+  CHECK(rp->Close().empty(), "Close() must return no error");
+  std::shared_ptr<std::string> v;
+  CHECK(!rp->CommitC->recv(v), "CommitC must be closed after Close()");
+}
+
+void test_cluster_and_restart(const std::string &core, const std::string &dir) {
+  const std::vector<std::string> peers = {"http://127.0.0.1:10000", "http://127.0.0.1:10001", "http://127.0.0.1:10002"};
+  auto tr = std::make_shared<LocalTransport>();
+  std::vector<std::shared_ptr<StrChan>> prop(3);
+  std::vector<std::unique_ptr<RaftPipe>> rp(3);
+  std::vector<std::unique_ptr<Collector>> col(3);
+  auto start = [&](int i) {
+    prop[i] = std::make_shared<StrChan>();
+    rp[i] = NewRaftPipe(i + 1, peers, prop[i], options(core, dir + "/clus", i + 1, tr, 0.01));
+    col[i].reset(new Collector(rp[i]->CommitC));
+  };
+  for (int i = 0; i < 3; ++i) start(i);
+  // createEntries (raftsql_test.go:54-69): one entry through node 0, then one through every node
+  prop[0]->send("CREATE");
+  for (int i = 0; i < 3; ++i) CHECK(col[i]->wait_for(1), "node %d never saw CREATE", i);
+  for (int i = 0; i < 3; ++i) prop[i]->send("INSERT-" + std::to_string(i));
+  for (int i = 0; i < 3; ++i) CHECK(col[i]->wait_for(4), "node %d committed %zu of 4", i, col[i]->size());
+  auto ref = col[0]->snapshot();
+  for (int i = 1; i < 3; ++i) CHECK(col[i]->snapshot() == ref, "node %d applied a different sequence", i);
+  CHECK(ref.size() == 4 && ref[0] == "CREATE", "unexpected log head");
+  for (int i = 0; i < 3; ++i) CHECK(col[i]->nils.load() == 1, "node %d: %d nil sentinels", i, col[i]->nils.load());
+
+  // TestRestartDB (raftsql_test.go:117-171): stop a FOLLOWER (a proposal forwarded to a dead leader is dropped by
+  // raft, upstream too), add an entry through another node, restart the victim from its WAL
+  int victim = rp[1]->node()->role() != MRQ_ROLE_LEADER ? 1 : 2;
+  int proposer = 3 - victim;
+  CHECK(rp[victim]->Close().empty(), "clean stop of node %d", victim);
+  col[victim].reset();
+  prop[proposer]->send("foo");
+  CHECK(col[proposer]->wait_for(5), "foo must commit with 2 of 3 nodes");
+  CHECK(col[0]->wait_for(5) || victim == 0, "node 0 must apply foo");
+  start(victim);
+  CHECK(col[victim]->wait_for(5), "restarted node must replay 4 entries and catch up to foo (has %zu)", col[victim]->size());
+  auto again = col[victim]->snapshot();
+  CHECK(again.size() == 5 && std::vector<std::string>(again.begin(), again.begin() + 4) == ref, "replay must be the original 4 entries in order");
+  CHECK(again.size() == 5 && again[4] == "foo", "catch-up entry must be foo");
+  CHECK(col[victim]->nils.load() == 1, "exactly one nil sentinel after the replay");
+  for (int i = 0; i < 3; ++i) CHECK(rp[i]->Close().empty(), "Close node %d", i);
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+  if (argc < 3) {
+    std::printf("usage: raftpipe_test oracle|engine <tmpdir>\n");
+    return 2;
+  }
+  const std::string core = argv[1], dir = argv[2];
+  ::mkdir(dir.c_str(), 0750);
+  ::mkdir((dir + "/single").c_str(), 0750);
+  ::mkdir((dir + "/clus").c_str(), 0750);
+  try {
+    test_single_node(core, dir);
+    test_cluster_and_restart(core, dir);
+  } catch (const std::exception &ex) {
+    std::printf("FAIL exception: %s\n", ex.what());
+    ++failures;
+  }
+  std::printf(failures ? "raftpipe_test: %d failure(s)\n" : "raftpipe_test: ok\n", failures);
+  return failures ? 1 : 0;
+}
