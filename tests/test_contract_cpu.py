@@ -1,0 +1,50 @@
+"""Contract checks that need no GPU: the ABI header is valid plain C (what cgo compiles), the bench's reference arm
+prints the JSON line the driver expects, and the repo layout promised in DESIGN.md exists."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_is_plain_c99(tmp_path):
+    src = tmp_path / "abi.c"
+    src.write_text('#include "mrq.h"\n#include "mrq_trace.h"\n'
+                   "int main(void) { mrq_config c; mrq_msg m; mrq_state s; mrq_inbox_packed p; mrq_counters k;\n"
+                   "  (void)c; (void)m; (void)s; (void)p; (void)k;\n"
+                   "  mrq_trace_params t = mrq_trace_preset(5); return (int)(sizeof(mrq_msg) != 48) + (t.lagging_pct != 20); }\n")
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           "-o", str(exe), str(src)])
+    assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_reference_arm_prints_the_contract_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "raft_ticks_per_sec_1Mx5" and line["unit"] == "ticks/s"
+    assert line["higher_is_better"] is True and line["steps"] == 2 and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "ticks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["groups"] == 1 << 20 and line["config"]["replicas"] == 5
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
+                       capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_layout():
+    for p in ("include/mrq.h", "include/mrq_trace.h", "oracle/raft_oracle.c", "oracle/Makefile", "tests/golden/upstream_kats.json",
+              "tests/golden/make_golden.py", "profiles/r01_launches.md", "profiles/r01_results.md", "DESIGN.md", "INTEGRATION.md",
+              "bench.py", "__graft_entry__.py", "raftsql_b200/csrc/mrq_kernels.cuh", "raftsql_b200/csrc/host/raftpipe.hpp",
+              "go/mrq/mrq.go", "go/raftpipe_mrq.go"):
+        assert os.path.exists(os.path.join(ROOT, p)), p
+    assert not os.path.exists(os.path.join(ROOT, "raftsql_b200", "models"))  # not an ML framework layout
+    gi = open(os.path.join(ROOT, ".gitignore")).read()
+    assert "oracle/_ref/" in gi and "*.so" in gi
