@@ -69,7 +69,7 @@ def _handler_for(rdb: RaftDB):
 
 def ServeHttpSqlAPI(port: int, rdb: RaftDB, *, background: bool = False):
     """reference httpapi.go:71-79.  background=True returns the server (tests) instead of blocking forever."""
-    srv = ThreadingHTTPServer(("127.0.0.1", port), _handler_for(rdb))
+    srv = ThreadingHTTPServer(("", port), _handler_for(rdb))  # Addr ":" + port (httpapi.go:73)
     if background:
         threading.Thread(target=srv.serve_forever, daemon=True).start()
         return srv
