@@ -304,10 +304,10 @@ def run_ours(args):
         launches_all = int(lt.item())
     else:
         launches_all = launches
-    # keep the GPU busy ~0.5 s more so the clock sampler sees it under this load even for short K.  The
+    # keep the GPU busy ~2 s more so the clock sampler sees it under this load even for short K.  The
     # repeat count is derived from the max-over-ranks time, so EVERY rank issues the same number of ticks
     # (a per-tick collective would deadlock on a time-based loop).
-    reps = max(4, min(4000, int(0.5 / max(1e-6, 8 * ms / K * 1e-3))))
+    reps = max(4, min(40000, int(2.0 / max(1e-6, 8 * ms / K * 1e-3))))  # ~2 s: several nvidia-smi samples
     for _ in range(reps):
         run_ticks(8, 0)
     eng.synchronize()
