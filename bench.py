@@ -135,11 +135,11 @@ def measured_peak_gbs() -> tuple[float, str]:
 
 # ---------------------------------------------------------------------------------------------------
 def cpu_reference_ticks(G: int, Rr: int, state: dict, inboxes: list, budget_s: float, warmup: int = 1,
-                        steps: int | None = None):
-    """Time the CPU restatement of the reference path (oracle/, 'port') on all host threads."""
+                        steps: int | None = None, nthreads: int | None = None):
+    """Time the CPU restatement of the reference path (oracle/, 'port') on all host threads (or `nthreads`)."""
     import oracle
 
-    nt = oracle.hw_threads()
+    nt = nthreads or oracle.hw_threads()
     orc = oracle.Oracle(G, Rr, seed=SEED)
     orc.import_state(state)
     k = 0
@@ -354,6 +354,8 @@ def run_ours(args):
             tps, nt, n, el, _ = cpu_reference_ticks(G_TOTAL, R, st0, host_ib, budget_s=12.0)
             line["cpu_baseline"] = {"value": tps, "unit": "ticks/s", "cores": nt, "kind": "port",
                                     "sample": f"{n} full ticks over all {G_TOTAL} groups x {R} replicas in {el:.1f} s on {nt} threads"}
+            tps1, _, n1, el1, _ = cpu_reference_ticks(G_TOTAL, R, st0, host_ib, budget_s=3.0, nthreads=1)
+            line["cpu_baseline"]["single_thread"] = {"value": tps1, "cores": 1, "sample": f"{n1} full ticks in {el1:.1f} s"}
         except Exception as ex:  # the baseline must never take the GPU numbers down with it
             line["cpu_baseline"] = {"value": None, "unit": "ticks/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
     if world > 1:

@@ -39,6 +39,13 @@ def test_reference_arm_other_ranks_exit_quietly():
     assert r.returncode == 0 and r.stdout.strip() == ""
 
 
+def test_oracle_selftest_under_asan_ubsan():
+    """The checker itself is run under AddressSanitizer + UBSan (oracle/selftest.c)."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "selftest_asan"], stdout=subprocess.DEVNULL)
+    r = subprocess.run([os.path.join(ROOT, "oracle", "selftest_asan")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "oracle selftest: ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_layout():
     for p in ("include/mrq.h", "include/mrq_trace.h", "oracle/raft_oracle.c", "oracle/Makefile", "tests/golden/upstream_kats.json",
               "tests/golden/make_golden.py", "profiles/r01_launches.md", "profiles/r01_results.md", "DESIGN.md", "INTEGRATION.md",
