@@ -386,6 +386,13 @@ int mrq_create(const mrq_config *cfg, mrq_engine **out) {
     if (prop.major < 10)
       return fail(e, MRQ_E_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", e->device, prop.major, prop.minor);
     g_sm_count = prop.multiProcessorCount;
+    // Experiment knob (off unless set): the tick kernel's evict-last hints may be confined to the persisting-L2
+    // carve-out, which defaults to ~25 MB on B200 (max ~83 MB); MRQ_L2_PERSIST_MB raises the device limit.
+    if (const char *mb = getenv("MRQ_L2_PERSIST_MB")) {
+      size_t want = (size_t)strtoull(mb, nullptr, 10) << 20;
+      if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
+      CK(e, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+    }
     if (cfg->stream) {
       e->stream = (cudaStream_t)cfg->stream;
     } else {
