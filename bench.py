@@ -253,7 +253,7 @@ def run_ours(args):
         eng.tick(t)
     eng.synchronize()
     e2e_slots = min(4, nslots)
-    host_ib = [eng.read_inbox(s) for s in range(e2e_slots)] if rank == 0 or True else []
+    host_ib = [eng.read_inbox(s) for s in range(e2e_slots)]  # every rank runs the e2e leg on its own shard
     eng.import_state(st0)
     eng.tick_count = 0
 

@@ -41,7 +41,8 @@ struct NcclApi {
       if (lib) break;
     }
     if (!lib) {
-      err = std::string("dlopen(libnccl.so.2) failed: ") + (dlerror() ? dlerror() : "?");
+      const char *why = dlerror();  // one call: dlerror() clears the message it returns
+      err = std::string("dlopen(libnccl.so.2) failed: ") + (why ? why : "?");
       return false;
     }
     GetUniqueId = (int (*)(NcclUniqueId *))dlsym(lib, "ncclGetUniqueId");
@@ -286,10 +287,12 @@ int launch_quorum_t(mrq_engine *e, const QuorumArgs &a0, int variant, cudaStream
     const uint64_t ntiles = a.G / kTmaTile;
     const size_t smem = (size_t)kTmaStages * (R + 2) * kTmaTile * 8 + kTmaStages * 8;
     auto kern = quorum_kernel_tma<R, kTmaTile, kTmaStages>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};  // the attribute is per device
+    int dev = 0;
+    CK(e, cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
       CK(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = true;
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     int per_sm = (int)((220 * 1024) / smem);
     if (per_sm < 1) per_sm = 1;
@@ -823,6 +826,7 @@ int mrq_tick_many(mrq_engine *e, const uint32_t *slots, uint32_t n) {
   key.push_back((char)('0' + (e->slow_parity & 1u)));
   key.push_back((char)('0' + e->tick_mode));
   key.push_back((char)('0' + ((e->comm_mode == 1 && e->ipc_attached) ? e->world : 1)));
+  key.push_back((char)('0' + (e->l2_policy ? 1 : 0)));  // a kernel argument, so part of what was captured
   const uint64_t tick0 = e->tick_no, launches0 = e->launches;
   const uint32_t tp0 = e->tick_parity, sp0 = e->slow_parity;
   auto it = e->graphs.find(key);
@@ -1059,6 +1063,9 @@ int mrq_comm_unique_id(uint8_t id_out[MRQ_COMM_ID_BYTES]) {
 }
 
 static int ensure_gather(mrq_engine *e, uint32_t world) {
+  // peers hold CUDA-IPC mappings of the current buffer and graphs hold its address: it cannot be replaced
+  if (e->ipc_attached) return fail(e, MRQ_E_STATE, "the gather buffer is already shared with the peers (mrq_ipc_attach)");
+  if (e->comm) return fail(e, MRQ_E_STATE, "a communicator is already attached to this engine");
   CK(e, cudaStreamSynchronize(e->stream));
   if (e->gathered) CK(e, cudaFree(e->gathered));
   e->gathered = nullptr;
@@ -1106,6 +1113,7 @@ int mrq_ipc_prepare(mrq_engine *e, uint32_t world) {
 
 int mrq_ipc_attach(mrq_engine *e, const uint8_t *handles, uint32_t rank, uint32_t world) {
   if (!e || !handles || world < 1 || world > 8 || rank >= world) return fail(e, MRQ_E_INVAL, "bad ipc arguments");
+  if (e->ipc_attached) return fail(e, MRQ_E_STATE, "mrq_ipc_attach called twice");
   CK(e, cudaSetDevice(e->device));
   for (uint32_t p = 0; p < world; ++p) {
     if (p == rank) {
@@ -1115,7 +1123,13 @@ int mrq_ipc_attach(mrq_engine *e, const uint8_t *handles, uint32_t rank, uint32_
     cudaIpcMemHandle_t h;
     memcpy(&h, handles + (size_t)p * MRQ_IPC_HANDLE_BYTES, sizeof h);
     void *ptr = nullptr;
-    CK(e, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    cudaError_t st = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (st != cudaSuccess) {  // unmap what was opened so far: a failed attach leaves the engine unattached
+      for (uint32_t q = 0; q < p; ++q)
+        if (q != rank && e->peer_gather[q]) cudaIpcCloseMemHandle(e->peer_gather[q]);
+      for (uint32_t q = 0; q < 8; ++q) e->peer_gather[q] = nullptr;
+      return fail(e, MRQ_E_CUDA, "cudaIpcOpenMemHandle(rank %u) failed: %s", p, cudaGetErrorString(st));
+    }
     e->peer_gather[p] = (uint64_t *)ptr;
   }
   e->world = world;
