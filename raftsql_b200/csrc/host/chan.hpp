@@ -9,6 +9,7 @@
 #include <deque>
 #include <mutex>
 #include <stdexcept>
+#include <utility>
 
 namespace raftsql {
 
@@ -22,17 +23,24 @@ class Chan {
   explicit Chan(size_t buffered = 0) : cap_(buffered) {}
 
   // Blocks until a receiver has taken the value (unbuffered) or there is room (buffered).
-  // `stop`, when given, aborts the wait: `select { case ch <- v: case <-stopc: }` (reference raft.go:89-93).
+  // `stop`, when given, aborts the wait: `select { case ch <- v: case <-stopc: }` (reference raft.go:89-93);
+  // an aborted send withdraws its value — as in Go, the receiver never sees it — and returns false.
   bool send(T v, const std::atomic<bool> *stop = nullptr) {
     std::unique_lock<std::mutex> lk(mu_);
     if (closed_) throw ChanClosed();
-    q_.push_back(std::move(v));
-    const unsigned long my = ++sent_;
+    const unsigned long my = ++seq_;
+    q_.emplace_back(my, std::move(v));
     cv_.notify_all();
     if (cap_ && q_.size() <= cap_) return true;
-    while (taken_ < my) {
-      if (closed_) throw ChanClosed();
-      if (stop && stop->load()) return false;
+    while (queued(my)) {
+      if (closed_) {
+        withdraw(my);
+        throw ChanClosed();
+      }
+      if (stop && stop->load()) {
+        withdraw(my);
+        return false;
+      }
       cv_.wait_for(lk, std::chrono::milliseconds(20));
     }
     return true;
@@ -47,9 +55,8 @@ class Chan {
       if (timeout_ms >= 0 && std::chrono::steady_clock::now() >= deadline) throw std::runtime_error("recv timed out");
       cv_.wait_for(lk, std::chrono::milliseconds(20));
     }
-    out = std::move(q_.front());
+    out = std::move(q_.front().second);
     q_.pop_front();
-    ++taken_;
     cv_.notify_all();
     return true;
   }
@@ -65,12 +72,26 @@ class Chan {
   }
 
  private:
+  // the queue is a handful of values at most (one per blocked sender): linear scans are fine
+  bool queued(unsigned long id) const {
+    for (const auto &p : q_)
+      if (p.first == id) return true;
+    return false;
+  }
+  void withdraw(unsigned long id) {
+    for (auto it = q_.begin(); it != q_.end(); ++it)
+      if (it->first == id) {
+        q_.erase(it);
+        return;
+      }
+  }
+
   std::mutex mu_;
   std::condition_variable cv_;
-  std::deque<T> q_;
+  std::deque<std::pair<unsigned long, T>> q_;
   size_t cap_;
   bool closed_ = false;
-  unsigned long sent_ = 0, taken_ = 0;
+  unsigned long seq_ = 0;
 };
 
 }  // namespace raftsql

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <stdexcept>
 
 #include "../../../include/mrq.h"
 
@@ -90,6 +91,9 @@ void Wal::read_all(std::vector<Entry> *ents, bool *has_hs, uint64_t hs[3]) {
   *has_hs = false;
   FILE *f = std::fopen(path_.c_str(), "rb");
   if (!f) return;
+  std::fseek(f, 0, SEEK_END);
+  const long file_size = std::ftell(f);
+  std::fseek(f, 0, SEEK_SET);
   for (;;) {
     char kind;
     uint64_t a, b, c;
@@ -97,6 +101,7 @@ void Wal::read_all(std::vector<Entry> *ents, bool *has_hs, uint64_t hs[3]) {
     if (std::fread(&kind, 1, 1, f) != 1 || std::fread(&a, 8, 1, f) != 1 || std::fread(&b, 8, 1, f) != 1 ||
         std::fread(&c, 8, 1, f) != 1 || std::fread(&len, 4, 1, f) != 1)
       break;
+    if ((long)len > file_size - std::ftell(f)) break;  // torn tail record: its length field outruns the file
     std::string payload(len, '\0');
     if (len && std::fread(&payload[0], 1, len, f) != len) break;  // torn tail record
     if (kind == 'H') {
@@ -176,7 +181,8 @@ std::vector<std::string> HostNode::start() {
   uint64_t hs[3] = {0, 0, 0};
   std::vector<Entry> ents;
   if (old) wal_->read_all(&ents, &has_hs, hs);
-  wal_->open();
+  // "raftsql: create wal error" / "error loading wal" are fatal in the reference (raft.go:102,107,114)
+  if (!wal_->open()) throw std::runtime_error("raftsql: cannot open the wal in " + wal_->dir());
   log_.ents = ents;
   if (has_hs) {  // unlike the reference (raft.go:124 discards it) the HardState is restored
     term_ = hs[0];

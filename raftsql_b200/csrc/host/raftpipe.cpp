@@ -112,6 +112,7 @@ std::string RaftPipe::Close() {
 RaftPipe::~RaftPipe() {
   if (thread_.joinable()) {
     ProposeC->close();
+    ErrorC->close();  // nobody will read it any more: a node that died with an error must not block on reporting it
     thread_.join();
   }
 }

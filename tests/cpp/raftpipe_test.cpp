@@ -176,6 +176,116 @@ void test_cluster_and_restart(const std::string &core, const std::string &dir) {
   for (int i = 0; i < 3; ++i) CHECK(rp[i]->Close().empty(), "Close node %d", i);
 }
 
+// Go channel semantics the seam relies on (raft.go:89-93 `select { case commitC <- v: case <-stopc: }`).
+void test_chan_semantics() {
+  {  // an aborted send withdraws its value: the receiver must never see it
+    Chan<int> ch;
+    std::atomic<bool> stop{false};
+    std::atomic<int> result{-1};
+    std::thread sender([&]() { result = ch.send(7, &stop) ? 1 : 0; });
+    std::this_thread::sleep_for(std::chrono::milliseconds(40));
+    stop = true;
+    sender.join();
+    CHECK(result.load() == 0, "a stopped send must report false");
+    ch.close();
+    int v = 0;
+    CHECK(!ch.recv(v), "the withdrawn value must not be delivered");
+  }
+  {  // unbuffered rendezvous: send returns only after the value was taken; FIFO across blocked senders
+    Chan<int> ch;
+    std::atomic<int> returned{0};
+    std::thread s1([&]() { ch.send(1); ++returned; });
+    std::this_thread::sleep_for(std::chrono::milliseconds(30));
+    std::thread s2([&]() { ch.send(2); ++returned; });
+    std::this_thread::sleep_for(std::chrono::milliseconds(30));
+    CHECK(returned.load() == 0, "unbuffered send returned before any receive");
+    int a = 0, b = 0;
+    CHECK(ch.recv(a, 2000) && ch.recv(b, 2000) && a == 1 && b == 2, "FIFO order across senders (%d, %d)", a, b);
+    s1.join();
+    s2.join();
+    CHECK(returned.load() == 2, "both senders must be released");
+  }
+  {  // close() fails a blocked sender (Go panics) and later sends; buffered values stay drainable
+    Chan<int> ch;
+    std::atomic<bool> threw{false};
+    std::thread s([&]() {
+      try {
+        ch.send(5);
+      } catch (const ChanClosed &) {
+        threw = true;
+      }
+    });
+    std::this_thread::sleep_for(std::chrono::milliseconds(30));
+    ch.close();
+    s.join();
+    CHECK(threw.load(), "send blocked on a channel that gets closed must throw");
+    bool again = false;
+    try {
+      ch.send(6);
+    } catch (const ChanClosed &) {
+      again = true;
+    }
+    CHECK(again, "send on a closed channel must throw");
+    Chan<int> buf(2);
+    buf.send(1);
+    buf.send(2);
+    buf.close();
+    int v = 0;
+    CHECK(buf.recv(v) && v == 1 && buf.recv(v) && v == 2 && !buf.recv(v), "buffered values drain after close");
+  }
+}
+
+// wal.ReadAll tolerates a torn tail (a crash mid-append); a WAL that cannot be opened is fatal (raft.go:102-114).
+void test_wal_recovery(const std::string &dir) {
+  const std::string wdir = dir + "/walrec";
+  {
+    Wal w(wdir);
+    CHECK(w.open(), "open a fresh wal");
+    std::vector<Entry> es(3);
+    for (int i = 0; i < 3; ++i) {
+      es[i].term = 2;
+      es[i].data = "payload-" + std::to_string(i);
+    }
+    const uint64_t hs[3] = {2, 1, 2};
+    w.save(hs, es, 1, false, 0);
+    w.close();
+  }
+  {  // a record header promising 3 GB, then nothing: must be ignored without allocating it
+    FILE *f = std::fopen((wdir + "/wal.bin").c_str(), "ab");
+    const char kind = 'E';
+    const uint64_t a = 4, b = 2, c = 0;
+    const uint32_t len = 0xC0000000u;
+    std::fwrite(&kind, 1, 1, f);
+    std::fwrite(&a, 8, 1, f);
+    std::fwrite(&b, 8, 1, f);
+    std::fwrite(&c, 8, 1, f);
+    std::fwrite(&len, 4, 1, f);
+    std::fwrite("xy", 1, 2, f);
+    std::fclose(f);
+  }
+  Wal w(wdir);
+  std::vector<Entry> ents;
+  bool has_hs = false;
+  uint64_t hs[3] = {0, 0, 0};
+  w.read_all(&ents, &has_hs, hs);
+  CHECK(ents.size() == 3 && ents[2].data == "payload-2" && ents[0].term == 2, "intact prefix must survive a torn tail (%zu entries)", ents.size());
+  CHECK(has_hs && hs[0] == 2 && hs[1] == 1 && hs[2] == 2, "hardstate must survive a torn tail");
+
+  // an unopenable wal directory (a regular file stands where the directory should be) fails start()
+  const std::string blocker = dir + "/not-a-dir";
+  FILE *f = std::fopen(blocker.c_str(), "wb");
+  std::fclose(f);
+  auto tr = std::make_shared<LocalTransport>();
+  HostNode node(std::unique_ptr<Core>(new OracleCore(1, 1)), 1, 1, tr, blocker);
+  bool threw = false;
+  try {
+    node.start();
+  } catch (const std::runtime_error &) {
+    threw = true;
+  }
+  CHECK(threw, "start() must fail when the wal cannot be opened");
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -188,6 +298,8 @@ int main(int argc, char **argv) {
   ::mkdir((dir + "/single").c_str(), 0750);
   ::mkdir((dir + "/clus").c_str(), 0750);
   try {
+    test_chan_semantics();
+    test_wal_recovery(dir);
     test_single_node(core, dir);
     test_cluster_and_restart(core, dir);
   } catch (const std::exception &ex) {
