@@ -124,7 +124,10 @@ class Wal:
             (n,) = struct.unpack_from("<I", buf, off)
             if off + 4 + n > len(buf):
                 break  # torn tail record
-            rec = json.loads(buf[off + 4: off + 4 + n])
+            try:
+                rec = json.loads(buf[off + 4: off + 4 + n])
+            except ValueError:
+                break  # a record whose bytes never all reached the disk: everything before it stands
             off += 4 + n
             if "hs" in rec:
                 hs = tuple(rec["hs"])
