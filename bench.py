@@ -371,9 +371,18 @@ def run_ours(args):
         e2e = bench_e2e(eng, st0, host_ib, K, W, dist=dist, torch=torch)
         if rank == 0:
             line["e2e"] = e2e
+    eng.close()
+    if rank == 0 and world == 1 and not fast and isinstance(line.get("e2e"), dict) and os.environ.get("MRQ_BENCH_NO_E2E8") != "1":
+        # the byte form of the packed inbox, measured in a process of its own once everything above is final;
+        # it becomes the e2e figure only if it verified itself against the wide form and is faster
+        r8 = e2e8_from_child(K)
+        line["e2e"]["packed8"] = r8
+        if r8.get("equals_wide_form") is True and r8.get("value", 0) > line["e2e"]["value"]:
+            for k in ("value", "h2d_bytes_per_step", "d2h_bytes_per_step", "steps", "api"):
+                line["e2e"][k] = r8[k]
+        line["e2e"]["packed_equals_wide"] = bool(line["e2e"]["packed_equals_wide"] and r8.get("equals_wide_form", True))
     if rank == 0:
         print(json.dumps(line))
-    eng.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -532,6 +541,99 @@ def bench_e2e(eng, st0, host_ib, K, W, dist=None, torch=None):
     return res
 
 
+def run_e2e8_child(args):
+    """The end-to-end leg on the BYTE form of the packed inbox (include/mrq_packed8.h: R-1 sender bytes + 1
+    proposal byte per group, window sliding on the device), N = 1.  It runs in a process of its own, launched by
+    run_ours after the main numbers are final: this form's device kernel is the newest code in the library, and
+    a fault in it must not be able to touch them.  Prints one JSON object.
+
+    Every step ships a DIFFERENT tick of the trace (S distinct frames built in order, as a live host would: the
+    sliding window only ever moves forward), and the result is accepted only if the commit indices it produces
+    equal the ones the same S ticks produce from the device-generated wide inbox."""
+    import ctypes as C
+
+    from raftsql_b200 import Engine, preset_trace
+    from raftsql_b200 import _ffi as F
+    from raftsql_b200.packed import Pack8, PinnedArray
+
+    G, Rr = G_TOTAL, R
+    S = max(4, min(args.steps, 64))
+    eng = Engine(G, Rr, seed=SEED, group_base=0, device=int(os.environ.get("LOCAL_RANK", "0")), inbox_slots=2)
+    st0 = steady_state(G, Rr, 0, SEED)
+    eng.import_state(st0)
+    p = preset_trace(3)
+    base0 = (st0["last_index"] - np.uint64(40)).astype(np.uint64)
+    pk = Pack8(st0["self_id"], base0, st0["term"], Rr)
+    views, keep, h2d, escapes = [], [], 0, 0
+    for t in range(S):  # the trace, tick by tick (each tick's acks depend on that tick's state), framed as it goes
+        eng.gen_trace(p, t, slot=0)
+        ib = eng.read_inbox(0)
+        pw, pp = PinnedArray((Rr - 1, G), np.uint8), PinnedArray((G,), np.uint8)
+        _, _, wide = pk.frame(ib, word_out=pw.array, prop8_out=pp.array)
+        arr = (F.Msg * max(1, len(wide)))()
+        for i, (g, frm, ty, term, index, logterm, commit) in enumerate(wide):
+            arr[i].group, arr[i].from_, arr[i].type = g, frm, ty
+            arr[i].term, arr[i].index, arr[i].logterm, arr[i].commit = term, index, logterm, commit
+        v = F.InboxPacked()
+        v.word, v.prop_count8 = pw.ptr, C.cast(pp.ptr, F.u8p)
+        v.wide, v.n_wide, v.word_bits = arr, len(wide), 8
+        views.append(v)
+        keep += [pw, pp, arr]
+        escapes += len(wide)
+        h2d = max(h2d, int(pw.nbytes + pp.nbytes + len(wide) * C.sizeof(F.Msg)))
+        eng.tick(0)
+    commits_ref = eng.sync_commits().copy()  # what these S ticks commit, from the wide device-generated inbox
+
+    L, h = eng.L, eng.h
+    delta = PinnedArray((G,), np.uint8)
+    dptr = C.cast(delta.ptr, F.u8p)
+
+    def run(nsteps, accumulate):
+        eng.import_state(st0)
+        eng.tick_count = 0
+        eng.set_packed_base(base0, st0["term"])
+        base = eng.sync_commits().copy()  # a full read also rebases the delta drain
+        acc = np.zeros(G, np.uint64)
+        t0 = time.perf_counter()
+        rc = L.mrq_post_inbox_packed(h, 0, C.byref(views[0]))
+        for k in range(nsteps):
+            rc |= L.mrq_tick(h, k % 2)
+            rc |= L.mrq_drain_commit_deltas(h, dptr)
+            if k + 1 < nsteps:  # next tick's frame starts copying underneath this tick
+                rc |= L.mrq_post_inbox_packed(h, (k + 1) % 2, C.byref(views[k + 1]))
+            rc |= L.mrq_drain_wait(h)  # this step's result is on the host
+            if rc != 0:
+                raise RuntimeError("C-ABI call failed: " + (L.mrq_last_error(h) or b"?").decode())
+            if accumulate:
+                assert delta.array.max() < 255
+                acc += delta.array
+        el = time.perf_counter() - t0
+        eng.synchronize()
+        return el, base + acc
+
+    run(3, False)
+    _, commits = run(S, True)
+    same = bool(np.array_equal(commits, commits_ref)) and bool(np.array_equal(commits, eng.sync_commits()))
+    el, _ = run(S, False)
+    res = {"value": S / el, "unit": "ticks/s", "steps": S, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(delta.nbytes),
+           "equals_wide_form": same, "escapes": escapes, "h2d_GBps_per_gpu": h2d * S / el / 1e9,
+           "api": "mrq_pack8 frames (pinned, 8-bit form, copy stream) + mrq_post_inbox_packed + mrq_tick + "
+                  "mrq_drain_commit_deltas/mrq_drain_wait (1 B/group)"}
+    print(json.dumps(res))
+    eng.close()
+
+
+def e2e8_from_child(steps: int) -> dict:
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--e2e8-child", "--steps", str(steps)],
+                           capture_output=True, text=True, timeout=300, cwd=ROOT)
+        if r.returncode != 0:
+            return {"error": f"exit {r.returncode}: {(r.stderr or r.stdout).strip()[-300:]}"}
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as ex:  # noqa: BLE001 — whatever happens there, the main line stands
+        return {"error": f"{type(ex).__name__}: {ex}"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -546,8 +648,11 @@ def main():
                     help="L2 residency hints of the tick kernel (default: the engine's, on)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="CUDA-graph replay of the tick sequence (auto: only for small shards)")
+    ap.add_argument("--e2e8-child", action="store_true", help=argparse.SUPPRESS)  # internal: see run_e2e8_child
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.e2e8_child:
+        run_e2e8_child(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -194,21 +194,43 @@ int mrq_post_inbox_delta(mrq_engine *e, uint32_t slot, const mrq_msg *msgs, size
  * bits 3..4 term code as above, bits 5..15 payload p (ack index / heartbeat commit = base_index[g] + p).
  * MSG_VOTE and MSG_APP always escape.
  *
+ * Byte form (word_bits = 8; `word` then points at uint8_t[R-1][G]): one byte per REMOTE sender — the row of
+ * each group's own replica slot is left out — with a 64-entry index window that slides by a rule both sides
+ * apply to the bytes alone (the device advances base_index itself).  Codec, row mapping and the window rule:
+ * include/mrq_packed8.h; build frames with mrq_pack8 below.
+ *
  * ASYNCHRONOUS: the copies run on the engine's copy stream so that the next tick's H2D overlaps the
  * current tick; `word`, `prop_count8` and `wide` should be page-locked (mrq_alloc_pinned) and must stay
  * valid and unmodified until a blocking call (mrq_sync_* / mrq_synchronize) made after the mrq_tick
  * that consumes the slot has returned.                                                         */
 typedef struct mrq_inbox_packed {
-  const void *word;           /* [R][G] uint32_t (word_bits 32 or 0) or uint16_t (word_bits 16) */
+  const void *word;           /* [R][G] uint32_t (word_bits 32 or 0) / uint16_t (16), or [R-1][G] uint8_t (8) */
   const uint8_t *prop_count8; /* [G] proposals (0..255) or NULL */
   const mrq_msg *wide;        /* escape list */
   size_t n_wide;
-  uint32_t word_bits;         /* 0 or 32: 32-bit words; 16: 16-bit words */
+  uint32_t word_bits;         /* 0 or 32: 32-bit words; 16: 16-bit words; 8: the byte form */
   uint32_t reserved;
 } mrq_inbox_packed;
 int mrq_post_inbox_packed(mrq_engine *e, uint32_t slot, const mrq_inbox_packed *in);
 /* Dense [G] decode bases for the packed form (NULL keeps the current column).  Blocking. */
 int mrq_set_packed_base(mrq_engine *e, const uint64_t *base_index, const uint64_t *base_term);
+
+/* Host-side frame builder for the byte form: PURE CPU CODE (no engine, no device; usable from any thread).
+ * Encodes the wide dense inbox `in` ([R][G] columns; prop_count may be NULL) of groups whose own ids are
+ * self_id[G] (1..R) into word_out[R-1][G] (+ prop8_out[G] if not NULL), appends what does not fit to wide_out
+ * (at most wide_cap entries; *n_wide = how many were needed) and slides base_index[G] exactly as the device
+ * will when it decodes the frame — call it once per frame, in posting order, on the host's copy of the base
+ * that was last given to mrq_set_packed_base.  MRQ_E_INVAL: bad arguments, more than 255 proposals for a
+ * group, or wide_cap too small (then nothing was changed: retry with *n_wide entries).               */
+int mrq_pack8(const mrq_inbox *in, const uint8_t *self_id, uint64_t n_groups, uint32_t n_replicas, uint64_t *base_index,
+              const uint64_t *base_term, uint8_t *word_out, uint8_t *prop8_out, mrq_msg *wide_out, size_t wide_cap,
+              size_t *n_wide);
+/* The decode the device performs, on the host (same inline codec): word[R-1][G] -> the wide dense columns of
+ * `out` ([R][G]; escaped and empty slots get type 0; only the columns Step() reads for a type are written,
+ * the others are left as they were) and the slid base_index.  For tests and for debugging a frame builder. */
+struct mrq_inbox_out;
+int mrq_unpack8(const uint8_t *word, const uint8_t *self_id, uint64_t n_groups, uint32_t n_replicas, uint64_t *base_index,
+                const uint64_t *base_term, const struct mrq_inbox_out *out);
 
 /* Proposals only (node.Propose, reference raft.go:211-215): sparse (group, count) pairs added to
  * inbox slot `slot`'s prop_count.                                                             */

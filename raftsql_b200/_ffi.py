@@ -111,6 +111,9 @@ SIGNATURES = {
     "mrq_post_inbox_delta": (C.c_int, [_EP, C.c_uint32, C.POINTER(Msg), C.c_size_t, C.c_int]),
     "mrq_post_inbox_packed": (C.c_int, [_EP, C.c_uint32, C.POINTER(InboxPacked)]),
     "mrq_set_packed_base": (C.c_int, [_EP, u64p, u64p]),
+    "mrq_pack8": (C.c_int, [C.POINTER(Inbox), u8p, C.c_uint64, C.c_uint32, u64p, u64p, u8p, u8p, C.POINTER(Msg), C.c_size_t,
+                            C.POINTER(C.c_size_t)]),
+    "mrq_unpack8": (C.c_int, [u8p, u8p, C.c_uint64, C.c_uint32, u64p, u64p, C.POINTER(InboxOut)]),
     "mrq_propose": (C.c_int, [_EP, C.c_uint32, u64p, u32p, C.c_size_t]),
     "mrq_clear_inbox": (C.c_int, [_EP, C.c_uint32]),
     "mrq_tick": (C.c_int, [_EP, C.c_uint32]),

@@ -678,10 +678,11 @@ int mrq_post_inbox_packed(mrq_engine *e, uint32_t slot, const mrq_inbox_packed *
   CK(e, cudaSetDevice(e->device));
   if (e->G == 0) return MRQ_OK;
   const uint32_t bits = in->word_bits ? in->word_bits : 32u;
-  if (bits != 16u && bits != 32u) return fail(e, MRQ_E_INVAL, "word_bits must be 16 or 32");
+  if (bits != 8u && bits != 16u && bits != 32u) return fail(e, MRQ_E_INVAL, "word_bits must be 8, 16 or 32");
   if (in->n_wide && !in->wide) return fail(e, MRQ_E_INVAL, "n_wide > 0 but wide == NULL");
   const size_t wsz = bits / 8;
-  const size_t wbytes = ((e->gs * e->R * wsz + 255) / 256) * 256, pbytes = ((e->gs + 255) / 256) * 256;
+  const size_t rows = bits == 8u ? e->R - 1u : e->R;  // the byte form leaves each group's own sender row out
+  const size_t wbytes = ((e->gs * rows * wsz + 255) / 256) * 256, pbytes = ((e->gs + 255) / 256) * 256;
   const size_t xbytes = in->n_wide * sizeof(mrq_msg);
   // The copy runs on its own stream into a per-slot staging buffer, so the H2D of the NEXT tick's inbox
   // overlaps this tick's kernels and drain; events order copy -> unpack (main stream) -> reuse of the stage.
@@ -707,7 +708,7 @@ int mrq_post_inbox_packed(mrq_engine *e, uint32_t slot, const mrq_inbox_packed *
   uint8_t *d_prop = d_word + wbytes;
   MsgRec *d_wide = (MsgRec *)(d_word + wbytes + pbytes);
   if (sg.used) CK(e, cudaStreamWaitEvent(e->copy_stream, sg.consumed, 0));
-  CK(e, cudaMemcpy2DAsync(d_word, e->gs * wsz, in->word, e->G * wsz, e->G * wsz, e->R, cudaMemcpyHostToDevice, e->copy_stream));
+  if (rows) CK(e, cudaMemcpy2DAsync(d_word, e->gs * wsz, in->word, e->G * wsz, e->G * wsz, rows, cudaMemcpyHostToDevice, e->copy_stream));
   if (in->prop_count8) CK(e, cudaMemcpyAsync(d_prop, in->prop_count8, e->G, cudaMemcpyHostToDevice, e->copy_stream));
   if (in->n_wide) CK(e, cudaMemcpyAsync(d_wide, in->wide, xbytes, cudaMemcpyHostToDevice, e->copy_stream));
   CK(e, cudaEventRecord(sg.copied, e->copy_stream));
@@ -715,6 +716,9 @@ int mrq_post_inbox_packed(mrq_engine *e, uint32_t slot, const mrq_inbox_packed *
   if (bits == 32u) {
     unpack_inbox_kernel<<<nblocks(e->G), 256, 0, e->stream>>>(e->inbox[slot].view(), e->pk_base_index, e->pk_base_term, e->gs,
                                                             e->G, e->R, (const uint32_t *)d_word, in->prop_count8 ? d_prop : nullptr);
+  } else if (bits == 8u) {
+    unpack8_inbox_kernel<<<nblocks(e->G), 256, 0, e->stream>>>(e->inbox[slot].view(), e->s.meta, e->pk_base_index, e->pk_base_term,
+                                                             e->gs, e->G, e->R, d_word, in->prop_count8 ? d_prop : nullptr);
   } else {
     unpack16_inbox_kernel<<<nblocks(e->G), 256, 0, e->stream>>>(e->inbox[slot].view(), e->pk_base_index, e->pk_base_term, e->gs,
                                                               e->G, e->R, (const uint16_t *)d_word, in->prop_count8 ? d_prop : nullptr);
@@ -738,6 +742,93 @@ int mrq_set_packed_base(mrq_engine *e, const uint64_t *base_index, const uint64_
   if (base_index) CK(e, cudaMemcpyAsync(e->pk_base_index, base_index, e->G * 8, cudaMemcpyHostToDevice, e->stream));
   if (base_term) CK(e, cudaMemcpyAsync(e->pk_base_term, base_term, e->G * 8, cudaMemcpyHostToDevice, e->stream));
   CK(e, cudaStreamSynchronize(e->stream));
+  return MRQ_OK;
+}
+
+// ---- the byte form's host side: plain CPU code around the shared codec (include/mrq_packed8.h) ----------------
+int mrq_pack8(const mrq_inbox *in, const uint8_t *self_id, uint64_t G, uint32_t R, uint64_t *base_index, const uint64_t *base_term,
+              uint8_t *word_out, uint8_t *prop8_out, mrq_msg *wide_out, size_t wide_cap, size_t *n_wide) {
+  if (!in || !in->type || !in->term || !in->index || !in->commit || !self_id || !base_index || !base_term || !n_wide)
+    return fail(nullptr, MRQ_E_INVAL, "mrq_pack8: null argument");
+  if (R < 1 || R > MRQ_MAX_REPLICAS) return fail(nullptr, MRQ_E_INVAL, "mrq_pack8: n_replicas %u outside 1..%u", R, MRQ_MAX_REPLICAS);
+  if (R > 1 && !word_out) return fail(nullptr, MRQ_E_INVAL, "mrq_pack8: null word_out");
+  // pass 1 (nothing written): what escapes, and are the proposal counts representable
+  size_t need = 0;
+  for (uint64_t g = 0; g < G; ++g) {
+    if (prop8_out && in->prop_count && in->prop_count[g] > 255u)
+      return fail(nullptr, MRQ_E_INVAL, "mrq_pack8: group %llu has %u proposals; the packed forms carry at most 255", (unsigned long long)g,
+                  in->prop_count[g]);
+    for (uint32_t r = 0; r < R; ++r) {
+      const uint64_t o = (uint64_t)r * G + g;
+      if ((in->type[o] & MRQ_MSG_TYPE_MASK) == 0) continue;
+      if (mrq_p8_row(r, self_id[g], R) >= R - 1u) continue;  // addressed from the group's own slot: never stepped
+      if (mrq_p8_encode(in->type[o], in->term[o], in->index[o], in->commit[o], base_index[g], base_term[g]) == MRQ_P8_ESCAPE) ++need;
+    }
+  }
+  *n_wide = need;
+  if (need > wide_cap || (need && !wide_out)) return fail(nullptr, MRQ_E_INVAL, "mrq_pack8: %zu escapes, room for %zu", need, wide_cap);
+  // pass 2: bytes, escapes, window
+  size_t nw = 0;
+  for (uint64_t g = 0; g < G; ++g) {
+    uint32_t min_ack = MRQ_P8_NO_ACK;
+    const uint64_t bi = base_index[g], bt = base_term[g];
+    for (uint32_t r = 0; r < R; ++r) {
+      const uint32_t row = mrq_p8_row(r, self_id[g], R);
+      if (row >= R - 1u) continue;
+      const uint64_t o = (uint64_t)r * G + g;
+      const uint8_t b = mrq_p8_encode(in->type[o], in->term[o], in->index[o], in->commit[o], bi, bt);
+      word_out[(uint64_t)row * G + g] = b;
+      if (b == MRQ_P8_ESCAPE) {
+        mrq_msg &m = wide_out[nw++];
+        memset(&m, 0, sizeof m);
+        m.group = g;
+        m.from = (uint8_t)(r + 1u);
+        m.type = in->type[o];
+        m.term = in->term[o];
+        m.index = in->index[o];
+        m.logterm = in->logterm ? in->logterm[o] : 0;
+        m.commit = in->commit[o];
+      } else if ((b & 3u) == 1u) {
+        const uint32_t p = b >> 2;
+        min_ack = p < min_ack ? p : min_ack;
+      }
+    }
+    base_index[g] = mrq_p8_next_base(bi, min_ack);
+    if (prop8_out) prop8_out[g] = in->prop_count ? (uint8_t)in->prop_count[g] : 0;
+  }
+  return MRQ_OK;
+}
+
+int mrq_unpack8(const uint8_t *word, const uint8_t *self_id, uint64_t G, uint32_t R, uint64_t *base_index, const uint64_t *base_term,
+                const mrq_inbox_out *out) {
+  if (!self_id || !base_index || !base_term || !out || !out->type || !out->term || !out->index || !out->commit)
+    return fail(nullptr, MRQ_E_INVAL, "mrq_unpack8: null argument");
+  if (R < 1 || R > MRQ_MAX_REPLICAS || (R > 1 && !word)) return fail(nullptr, MRQ_E_INVAL, "mrq_unpack8: bad arguments");
+  for (uint64_t g = 0; g < G; ++g) {  // the body of unpack8_inbox_kernel, one group at a time
+    const uint64_t bi = base_index[g], bt = base_term[g];
+    uint32_t min_ack = MRQ_P8_NO_ACK;
+    for (uint32_t r = 0; r < R; ++r) {
+      const uint64_t o = (uint64_t)r * G + g;
+      const uint32_t row = mrq_p8_row(r, self_id[g], R);
+      if (row >= R - 1u) {
+        out->type[o] = 0;
+        continue;
+      }
+      const mrq_p8_cell c = mrq_p8_decode(word[(uint64_t)row * G + g], bi);
+      out->type[o] = c.type;
+      if (c.type == 0) continue;
+      out->term[o] = bt;
+      if (c.is_ack) {
+        out->index[o] = c.value;
+        min_ack = c.pay < min_ack ? c.pay : min_ack;
+      } else if (c.is_hb) {
+        out->commit[o] = c.value;
+      } else {
+        out->index[o] = 0;
+      }
+    }
+    base_index[g] = mrq_p8_next_base(bi, min_ack);
+  }
   return MRQ_OK;
 }
 

@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #include "../../include/mrq.h"
+#include "../../include/mrq_packed8.h"
 #include "../../include/mrq_trace.h"
 
 namespace mrq {
@@ -1207,6 +1208,43 @@ __global__ void __launch_bounds__(256) unpack16_inbox_kernel(InboxView in, const
       in.index[o] = 0;
     }
   }
+  if (in.prop) in.prop[i] = prop8 ? prop8[i] : 0u;
+}
+
+// Byte form (include/mrq_packed8.h): R-1 rows of one byte per remote sender, the row of the group's own slot
+// left out (the own id is the static `self` field of meta: it never changes while the engine runs, so the
+// decode is still independent of anything a pipelined host could be behind on).  Also slides the window:
+// base_index is read, used for this frame, and advanced for the next one.
+__global__ void __launch_bounds__(256) unpack8_inbox_kernel(InboxView in, const uint64_t *meta, uint64_t *base_index,
+                                                             const uint64_t *base_term, uint64_t gs, uint64_t G,
+                                                             uint32_t R, const uint8_t *word, const uint8_t *prop8) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G) return;
+  const uint32_t self = meta_unpack(meta[i]).self;
+  const uint64_t bi = base_index[i], bt = base_term[i];
+  uint32_t min_ack = MRQ_P8_NO_ACK;
+  for (uint32_t r = 0; r < R; ++r) {
+    const uint64_t o = (uint64_t)r * gs + i;
+    const uint32_t row = mrq_p8_row(r, self, R);
+    if (row >= R - 1u) {  // the group's own slot (or an id outside 1..R): nothing is ever sent from there
+      in.type[o] = 0;
+      continue;
+    }
+    const mrq_p8_cell c = mrq_p8_decode(word[(uint64_t)row * gs + i], bi);
+    in.type[o] = c.type;
+    if (c.type == 0) continue;  // none, or escaped to the wide list (scattered afterwards)
+    in.term[o] = bt;
+    if (c.is_ack) {
+      in.index[o] = c.value;
+      min_ack = c.pay < min_ack ? c.pay : min_ack;
+    } else if (c.is_hb) {
+      in.commit[o] = c.value;
+    } else {
+      in.index[o] = 0;
+    }
+  }
+  const uint64_t nb = mrq_p8_next_base(bi, min_ack);
+  if (nb != bi) base_index[i] = nb;
   if (in.prop) in.prop[i] = prop8 ? prop8[i] : 0u;
 }
 

@@ -153,13 +153,17 @@ class Engine:
         self._ck(self.L.mrq_post_inbox_delta(self.h, slot, arr, len(msgs), int(accumulate)))
 
     def post_inbox_packed(self, word: np.ndarray, prop8: np.ndarray | None = None, wide=(), slot: int = 0):
-        """word: uint32 or uint16 [R][G] (raftsql_b200.packed.pack_inbox / pack_inbox16).  The copy is
-        asynchronous: this convenience wrapper synchronises before returning so numpy temporaries are safe;
-        hosts that pipeline call mrq_post_inbox_packed directly with pinned buffers (see bench.py)."""
-        assert word.dtype in (np.uint32, np.uint16) and word.flags["C_CONTIGUOUS"]
+        """word: uint32 or uint16 [R][G] (raftsql_b200.packed.pack_inbox / pack_inbox16), or uint8 [R-1][G] (the
+        byte form, raftsql_b200.packed.Pack8).  The copy is asynchronous: this convenience wrapper synchronises
+        before returning so numpy temporaries are safe; hosts that pipeline call mrq_post_inbox_packed directly
+        with pinned buffers (see bench.py)."""
+        assert word.dtype in (np.uint32, np.uint16, np.uint8) and word.flags["C_CONTIGUOUS"]
+        rows = self.R - 1 if word.dtype == np.uint8 else self.R
+        assert word.shape == (rows, self.G), f"word must be [{rows}][{self.G}]"
         v = F.InboxPacked()
-        v.word, v.prop_count8 = word.ctypes.data, _p(prop8, F.u8p)
-        v.word_bits = 16 if word.dtype == np.uint16 else 32
+        keep = word if word.size else np.zeros(1, np.uint8)  # R = 1 in the byte form: no sender rows at all
+        v.word, v.prop_count8 = keep.ctypes.data, _p(prop8, F.u8p)
+        v.word_bits = 8 * word.dtype.itemsize
         arr = (F.Msg * max(1, len(wide)))()
         for i, m in enumerate(wide):
             g, frm, ty, term, index, logterm, commit = m

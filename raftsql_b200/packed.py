@@ -98,6 +98,77 @@ def pack_inbox16(ib: dict, base_index: np.ndarray, base_term: np.ndarray):
     return np.ascontiguousarray(word), prop8, wide
 
 
+def _p(a: np.ndarray, ct):
+    return a.ctypes.data_as(ct)
+
+
+class Pack8:
+    """Frame builder for the byte form (include/mrq_packed8.h; `mrq_pack8` in libmrq.so — host CPU code).
+
+    Keeps the host's copy of the sliding window base: construct it with the base columns handed to
+    `mrq_set_packed_base`, then call `frame()` once per inbox, in posting order."""
+
+    def __init__(self, self_id: np.ndarray, base_index: np.ndarray, base_term: np.ndarray, n_replicas: int):
+        self.L = F.load()
+        self.R = int(n_replicas)
+        self.G = int(self_id.shape[0])
+        self.self_id = np.ascontiguousarray(self_id, np.uint8)
+        self.base_index = np.ascontiguousarray(base_index, np.uint64).copy()
+        self.base_term = np.ascontiguousarray(base_term, np.uint64).copy()
+
+    def frame(self, ib: dict, word_out: np.ndarray | None = None, prop8_out: np.ndarray | None = None):
+        """-> (word[R-1][G] uint8, prop8[G] uint8 or None, wide list of mrq_msg tuples).  Slides the window."""
+        G, Rr = self.G, self.R
+        cols = {k: np.ascontiguousarray(ib[k], dt) for k, dt in (("type", np.uint8), ("term", np.uint64), ("index", np.uint64),
+                                                                  ("logterm", np.uint64), ("commit", np.uint64))}
+        assert cols["type"].shape == (Rr, G)
+        prop = ib.get("prop_count")
+        prop = None if prop is None else np.ascontiguousarray(prop, np.uint32)
+        view = F.Inbox(_p(cols["type"], F.u8p), _p(cols["term"], F.u64p), _p(cols["index"], F.u64p), _p(cols["logterm"], F.u64p),
+                       _p(cols["commit"], F.u64p), _p(prop, F.u32p) if prop is not None else None)
+        word = word_out if word_out is not None else np.zeros((max(Rr - 1, 0), G), np.uint8)
+        assert word.dtype == np.uint8 and word.shape == (max(Rr - 1, 0), G) and word.flags.c_contiguous
+        p8 = None
+        if prop is not None:
+            p8 = prop8_out if prop8_out is not None else np.zeros(G, np.uint8)
+        n_wide = C.c_size_t(0)
+        cap = 0
+        wide = (F.Msg * 1)()
+        while True:
+            rc = self.L.mrq_pack8(C.byref(view), _p(self.self_id, F.u8p), G, Rr, _p(self.base_index, F.u64p),
+                                  _p(self.base_term, F.u64p), _p(word, F.u8p) if word.size else None,
+                                  _p(p8, F.u8p) if p8 is not None else None, wide, cap, C.byref(n_wide))
+            if rc == F.MRQ_OK:
+                break
+            if n_wide.value > cap:  # the escape list was too small: nothing was changed, retry with room
+                cap = n_wide.value
+                wide = (F.Msg * cap)()
+                continue
+            raise ValueError((self.L.mrq_last_error(None) or b"mrq_pack8 failed").decode())
+        msgs = [(int(m.group), int(m.from_), int(m.type), int(m.term), int(m.index), int(m.logterm), int(m.commit))
+                for m in wide[: n_wide.value]]
+        return word, p8, msgs
+
+
+def unpack8(word: np.ndarray, self_id: np.ndarray, base_index: np.ndarray, base_term: np.ndarray, n_replicas: int):
+    """`mrq_unpack8`: the device's decode of one byte-form frame, on the host.  -> (wide dense columns, slid base)."""
+    L = F.load()
+    G = int(self_id.shape[0])
+    out = {"type": np.zeros((n_replicas, G), np.uint8)}
+    for k in ("term", "index", "logterm", "commit"):
+        out[k] = np.zeros((n_replicas, G), np.uint64)
+    base = np.ascontiguousarray(base_index, np.uint64).copy()
+    bt = np.ascontiguousarray(base_term, np.uint64)
+    sid = np.ascontiguousarray(self_id, np.uint8)
+    w = np.ascontiguousarray(word, np.uint8)
+    view = F.InboxOut(_p(out["type"], F.u8p), _p(out["term"], F.u64p), _p(out["index"], F.u64p), _p(out["logterm"], F.u64p),
+                      _p(out["commit"], F.u64p), None)
+    rc = L.mrq_unpack8(_p(w, F.u8p) if w.size else None, _p(sid, F.u8p), G, n_replicas, _p(base, F.u64p), _p(bt, F.u64p), C.byref(view))
+    if rc != F.MRQ_OK:
+        raise ValueError((L.mrq_last_error(None) or b"mrq_unpack8 failed").decode())
+    return out, base
+
+
 class PinnedArray:
     """A numpy array over page-locked host memory from mrq_alloc_pinned (asynchronous H2D / D2H)."""
 
