@@ -286,6 +286,76 @@ void test_wal_recovery(const std::string &dir) {
   CHECK(threw, "start() must fail when the wal cannot be opened");
 }
 
+// upstream raft_test.go TestHandleMsgApp (recalled; each row re-derived from raftLog.maybeAppend / commitTo in
+// tests/test_hostnode_kat_cpu.py, which runs the same table over the Python host): follower of term 2 with the log
+// [1:t1, 2:t2], committed 0; the host resolves the append against its log, the core applies the outcome.
+void test_handle_msgapp_table(const std::string &dir) {
+  struct Row {
+    uint64_t index, logterm, commit;
+    std::vector<uint64_t> ents;
+    uint64_t windex, wcommit;
+    bool wreject;
+  };
+  const std::vector<Row> rows = {
+      {2, 3, 3, {}, 2, 0, true},     {3, 3, 3, {}, 2, 0, true},     {1, 1, 1, {}, 2, 1, false},    {0, 0, 1, {2}, 1, 1, false},
+      {2, 2, 3, {2, 2}, 4, 3, false}, {2, 2, 4, {2}, 3, 3, false},   {1, 1, 4, {2}, 2, 2, false},   {1, 1, 3, {}, 2, 1, false},
+      {1, 1, 3, {2}, 2, 2, false},   {2, 2, 3, {}, 2, 2, false},    {2, 2, 4, {}, 2, 2, false},
+  };
+  for (size_t k = 0; k < rows.size(); ++k) {
+    const Row &r = rows[k];
+    const std::string wdir = dir + "/kat-" + std::to_string(k);
+    {
+      Wal w(wdir);
+      CHECK(w.open(), "open wal");
+      std::vector<Entry> es(2);
+      es[0].term = 1;
+      es[0].data = "a";
+      es[1].term = 2;
+      es[1].data = "b";
+      const uint64_t hs[3] = {2, 0, 0};
+      w.save(hs, es, 1, false, 0);
+    }
+    auto tr = std::make_shared<LocalTransport>();
+    tr->add(2);
+    HostNode node(std::unique_ptr<Core>(new OracleCore(3, 1)), 1, 3, tr, wdir);
+    node.start();
+    raftsql::Message m;  // (the oracle's C header has a Message of its own)
+    m.type = kMsgApp;
+    m.to = 1;
+    m.from = 2;
+    m.term = 2;
+    m.index = r.index;
+    m.logterm = r.logterm;
+    m.commit = r.commit;
+    for (uint64_t t : r.ents) {
+      Entry e;
+      e.term = t;
+      e.data = "y";
+      m.entries.push_back(e);
+    }
+    tr->send({m});
+    node.step_tick();
+    const std::vector<raftsql::Message> rep = tr->drain(2);
+    CHECK(rep.size() == 1 && rep[0].type == kMsgAppResp && rep[0].term == 2, "row %zu: one MsgAppResp of term 2", k);
+    if (rep.size() != 1) continue;
+    CHECK(rep[0].reject == r.wreject, "row %zu: reject", k);
+    if (r.wreject)
+      CHECK(rep[0].index == r.index && rep[0].reject_hint == 2, "row %zu: reject carries Index = m.Index, hint = lastIndex", k);
+    else
+      CHECK(rep[0].index == r.index + r.ents.size(), "row %zu: ack carries lastnewi", k);
+    CHECK(node.commit() == r.wcommit, "row %zu: commit %llu, want %llu", k, (unsigned long long)node.commit(), (unsigned long long)r.wcommit);
+    node.stop();
+    // the log the node persisted is the log upstream ends with: replay it
+    Wal w(wdir);
+    std::vector<Entry> ents;
+    bool has_hs = false;
+    uint64_t hs[3];
+    w.read_all(&ents, &has_hs, hs);
+    CHECK(ents.size() == r.windex, "row %zu: lastIndex %zu, want %llu", k, ents.size(), (unsigned long long)r.windex);
+    CHECK(has_hs && hs[2] == r.wcommit, "row %zu: persisted commit", k);
+  }
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -300,6 +370,7 @@ int main(int argc, char **argv) {
   try {
     test_chan_semantics();
     test_wal_recovery(dir);
+    test_handle_msgapp_table(dir);
     test_single_node(core, dir);
     test_cluster_and_restart(core, dir);
   } catch (const std::exception &ex) {
