@@ -1,0 +1,61 @@
+#!/bin/bash
+# The first GPU call of round 2, in one go (≈ 12 GPU-minutes at N = 1):
+#
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'
+#
+# 1. the byte-form inbox on hardware for the first time (tests/test_zz_packed8_gpu.py WITHOUT the xfail shield),
+#    and under compute-sanitizer memcheck on a reduced run;
+# 2. the default bench (e2e.packed8 = the byte form's end-to-end number, from its child process);
+# 3. the persisting-L2 experiment of DESIGN.md §10 item 0: the same bench with the device limit raised;
+# 4. a launch list of the byte-form e2e leg (share of unpack8 / tick / drain kernels in its step).
+# Everything lands in gpurun_out/r02_first/ — summarise into profiles/ afterwards (tools/ncu_summary.py).
+set -u
+OUT=gpurun_out/r02_first
+mkdir -p "$OUT"
+
+echo "== 1. byte-form GPU tests (xfail shield off)" | tee "$OUT/summary.txt"
+timeout 900 python -m pytest tests/test_zz_packed8_gpu.py -m gpu --runxfail -x -q > "$OUT/packed8_tests.log" 2>&1
+echo "exit $?" | tee -a "$OUT/summary.txt"
+tail -5 "$OUT/packed8_tests.log" | tee -a "$OUT/summary.txt"
+
+echo "== 1b. memcheck on one byte-form case" | tee -a "$OUT/summary.txt"
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 \
+  python -m pytest "tests/test_zz_packed8_gpu.py::test_byte_form_decodes_like_the_host_and_ticks_like_the_oracle[777-2-5]" \
+  -m gpu --runxfail -x -q > "$OUT/packed8_memcheck.log" 2>&1
+echo "exit $?" | tee -a "$OUT/summary.txt"
+grep -E "ERROR SUMMARY|passed|failed" "$OUT/packed8_memcheck.log" | tail -3 | tee -a "$OUT/summary.txt"
+
+echo "== 2. default bench" | tee -a "$OUT/summary.txt"
+timeout 900 python bench.py > "$OUT/bench_default.json" 2> "$OUT/bench_default.err"
+echo "exit $?" | tee -a "$OUT/summary.txt"
+python - "$OUT/bench_default.json" <<'EOF' | tee -a "$OUT/summary.txt"
+import json, sys
+try:
+    l = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print("ticks/s", round(l["value"]), "us/step", round(1e3 * l["ms_per_step"], 2), "frac", round(l["roofline"]["frac"], 3))
+    e = l["e2e"]
+    print("e2e", round(e["value"]), "api", e["api"][:40], "| packed16", round(e["packed16"]["value"]), "| packed8", e.get("packed8"))
+except Exception as ex:
+    print("could not read the bench line:", ex)
+EOF
+
+echo "== 3. persisting-L2 limit raised (MRQ_L2_PERSIST_MB=80), kernels only" | tee -a "$OUT/summary.txt"
+for mb in 80 48; do
+  MRQ_L2_PERSIST_MB=$mb MRQ_BENCH_FAST=1 timeout 600 python bench.py > "$OUT/bench_l2_$mb.json" 2> "$OUT/bench_l2_$mb.err"
+  python - "$OUT/bench_l2_$mb.json" $mb <<'EOF' | tee -a "$OUT/summary.txt"
+import json, sys
+try:
+    l = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print("persist MB", sys.argv[2], "us/step", round(1e3 * l["ms_per_step"], 2), "frac", round(l["roofline"]["frac"], 3))
+except Exception as ex:
+    print("persist MB", sys.argv[2], "failed:", ex)
+EOF
+done
+MRQ_BENCH_FAST=1 timeout 600 python bench.py --l2 0 > "$OUT/bench_l2_off.json" 2> "$OUT/bench_l2_off.err"
+
+echo "== 4. launch list of the byte-form e2e leg (a number printed under ncu is not a bench value)" | tee -a "$OUT/summary.txt"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches_e2e8.csv" \
+  python bench.py --e2e8-child --steps 8 > "$OUT/e2e8_under_ncu.log" 2>&1
+echo "exit $?" | tee -a "$OUT/summary.txt"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_event_reasons.active --format=csv >> "$OUT/summary.txt" 2>&1
+cat "$OUT/summary.txt"
