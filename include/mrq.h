@@ -221,7 +221,8 @@ int mrq_set_packed_base(mrq_engine *e, const uint64_t *base_index, const uint64_
  * (at most wide_cap entries; *n_wide = how many were needed) and slides base_index[G] exactly as the device
  * will when it decodes the frame — call it once per frame, in posting order, on the host's copy of the base
  * that was last given to mrq_set_packed_base.  MRQ_E_INVAL: bad arguments, more than 255 proposals for a
- * group, or wide_cap too small (then nothing was changed: retry with *n_wide entries).               */
+ * group, or wide_cap too small — base_index is then unchanged (the output buffers hold a discarded frame):
+ * retry with room for *n_wide entries.  Large frames are built on several host threads (MRQ_HOST_THREADS).  */
 int mrq_pack8(const mrq_inbox *in, const uint8_t *self_id, uint64_t n_groups, uint32_t n_replicas, uint64_t *base_index,
               const uint64_t *base_term, uint8_t *word_out, uint8_t *prop8_out, mrq_msg *wide_out, size_t wide_cap,
               size_t *n_wide);

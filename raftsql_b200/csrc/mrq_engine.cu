@@ -12,6 +12,7 @@
 
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "mrq_kernels.cuh"
@@ -746,55 +747,98 @@ int mrq_set_packed_base(mrq_engine *e, const uint64_t *base_index, const uint64_
 }
 
 // ---- the byte form's host side: plain CPU code around the shared codec (include/mrq_packed8.h) ----------------
+}  // extern "C"
+
+namespace {
+// Contiguous group ranges on host threads: frames of a million groups are memory-bound host work (33 B of wide
+// columns read per cell), so the builder scales with the cores the host gives it.  MRQ_HOST_THREADS overrides.
+unsigned host_threads(uint64_t G) {
+  unsigned hw = std::thread::hardware_concurrency();
+  if (const char *s = getenv("MRQ_HOST_THREADS")) hw = (unsigned)strtoul(s, nullptr, 10);
+  if (hw < 1) hw = 1;
+  const uint64_t by_size = G / 32768;  // below ~32k groups per thread the spawn costs more than it saves
+  if (by_size < hw) hw = (unsigned)(by_size < 1 ? 1 : by_size);
+  return hw > 16 ? 16 : hw;  // memory-bound work: more threads than memory channels buys nothing
+}
+template <class F>
+void for_group_chunks(uint64_t G, unsigned nt, F f) {  // f(chunk, g0, g1)
+  if (nt <= 1) {
+    f(0u, (uint64_t)0, G);
+    return;
+  }
+  std::vector<std::thread> th;
+  th.reserve(nt);
+  for (unsigned c = 0; c < nt; ++c) th.emplace_back(f, c, G * c / nt, G * (c + 1) / nt);
+  for (auto &t : th) t.join();
+}
+}  // namespace
+
+extern "C" {
+
 int mrq_pack8(const mrq_inbox *in, const uint8_t *self_id, uint64_t G, uint32_t R, uint64_t *base_index, const uint64_t *base_term,
               uint8_t *word_out, uint8_t *prop8_out, mrq_msg *wide_out, size_t wide_cap, size_t *n_wide) {
   if (!in || !in->type || !in->term || !in->index || !in->commit || !self_id || !base_index || !base_term || !n_wide)
     return fail(nullptr, MRQ_E_INVAL, "mrq_pack8: null argument");
   if (R < 1 || R > MRQ_MAX_REPLICAS) return fail(nullptr, MRQ_E_INVAL, "mrq_pack8: n_replicas %u outside 1..%u", R, MRQ_MAX_REPLICAS);
   if (R > 1 && !word_out) return fail(nullptr, MRQ_E_INVAL, "mrq_pack8: null word_out");
-  // pass 1 (nothing written): what escapes, and are the proposal counts representable
-  size_t need = 0;
-  for (uint64_t g = 0; g < G; ++g) {
-    if (prop8_out && in->prop_count && in->prop_count[g] > 255u)
-      return fail(nullptr, MRQ_E_INVAL, "mrq_pack8: group %llu has %u proposals; the packed forms carry at most 255", (unsigned long long)g,
-                  in->prop_count[g]);
-    for (uint32_t r = 0; r < R; ++r) {
-      const uint64_t o = (uint64_t)r * G + g;
-      if ((in->type[o] & MRQ_MSG_TYPE_MASK) == 0) continue;
-      if (mrq_p8_row(r, self_id[g], R) >= R - 1u) continue;  // addressed from the group's own slot: never stepped
-      if (mrq_p8_encode(in->type[o], in->term[o], in->index[o], in->commit[o], base_index[g], base_term[g]) == MRQ_P8_ESCAPE) ++need;
-    }
-  }
-  *n_wide = need;
-  if (need > wide_cap || (need && !wide_out)) return fail(nullptr, MRQ_E_INVAL, "mrq_pack8: %zu escapes, room for %zu", need, wide_cap);
-  // pass 2: bytes, escapes, window
-  size_t nw = 0;
-  for (uint64_t g = 0; g < G; ++g) {
-    uint32_t min_ack = MRQ_P8_NO_ACK;
-    const uint64_t bi = base_index[g], bt = base_term[g];
-    for (uint32_t r = 0; r < R; ++r) {
-      const uint32_t row = mrq_p8_row(r, self_id[g], R);
-      if (row >= R - 1u) continue;
-      const uint64_t o = (uint64_t)r * G + g;
-      const uint8_t b = mrq_p8_encode(in->type[o], in->term[o], in->index[o], in->commit[o], bi, bt);
-      word_out[(uint64_t)row * G + g] = b;
-      if (b == MRQ_P8_ESCAPE) {
-        mrq_msg &m = wide_out[nw++];
-        memset(&m, 0, sizeof m);
-        m.group = g;
-        m.from = (uint8_t)(r + 1u);
-        m.type = in->type[o];
-        m.term = in->term[o];
-        m.index = in->index[o];
-        m.logterm = in->logterm ? in->logterm[o] : 0;
-        m.commit = in->commit[o];
-      } else if ((b & 3u) == 1u) {
-        const uint32_t p = b >> 2;
-        min_ack = p < min_ack ? p : min_ack;
+  const unsigned nt = host_threads(G);
+  // One pass over the wide columns (they are the cost: 33 B per cell): bytes and proposal counts go straight to
+  // the output buffers, escapes and the slid bases are staged per chunk and published only if everything fits,
+  // so a refused call leaves base_index — the state that must stay in step with the device — untouched.
+  constexpr uint64_t kNone = ~0ull;
+  std::vector<std::vector<mrq_msg>> esc(nt);
+  std::vector<std::vector<uint64_t>> slid(nt);
+  std::vector<uint64_t> bad(nt, kNone);
+  for_group_chunks(G, nt, [&](unsigned c, uint64_t g0, uint64_t g1) {
+    std::vector<uint64_t> &nb = slid[c];
+    nb.resize(g1 - g0);
+    for (uint64_t g = g0; g < g1; ++g) {
+      uint32_t min_ack = MRQ_P8_NO_ACK;
+      const uint64_t bi = base_index[g], bt = base_term[g];
+      for (uint32_t r = 0; r < R; ++r) {
+        const uint32_t row = mrq_p8_row(r, self_id[g], R);
+        if (row >= R - 1u) continue;  // the group's own slot: nothing is ever stepped from there
+        const uint64_t o = (uint64_t)r * G + g;
+        const uint8_t b = mrq_p8_encode(in->type[o], in->term[o], in->index[o], in->commit[o], bi, bt);
+        word_out[(uint64_t)row * G + g] = b;
+        if (b == MRQ_P8_ESCAPE) {
+          mrq_msg m;
+          memset(&m, 0, sizeof m);
+          m.group = g;
+          m.from = (uint8_t)(r + 1u);
+          m.type = in->type[o];
+          m.term = in->term[o];
+          m.index = in->index[o];
+          m.logterm = in->logterm ? in->logterm[o] : 0;
+          m.commit = in->commit[o];
+          esc[c].push_back(m);
+        } else if ((b & 3u) == 1u) {
+          const uint32_t p = b >> 2;
+          min_ack = p < min_ack ? p : min_ack;
+        }
+      }
+      nb[g - g0] = mrq_p8_next_base(bi, min_ack);
+      if (prop8_out) {
+        const uint32_t n = in->prop_count ? in->prop_count[g] : 0u;
+        if (n > 255u && bad[c] == kNone) bad[c] = g;
+        prop8_out[g] = (uint8_t)n;
       }
     }
-    base_index[g] = mrq_p8_next_base(bi, min_ack);
-    if (prop8_out) prop8_out[g] = in->prop_count ? (uint8_t)in->prop_count[g] : 0;
+  });
+  for (unsigned c = 0; c < nt; ++c)
+    if (bad[c] != kNone)
+      return fail(nullptr, MRQ_E_INVAL, "mrq_pack8: group %llu has %u proposals; the packed forms carry at most 255",
+                  (unsigned long long)bad[c], in->prop_count[bad[c]]);
+  size_t total = 0;
+  for (unsigned c = 0; c < nt; ++c) total += esc[c].size();
+  *n_wide = total;
+  if (total > wide_cap || (total && !wide_out)) return fail(nullptr, MRQ_E_INVAL, "mrq_pack8: %zu escapes, room for %zu", total, wide_cap);
+  size_t at = 0;
+  for (unsigned c = 0; c < nt; ++c) {  // chunks are contiguous group ranges: the list stays in group order
+    if (!esc[c].empty()) memcpy(wide_out + at, esc[c].data(), esc[c].size() * sizeof(mrq_msg));
+    at += esc[c].size();
+    const uint64_t g0 = G * c / nt;
+    if (!slid[c].empty()) memcpy(base_index + g0, slid[c].data(), slid[c].size() * sizeof(uint64_t));
   }
   return MRQ_OK;
 }

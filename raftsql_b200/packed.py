@@ -115,6 +115,7 @@ class Pack8:
         self.self_id = np.ascontiguousarray(self_id, np.uint8)
         self.base_index = np.ascontiguousarray(base_index, np.uint64).copy()
         self.base_term = np.ascontiguousarray(base_term, np.uint64).copy()
+        self._cap, self._wide = 0, (F.Msg * 1)()  # escape list, grown on demand
 
     def frame(self, ib: dict, word_out: np.ndarray | None = None, prop8_out: np.ndarray | None = None):
         """-> (word[R-1][G] uint8, prop8[G] uint8 or None, wide list of mrq_msg tuples).  Slides the window."""
@@ -132,21 +133,19 @@ class Pack8:
         if prop is not None:
             p8 = prop8_out if prop8_out is not None else np.zeros(G, np.uint8)
         n_wide = C.c_size_t(0)
-        cap = 0
-        wide = (F.Msg * 1)()
         while True:
             rc = self.L.mrq_pack8(C.byref(view), _p(self.self_id, F.u8p), G, Rr, _p(self.base_index, F.u64p),
                                   _p(self.base_term, F.u64p), _p(word, F.u8p) if word.size else None,
-                                  _p(p8, F.u8p) if p8 is not None else None, wide, cap, C.byref(n_wide))
+                                  _p(p8, F.u8p) if p8 is not None else None, self._wide, self._cap, C.byref(n_wide))
             if rc == F.MRQ_OK:
                 break
-            if n_wide.value > cap:  # the escape list was too small: nothing was changed, retry with room
-                cap = n_wide.value
-                wide = (F.Msg * cap)()
+            if n_wide.value > self._cap:  # the escape list was too small: the base is unchanged, retry with room
+                self._cap = n_wide.value + n_wide.value // 4  # (kept for the next frames)
+                self._wide = (F.Msg * self._cap)()
                 continue
             raise ValueError((self.L.mrq_last_error(None) or b"mrq_pack8 failed").decode())
         msgs = [(int(m.group), int(m.from_), int(m.type), int(m.term), int(m.index), int(m.logterm), int(m.commit))
-                for m in wide[: n_wide.value]]
+                for m in self._wide[: n_wide.value]]
         return word, p8, msgs
 
 

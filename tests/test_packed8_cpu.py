@@ -138,6 +138,32 @@ def test_window_follows_a_steady_state_leader_without_escapes():
     assert word.nbytes + p8.nbytes == G * R  # (R-1) sender bytes + 1 proposal byte per group
 
 
+def test_frame_is_the_same_on_one_and_on_many_host_threads(monkeypatch):
+    """mrq_pack8 splits large frames into contiguous group ranges on host threads: bytes, escape order (group
+    order) and the slid bases must not depend on how many."""
+    rng = np.random.default_rng(8)
+    G, R = 200_000, 5
+    self_id = (np.arange(G) % R + 1).astype(np.uint8)
+    li = rng.integers(1 << 20, 1 << 40, size=G).astype(np.uint64)
+    bt = rng.integers(1, 9, size=G).astype(np.uint64)
+    ib = oracle.empty_inbox(G, R)
+    ib["type"][:] = F.MSG_APP_RESP
+    ib["term"][:] = bt[None, :]
+    ib["index"][:] = li[None, :] - rng.geometric(0.2, size=(R, G)).astype(np.uint64)
+    ib["index"][2, ::97] += np.uint64(1 << 20)  # escapes scattered over every chunk
+    ib["term"][4, ::1013] += np.uint64(1)
+    ib["prop_count"][:] = rng.integers(0, 4, size=G)
+    got = {}
+    for nt in ("1", "6"):
+        monkeypatch.setenv("MRQ_HOST_THREADS", nt)
+        pk = Pack8(self_id, li - np.uint64(40), bt, R)
+        w1, p1, wide1 = pk.frame(ib)
+        w2, p2, wide2 = pk.frame(ib)  # a second frame from the slid base
+        got[nt] = (w1.tobytes(), p1.tobytes(), wide1, w2.tobytes(), wide2, pk.base_index.tobytes())
+    assert got["1"] == got["6"]
+    assert len(got["1"][2]) > 1500 and [m[0] for m in got["1"][2]] == sorted(m[0] for m in got["1"][2])
+
+
 def test_too_many_proposals_and_small_escape_buffers_are_refused_without_side_effects():
     L = F.load()
     G, R = 4, 3
