@@ -528,7 +528,8 @@ def bench_e2e(eng, st0, host_ib, K, W, dist=None, torch=None):
         el_p, _ = run_packed(steps, False)
         ws = 1 if dist is None else dist.get_world_size()  # bytes are whole-job figures (all ranks)
         results[bits] = {"value": steps / el_p, "h2d_bytes_per_step": h2d * ws, "d2h_bytes_per_step": int(delta.nbytes) * ws,
-                         "equals_wide_form": same, "h2d_GBps_per_gpu": h2d * steps / el_p / 1e9}
+                         "equals_wide_form": same, "h2d_GBps_per_gpu": h2d * steps / el_p / 1e9,
+                         "inputs": f"{n} distinct ticks of the trace, cycled over the {steps} steps (same bytes per step)"}
     best = max(results, key=lambda b: results[b]["value"])
     res = {"value": results[best]["value"], "unit": "ticks/s", "h2d_bytes_per_step": results[best]["h2d_bytes_per_step"],
            "d2h_bytes_per_step": results[best]["d2h_bytes_per_step"], "steps": steps,
@@ -617,6 +618,7 @@ def run_e2e8_child(args):
     el, _ = run(S, False)
     res = {"value": S / el, "unit": "ticks/s", "steps": S, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(delta.nbytes),
            "equals_wide_form": same, "escapes": escapes, "h2d_GBps_per_gpu": h2d * S / el / 1e9,
+           "inputs": f"{S} distinct consecutive ticks of the trace, one per step",
            "api": "mrq_pack8 frames (pinned, 8-bit form, copy stream) + mrq_post_inbox_packed + mrq_tick + "
                   "mrq_drain_commit_deltas/mrq_drain_wait (1 B/group)"}
     print(json.dumps(res))
