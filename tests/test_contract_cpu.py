@@ -37,6 +37,38 @@ def test_reference_arm_prints_the_contract_line():
     assert line["config"]["groups"] == 1 << 20 and line["config"]["replicas"] == 5
 
 
+def test_byte_form_leg_can_only_add_to_the_bench_line():
+    """bench.py measures the byte-form inbox in a child process and merges its outcome: adopted only when it
+    verified itself and is faster, recorded otherwise, and nothing the child returns can break the line."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    def e2e():
+        return {"value": 4467.0, "unit": "ticks/s", "h2d_bytes_per_step": 11_534_336, "d2h_bytes_per_step": 1 << 20, "steps": 20,
+                "api": "16-bit", "packed_equals_wide": True}
+
+    good = {"value": 9000.0, "unit": "ticks/s", "steps": 20, "h2d_bytes_per_step": 5 << 20, "d2h_bytes_per_step": 1 << 20,
+            "equals_wide_form": True, "escapes": 0, "api": "8-bit"}
+    e = e2e()
+    bench.merge_packed8(e, good)
+    assert e["value"] == 9000.0 and e["api"] == "8-bit" and e["h2d_bytes_per_step"] == 5 << 20 and e["packed8"] is good
+    assert e["packed_equals_wide"] is True
+    e = e2e()
+    bench.merge_packed8(e, dict(good, value=3000.0))  # verified but slower: recorded, not adopted
+    assert e["value"] == 4467.0 and e["api"] == "16-bit" and e["packed8"]["value"] == 3000.0
+    e = e2e()
+    bench.merge_packed8(e, dict(good, equals_wide_form=False))  # wrong answers: never adopted, and flagged
+    assert e["value"] == 4467.0 and e["packed_equals_wide"] is False
+    for junk in ({"error": "exit 1: boom"}, {}, None, [1, 2], "text", {"equals_wide_form": True}):
+        e = e2e()
+        bench.merge_packed8(e, junk)
+        assert e["value"] == 4467.0 and e["api"] == "16-bit" and "packed8" in e
+        json.dumps(e)
+    # and on a machine without a GPU the child itself fails cleanly
+    r = bench.e2e8_from_child(4)
+    assert set(r) == {"error"} and "no CUDA device" in r["error"]
+
+
 def test_reference_arm_other_ranks_exit_quietly():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
