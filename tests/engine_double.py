@@ -1,0 +1,134 @@
+"""TEST-ONLY double of the GPU engine for rehearsing host-side code paths on the CPU: the CPU oracle behind the
+Engine methods and the few raw C-ABI calls that bench.py and the byte-form GPU tests make.  Posted byte-form frames
+are decoded with `mrq_unpack8` — the same inline codec the device kernel runs (include/mrq_packed8.h).
+
+It exists to separate two kinds of failure before code meets hardware: a rehearsal that passes here shows the
+host-side code (tests, bench legs) is sound, so a failure on the GPU implicates the device path alone.  It proves
+nothing about the device kernels themselves."""
+import ctypes as C
+
+import numpy as np
+
+import oracle
+from oracle import Oracle
+from raftsql_b200 import _ffi as F
+from raftsql_b200.packed import unpack8
+
+
+class FakePinned:
+    def __init__(self, shape, dtype):
+        self.array = np.zeros(shape, dtype)
+        self.ptr = self.array.ctypes.data
+        self.nbytes = self.array.nbytes
+
+    def free(self):
+        pass
+
+
+def _apply_wide(cols, wide):
+    for g, frm, ty, term, index, logterm, commit in wide:
+        r = frm - 1
+        cols["type"][r, g], cols["term"][r, g], cols["index"][r, g] = ty, term, index
+        cols["logterm"][r, g], cols["commit"][r, g] = logterm, commit
+
+
+class FakeL:
+    """the C-ABI calls made directly (not through Engine methods), over the double's state"""
+
+    def __init__(self, eng):
+        self.e = eng
+        self.posts = 0
+
+    def mrq_post_inbox_packed(self, h, slot, ref):
+        e, v = self.e, ref._obj
+        assert v.word_bits == 8
+        G, R = e.G, e.R
+        word = np.ctypeslib.as_array((C.c_uint8 * max(1, (R - 1) * G)).from_address(v.word))[: (R - 1) * G].reshape(R - 1, G)
+        wide = [(v.wide[i].group, v.wide[i].from_, v.wide[i].type, v.wide[i].term, v.wide[i].index, v.wide[i].logterm,
+                 v.wide[i].commit) for i in range(v.n_wide)]
+        prop8 = np.ctypeslib.as_array(v.prop_count8, shape=(G,)) if v.prop_count8 else None
+        e.post_inbox_packed(word, prop8, wide, slot=slot)
+        self.posts += 1
+        return 0
+
+    def mrq_tick(self, h, slot):
+        self.e.tick(slot)
+        return 0
+
+    def mrq_drain_commit_deltas(self, h, dptr):
+        e = self.e
+        c = e.o.export()["committed"]
+        d = c - e.prev
+        np.ctypeslib.as_array(dptr, shape=(e.G,))[:] = np.minimum(d, 255).astype(np.uint8)
+        e.prev = np.where(d > 255, e.prev, c)
+        return 0
+
+    def mrq_drain_wait(self, h):
+        return 0
+
+    def mrq_last_error(self, h):
+        return b""
+
+
+class FakeEngine:
+    def __init__(self, G, R, seed=0, group_base=0, device=0, inbox_slots=2, self_id=0, **_):
+        self.G, self.R = G, R
+        self.o = Oracle(G, R, seed=seed, group_base=group_base, self_id=self_id)
+        self.slots = [oracle.empty_inbox(G, R) for _ in range(inbox_slots)]
+        self.base_index = np.zeros(G, np.uint64)
+        self.base_term = np.zeros(G, np.uint64)
+        self.prev = np.zeros(G, np.uint64)
+        self.L, self.h = FakeL(self), 1
+
+    def _self_id(self):
+        return self.o.export()["self_id"]
+
+    def import_state(self, st):
+        self.o.import_state(st)
+
+    def export_state(self, columns=None):
+        return self.o.export()
+
+    def gen_trace(self, p, t, slot=0):
+        q = oracle.TraceParams()
+        for n, _ in F.TraceParams._fields_:
+            setattr(q, n, getattr(p, n))
+        self.slots[slot] = self.o.gen_trace(q, t)
+
+    def read_inbox(self, slot=0):
+        return {k: v.copy() for k, v in self.slots[slot].items()}
+
+    def post_inbox_packed(self, word, prop8=None, wide=(), slot=0):
+        assert word.dtype == np.uint8 and word.shape == (max(self.R - 1, 0), self.G)
+        cols, self.base_index = unpack8(word, self._self_id(), self.base_index, self.base_term, self.R)
+        _apply_wide(cols, wide)
+        cols["prop_count"] = np.zeros(self.G, np.uint32) if prop8 is None else np.asarray(prop8).astype(np.uint32)
+        self.slots[slot] = cols
+
+    def tick(self, slot=0):
+        self.o.tick(self.slots[slot])
+
+    def sync_commits(self):
+        c = self.o.export()["committed"].copy()
+        self.prev = c.copy()  # a full read rebases the delta drain (mrq_sync_commits)
+        return c
+
+    @property
+    def tick_count(self):
+        return self.o.tick_count
+
+    @tick_count.setter
+    def tick_count(self, t):
+        self.o.tick_count = t
+
+    def set_packed_base(self, bi, bt):
+        if bi is not None:
+            self.base_index = np.array(bi, np.uint64)
+        if bt is not None:
+            self.base_term = np.array(bt, np.uint64)
+
+    def synchronize(self):
+        pass
+
+    def close(self):
+        pass
