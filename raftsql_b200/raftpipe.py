@@ -30,26 +30,35 @@ class Chan:
     def __init__(self, buffered: int = 0):
         self.cap = buffered
         self.cv = threading.Condition()
-        self.items: list = []
+        self.items: list = []  # [(ticket, value)]: a handful at most, one per blocked sender
         self.closed = False
-        self.waiting_recv = 0
-        self.taken = 0
-        self.sent = 0
+        self.seq = 0
 
-    def send(self, v):
+    def send(self, v, stop: threading.Event | None = None) -> bool:
+        """Blocks until a receiver has taken the value (unbuffered) or there is room (buffered).  With `stop` it is
+        `select { case ch <- v: case <-stopc: }` (raft.go:89-93): an aborted send WITHDRAWS its value — as in Go the
+        receiver never sees it — and returns False.  A channel closed under a blocked sender raises (Go panics)."""
         with self.cv:
             if self.closed:
                 raise ChanClosed("send on closed channel")
-            self.items.append(v)
-            self.sent += 1
-            my = self.sent
+            self.seq += 1
+            my = self.seq
+            self.items.append((my, v))
             self.cv.notify_all()
             if self.cap and len(self.items) <= self.cap:
-                return
-            while self.taken < my:  # unbuffered: block until a receiver has taken this value
-                if self.closed and self.taken < my:
+                return True
+            while any(t == my for t, _ in self.items):  # unbuffered: until a receiver has taken this value
+                if self.closed:
+                    self._withdraw(my)
                     raise ChanClosed("channel closed while sending")
-                self.cv.wait(0.05)
+                if stop is not None and stop.is_set():
+                    self._withdraw(my)
+                    return False
+                self.cv.wait(0.02 if stop is not None else 0.05)
+            return True
+
+    def _withdraw(self, ticket):
+        self.items = [(t, v) for t, v in self.items if t != ticket]
 
     def recv(self, timeout: float | None = None):
         """-> (value, ok); ok is False when the channel is closed and drained."""
@@ -65,8 +74,7 @@ class Chan:
                     self.cv.wait(min(left, 0.05))
                 else:
                     self.cv.wait(0.05)
-            v = self.items.pop(0)
-            self.taken += 1
+            _, v = self.items.pop(0)
             self.cv.notify_all()
             return v, True
 
@@ -198,18 +206,9 @@ def newRaftNode(id: int, peers, proposeC: Chan, *, tick_seconds: float = 0.1, wa
 
 
 def _send_or_stop(ch: Chan, v, stop: threading.Event):
-    """`select { case commitC <- v: case <-stopc: }` (raft.go:89-93)."""
-    with ch.cv:
-        if ch.closed:
-            raise ChanClosed()
-        ch.items.append(v)
-        ch.sent += 1
-        my = ch.sent
-        ch.cv.notify_all()
-        while ch.taken < my:
-            if stop.is_set():  # shutting down: the channel is closed right after, the value is dropped
-                raise ChanClosed()
-            ch.cv.wait(0.02)
+    """`select { case commitC <- v: case <-stopc: }` (raft.go:89-93); raises ChanClosed when the stop side won."""
+    if not ch.send(v, stop):
+        raise ChanClosed()
 
 
 def NewRaftPipe(id: int, peers, proposeC: Chan, **kw) -> RaftPipe:
