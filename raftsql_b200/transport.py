@@ -102,7 +102,10 @@ class HttpTransport:
                 if local is not None and to in self.servers:  # same process: short-circuit
                     local.extend(batch)
                     continue
-            self._sender(to).put(batch)
+            try:
+                self._sender(to).put_nowait(batch)
+            except queue.Full:
+                pass  # a peer that has been unreachable for a while: drop, never stall the node's own tick loop
 
     def _sender(self, to: int) -> queue.Queue:
         with self.lock:

@@ -64,6 +64,18 @@ def test_wire_format_roundtrip():
            [(m.type, m.to, m.frm, m.term, m.logterm, m.index, m.commit, m.reject, m.reject_hint, m.entries) for m in msgs]
 
 
+def test_a_dead_peer_never_stalls_the_sender():
+    """rafthttp drops what it cannot deliver (ReportUnreachable is a no-op in the reference, raft.go:271-273): a node's
+    tick loop must not block on a peer that is down, however long it stays down."""
+    dead = free_ports(1)[0]  # nobody listens there
+    tr = HttpTransport([f"http://127.0.0.1:{free_ports(1)[0]}", f"http://127.0.0.1:{dead}"])
+    t0 = time.monotonic()
+    for k in range(2000):  # far more batches than the per-peer queue holds
+        tr.send([Message(8, 2, 1, term=1, commit=k)])
+    assert time.monotonic() - t0 < 2.0
+    tr.close()
+
+
 def test_three_nodes_over_loopback_tcp_oracle_core(tmp_path):
     raft_ports, sql_ports = free_ports(3), free_ports(3)
     peers = [f"http://127.0.0.1:{p}" for p in raft_ports]
