@@ -19,8 +19,9 @@
 //   rc.publishEntries          raft.go:82-96    publish (applied, committed] — on COMMIT, not on append
 //   rc.node.Advance()          raft.go:235      nothing to do: the engine has no Ready queue
 //
-// For many groups per process (the multi-raft shape the engine is built for) use NewMultiRaftPipe: one
-// engine with G groups, one tick loop, and committed[g] advances demultiplexed into per-group CommitC's.
+// For many groups per process (the multi-raft shape the engine is built for) use NewMultiRaftPipe
+// (multiraftpipe_mrq.go): one engine with G groups, one tick loop, and committed[g] advances demultiplexed
+// into per-group CommitC's.
 package raftsql
 
 import (

@@ -239,6 +239,14 @@ class HostNode:
     def step_tick(self) -> list[bytes]:
         """Inbound messages -> engine inbox; proposals; one engine tick; Ready handling.  Returns the payloads
         newly committed by this tick, in log order (what goes to commitC)."""
+        app_replies = self.prepare_tick()
+        self.core.tick(0)
+        return self._ready(app_replies)
+
+    def prepare_tick(self) -> dict:
+        """Everything of step_tick that precedes the engine's tick (posts this tick's inbox and proposals).  Split
+        out so that a multi-group host can prepare every group, tick the shared engine ONCE, then finish every
+        group (raftsql_b200.multipipe)."""
         inbound = self.backlog + self.tr.drain(self.id)
         self.backlog = []
         eng_msgs, app_replies = [], {}
@@ -276,7 +284,10 @@ class HostNode:
         elif self.pending and self.lead not in (0, self.id):
             fwd, self.pending = self.pending, []
             self.tr.send([Message(MsgProp, self.lead, self.id, entries=[(0, d) for d in fwd])])
-        self.core.tick(0)
+        return app_replies
+
+    def finish_tick(self, app_replies: dict) -> list[bytes]:
+        """Everything of step_tick that follows the engine's tick (Ready handling)."""
         return self._ready(app_replies)
 
     def _resolve_append(self, m: Message, replies: dict):

@@ -78,6 +78,16 @@ class Chan:
             self.cv.notify_all()
             return v, True
 
+    def try_recv(self):
+        """`select { case v, ok := <-ch: ... default: }` -> (value, ok, ready): ready is False when nothing is
+        offered right now; ok is False (with ready True) once the channel is closed and drained."""
+        with self.cv:
+            if self.items:
+                _, v = self.items.pop(0)
+                self.cv.notify_all()
+                return v, True, True
+            return (None, False, True) if self.closed else (None, False, False)
+
     def close(self):
         with self.cv:
             self.closed = True

@@ -9,18 +9,18 @@ import oracle
 
 
 class OracleCore:
-    def __init__(self, npeers: int, nid: int, seed: int = 0, election_tick: int = 10, heartbeat_tick: int = 1, **_):
-        self.G, self.R = 1, npeers
-        self.o = oracle.Oracle(1, npeers, self_id=nid, seed=seed or (0x5EED + nid), election_tick=election_tick,
+    def __init__(self, npeers: int, nid: int, seed: int = 0, election_tick: int = 10, heartbeat_tick: int = 1, n_groups: int = 1, **_):
+        self.G, self.R = n_groups, npeers
+        self.o = oracle.Oracle(n_groups, npeers, self_id=nid, seed=seed or (0x5EED + nid), election_tick=election_tick,
                                heartbeat_tick=heartbeat_tick)
-        self.ib = oracle.empty_inbox(1, npeers)
+        self.ib = oracle.empty_inbox(n_groups, npeers)
 
     def import_state(self, s):
         self.o.import_state({k: np.ascontiguousarray(v) for k, v in s.items()})
 
     def post_inbox_delta(self, msgs, slot=0, accumulate=False):
         if not accumulate:
-            self.ib = oracle.empty_inbox(1, self.R)
+            self.ib = oracle.empty_inbox(self.G, self.R)
         for g, frm, ty, term, index, logterm, commit in msgs:
             r = frm - 1
             self.ib["type"][r, g], self.ib["term"][r, g], self.ib["index"][r, g] = ty, term, index
@@ -32,7 +32,7 @@ class OracleCore:
 
     def tick(self, slot=0):
         self.o.tick(self.ib)
-        self.ib = oracle.empty_inbox(1, self.R)
+        self.ib = oracle.empty_inbox(self.G, self.R)
 
     def export_state(self, columns=None):
         return self.o.export()
@@ -46,3 +46,8 @@ class OracleCore:
 
 def make_oracle_core(npeers, nid, **kw):
     return OracleCore(npeers, nid, **kw)
+
+
+def make_oracle_multicore(npeers, nid, n_groups, **kw):
+    """the multi-group core of raftsql_b200.multipipe (one engine of G groups), CPU checker version"""
+    return OracleCore(npeers, nid, n_groups=n_groups, **kw)
