@@ -61,6 +61,19 @@ class Chan {
     return true;
   }
 
+  // `select { case v, ok := <-ch: ... default: }`: 1 = took a value, 0 = nothing offered right now,
+  // -1 = closed and drained.
+  int try_recv(T &out) {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (!q_.empty()) {
+      out = std::move(q_.front().second);
+      q_.pop_front();
+      cv_.notify_all();
+      return 1;
+    }
+    return closed_ ? -1 : 0;
+  }
+
   void close() {
     std::lock_guard<std::mutex> lk(mu_);
     closed_ = true;

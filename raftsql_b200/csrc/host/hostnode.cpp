@@ -190,11 +190,19 @@ std::vector<std::string> HostNode::start() {
     commit_ = hs[2];
   }
   commit_ = std::min<uint64_t>(commit_, log_.last_index());
-  core_->import_hardstate(term_, vote_, commit_, log_.last_index(), log_.last_term());
+  if (core_) core_->import_hardstate(term_, vote_, commit_, log_.last_index(), log_.last_term());
   for (uint64_t i = 1; i <= commit_; ++i)
     if (!log_.ents[i - 1].data.empty()) replay.push_back(log_.ents[i - 1].data);
   applied_ = commit_;
   return replay;
+}
+
+void HostNode::hardstate(uint64_t *term, uint64_t *vote, uint64_t *commit, uint64_t *last_index, uint64_t *last_term) const {
+  *term = term_;
+  *vote = vote_;
+  *commit = commit_;
+  *last_index = log_.last_index();
+  *last_term = log_.last_term();
 }
 
 void HostNode::propose(const std::string &data) { pending_.push_back(data); }
@@ -240,14 +248,23 @@ bool HostNode::resolve_append(const Message &m, std::map<uint32_t, Message> *rep
 }
 
 std::vector<std::string> HostNode::step_tick() {
+  Prepared p = prepare_tick();
+  const CoreState s = core_->tick(p.msgs, p.nprop);
+  return finish_tick(s, p);
+}
+
+std::vector<std::string> HostNode::finish_tick(const CoreState &s, Prepared &p) { return ready(s, p.replies); }
+
+HostNode::Prepared HostNode::prepare_tick() {
   std::vector<Message> inbound = std::move(backlog_);
   backlog_.clear();
   {
     std::vector<Message> fresh = tr_->drain(id_);
     inbound.insert(inbound.end(), fresh.begin(), fresh.end());
   }
-  std::vector<CoreMsg> eng_msgs;
-  std::map<uint32_t, Message> replies;
+  Prepared prep;
+  std::vector<CoreMsg> &eng_msgs = prep.msgs;
+  std::map<uint32_t, Message> &replies = prep.replies;
   std::set<uint32_t> seen;
   for (const Message &m : inbound) {
     if (m.type == kMsgProp) {  // a follower forwarded client proposals to us
@@ -297,8 +314,8 @@ std::vector<std::string> HostNode::step_tick() {
     pending_.clear();
     tr_->send({fwd});
   }
-  const CoreState s = core_->tick(eng_msgs, nprop);
-  return ready(s, replies);
+  prep.nprop = nprop;
+  return prep;
 }
 
 std::vector<std::string> HostNode::ready(const CoreState &s, std::map<uint32_t, Message> &replies) {
@@ -417,6 +434,50 @@ std::vector<std::string> HostNode::ready(const CoreState &s, std::map<uint32_t, 
     if (!d.empty()) published.push_back(d);  // "ignore conf changes and empty messages" (raft.go:84-86)
   }
   return published;
+}
+
+// ---- MultiHostNode ------------------------------------------------------------------------------------------------
+MultiHostNode::MultiHostNode(std::unique_ptr<MultiCore> core, uint32_t id, uint32_t npeers, size_t n_groups,
+                             std::shared_ptr<MultiLocalTransport> tr, const std::string &waldir)
+    : core_(std::move(core)) {
+  if (!waldir.empty()) ::mkdir(waldir.c_str(), 0750);  // one sub-directory per group below it
+  for (size_t g = 0; g < n_groups; ++g)
+    nodes_.emplace_back(new HostNode(nullptr, id, npeers, tr->groups.at(g),
+                                     waldir.empty() ? std::string() : waldir + "/group-" + std::to_string(g)));
+}
+
+std::vector<std::vector<std::string>> MultiHostNode::start() {
+  const size_t G = nodes_.size();
+  std::vector<std::vector<std::string>> replay(G);
+  std::vector<uint64_t> term(G), vote(G), commit(G), li(G), lt(G);
+  bool any = false;
+  for (size_t g = 0; g < G; ++g) {
+    replay[g] = nodes_[g]->start();
+    nodes_[g]->hardstate(&term[g], &vote[g], &commit[g], &li[g], &lt[g]);
+    any = any || term[g] || vote[g] || commit[g] || li[g];
+  }
+  if (any) core_->import_hardstate(term, vote, commit, li, lt);  // ONE import of the restored columns
+  return replay;
+}
+
+std::vector<std::vector<std::string>> MultiHostNode::step_tick() {
+  const size_t G = nodes_.size();
+  std::vector<HostNode::Prepared> prep(G);
+  std::vector<std::vector<CoreMsg>> msgs(G);
+  std::vector<uint32_t> nprop(G, 0);
+  for (size_t g = 0; g < G; ++g) {
+    prep[g] = nodes_[g]->prepare_tick();
+    msgs[g] = prep[g].msgs;
+    nprop[g] = prep[g].nprop;
+  }
+  const std::vector<CoreState> st = core_->tick(msgs, nprop);  // ONE tick for all groups
+  std::vector<std::vector<std::string>> out(G);
+  for (size_t g = 0; g < G; ++g) out[g] = nodes_[g]->finish_tick(st.at(g), prep[g]);
+  return out;
+}
+
+void MultiHostNode::stop() {
+  for (auto &n : nodes_) n->stop();
 }
 
 }  // namespace raftsql

@@ -114,6 +114,18 @@ class HostNode {
   void propose(const std::string &data);
   // one iteration of serveChannels (raft.go:221-245); returns the payloads newly committed, in log order
   std::vector<std::string> step_tick();
+  // step_tick in two halves around the core's tick, so that a multi-group host can prepare every group, tick
+  // the shared engine ONCE, and finish every group (MultiHostNode below): step_tick() is
+  // finish_tick(core->tick(p.msgs, p.nprop), p) with p = prepare_tick().
+  struct Prepared {
+    std::vector<CoreMsg> msgs;  // this tick's inbox of the group (MsgApp already resolved against the log)
+    uint32_t nprop = 0;         // proposals handed to the core this tick
+    std::map<uint32_t, Message> replies;
+  };
+  Prepared prepare_tick();
+  std::vector<std::string> finish_tick(const CoreState &s, Prepared &p);
+  // what start() restored from the WAL, for hosts that import it into a shared core themselves
+  void hardstate(uint64_t *term, uint64_t *vote, uint64_t *commit, uint64_t *last_index, uint64_t *last_term) const;
   void stop();
   uint32_t role() const { return role_; }
   uint64_t term() const { return term_; }
@@ -136,6 +148,46 @@ class HostNode {
   uint64_t applied_ = 0, term_ = 0, vote_ = 0, commit_ = 0;
   uint32_t role_ = 0, lead_ = 0;
   bool stopped_ = false;
+};
+
+// ---- many groups of one node over ONE core (the multi-group seam) -----------------------------------
+// What a multi-group host needs from the consensus core: the same two calls as Core, for G groups at once — the
+// product implementation is one engine of G groups (ONE mrq_tick per tick for all of them).
+class MultiCore {
+ public:
+  virtual ~MultiCore() {}
+  // restored columns, [G] each
+  virtual void import_hardstate(const std::vector<uint64_t> &term, const std::vector<uint64_t> &vote,
+                                const std::vector<uint64_t> &committed, const std::vector<uint64_t> &last_index,
+                                const std::vector<uint64_t> &last_term) = 0;
+  // one tick of every group: msgs[g] (one per sender), nprop[g]; returns the Ready state of every group
+  virtual std::vector<CoreState> tick(const std::vector<std::vector<CoreMsg>> &msgs, const std::vector<uint32_t> &nprop) = 0;
+};
+
+// In-process stand-in for rafthttp with one mailbox set per group.
+struct MultiLocalTransport {
+  explicit MultiLocalTransport(size_t n_groups) {
+    for (size_t g = 0; g < n_groups; ++g) groups.push_back(std::make_shared<LocalTransport>());
+  }
+  std::vector<std::shared_ptr<LocalTransport>> groups;
+};
+
+// G HostNodes (the single-group host logic, unchanged: log, maybeAppend, Progress.Next, Ready.Messages, WAL)
+// around one MultiCore: per-group prepare, ONE core tick, per-group Ready.
+class MultiHostNode {
+ public:
+  MultiHostNode(std::unique_ptr<MultiCore> core, uint32_t id, uint32_t npeers, size_t n_groups,
+                std::shared_ptr<MultiLocalTransport> tr, const std::string &waldir /* "" = none; else <waldir>/group-<g> */);
+  std::vector<std::vector<std::string>> start();  // replayWAL for every group; committed payloads per group
+  void propose(size_t g, const std::string &data) { nodes_[g]->propose(data); }
+  std::vector<std::vector<std::string>> step_tick();  // newly committed payloads per group, in log order
+  void stop();
+  size_t n_groups() const { return nodes_.size(); }
+  HostNode *group(size_t g) { return nodes_[g].get(); }
+
+ private:
+  std::unique_ptr<MultiCore> core_;
+  std::vector<std::unique_ptr<HostNode>> nodes_;
 };
 
 }  // namespace raftsql

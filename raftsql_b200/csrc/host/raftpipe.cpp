@@ -199,4 +199,202 @@ std::unique_ptr<RaftPipe> NewRaftPipe(int id, const std::vector<std::string> &pe
   return rp;
 }
 
+// ---- the multi-group seam -----------------------------------------------------------------------------------------
+namespace {
+// One engine of G groups through the C-ABI: one sparse post, one mrq_propose, ONE mrq_tick, one export per tick.
+class EngineMultiCore : public MultiCore {
+ public:
+  EngineMultiCore(uint32_t npeers, uint32_t id, size_t n_groups, int device) : G_(n_groups), R_(npeers) {
+    mrq_config cfg;
+    mrq_config_default(&cfg);  // ElectionTick 10, HeartbeatTick 1 (raft.go:154-155)
+    cfg.n_groups = n_groups;
+    cfg.n_replicas = npeers;
+    cfg.self_id = id;  // this node's id in every group
+    cfg.seed = 0x5EED + id;
+    cfg.device = device;
+    cfg.inbox_slots = 1;
+    if (mrq_create(&cfg, &e_) != MRQ_OK) throw std::runtime_error(std::string("mrq_create: ") + mrq_last_error(nullptr));
+  }
+  ~EngineMultiCore() override { mrq_destroy(e_); }
+
+  void import_hardstate(const std::vector<uint64_t> &term, const std::vector<uint64_t> &vote, const std::vector<uint64_t> &committed,
+                        const std::vector<uint64_t> &last_index, const std::vector<uint64_t> &last_term) override {
+    mrq_state st{};
+    st.term = const_cast<uint64_t *>(term.data());
+    st.vote = const_cast<uint64_t *>(vote.data());
+    st.committed = const_cast<uint64_t *>(committed.data());
+    st.last_index = const_cast<uint64_t *>(last_index.data());
+    st.last_term = const_cast<uint64_t *>(last_term.data());
+    check(mrq_import_state(e_, &st));
+  }
+
+  std::vector<CoreState> tick(const std::vector<std::vector<CoreMsg>> &msgs, const std::vector<uint32_t> &nprop) override {
+    std::vector<mrq_msg> m;
+    std::vector<uint64_t> pg;
+    std::vector<uint32_t> pn;
+    for (size_t g = 0; g < G_; ++g) {
+      for (const CoreMsg &c : msgs[g]) {
+        mrq_msg x{};
+        x.group = g;
+        x.from = (uint8_t)c.from;
+        x.type = (uint8_t)c.type;
+        x.term = c.term;
+        x.index = c.index;
+        x.logterm = c.logterm;
+        x.commit = c.commit;
+        m.push_back(x);
+      }
+      if (nprop[g]) {
+        pg.push_back(g);
+        pn.push_back(nprop[g]);
+      }
+    }
+    check(mrq_post_inbox_delta(e_, 0, m.empty() ? nullptr : m.data(), m.size(), 0));
+    if (!pg.empty()) check(mrq_propose(e_, 0, pg.data(), pn.data(), pg.size()));
+    check(mrq_tick(e_, 0));
+    std::vector<uint64_t> term(G_), vote(G_), committed(G_), li(G_), lt(G_), match(G_ * R_);
+    std::vector<uint8_t> role(G_), lead(G_);
+    std::vector<uint32_t> out(G_);
+    mrq_state st{};
+    st.term = term.data();
+    st.vote = vote.data();
+    st.committed = committed.data();
+    st.last_index = li.data();
+    st.last_term = lt.data();
+    st.match = match.data();  // [R][G]
+    st.role = role.data();
+    st.lead = lead.data();
+    check(mrq_export_state(e_, &st));
+    check(mrq_sync_out(e_, out.data()));
+    std::vector<CoreState> s(G_);
+    for (size_t g = 0; g < G_; ++g) {
+      s[g].term = term[g];
+      s[g].vote = vote[g];
+      s[g].committed = committed[g];
+      s[g].last_index = li[g];
+      s[g].last_term = lt[g];
+      s[g].role = role[g];
+      s[g].lead = lead[g];
+      s[g].out = out[g];
+      s[g].match.resize(R_);
+      for (uint32_t r = 0; r < R_; ++r) s[g].match[r] = match[(size_t)r * G_ + g];
+    }
+    return s;
+  }
+
+ private:
+  void check(int rc) {
+    if (rc != MRQ_OK) throw std::runtime_error(std::string("mrq: ") + mrq_last_error(e_));
+  }
+  mrq_engine *e_ = nullptr;
+  size_t G_;
+  uint32_t R_;
+};
+}  // namespace
+
+std::unique_ptr<MultiCore> make_engine_multicore(uint32_t npeers, uint32_t id, size_t n_groups, int device) {
+  return std::unique_ptr<MultiCore>(new EngineMultiCore(npeers, id, n_groups, device));
+}
+
+std::string MultiRaftPipe::Close() {
+  for (auto &c : ProposeC) c->close();
+  std::string err;
+  const bool ok = ErrorC->recv(err);
+  if (thread_.joinable()) thread_.join();
+  return ok ? err : std::string();
+}
+
+MultiRaftPipe::~MultiRaftPipe() {
+  if (thread_.joinable()) {
+    for (auto &c : ProposeC) c->close();
+    ErrorC->close();  // nobody will read it any more
+    thread_.join();
+  }
+}
+
+std::unique_ptr<MultiRaftPipe> NewMultiRaftPipe(int id, const std::vector<std::string> &peers, size_t n_groups,
+                                                const MultiRaftPipeOptions &opt) {
+  std::unique_ptr<MultiRaftPipe> mp(new MultiRaftPipe());
+  for (size_t g = 0; g < n_groups; ++g) {
+    mp->ProposeC.push_back(std::make_shared<StrChan>());
+    mp->CommitC.push_back(std::make_shared<CommitChan>());  // unbuffered (raft.go:65)
+  }
+  mp->ErrorC = std::make_shared<StrChan>();
+  auto tr = opt.transport ? opt.transport : std::make_shared<MultiLocalTransport>(n_groups);
+  const uint32_t n = (uint32_t)peers.size();
+  std::unique_ptr<MultiCore> core =
+      opt.core_factory ? opt.core_factory(n, (uint32_t)id, n_groups) : make_engine_multicore(n, (uint32_t)id, n_groups);
+  const std::string waldir = opt.waldir == "auto" ? "raftsql-" + std::to_string(id) : opt.waldir;
+  mp->node_ = std::make_shared<MultiHostNode>(std::move(core), (uint32_t)id, n, n_groups, tr, waldir);
+
+  auto node = mp->node_;
+  auto proposeC = mp->ProposeC;
+  auto commitC = mp->CommitC;
+  auto errorC = mp->ErrorC;
+  const double tick_seconds = opt.tick_seconds;
+  mp->thread_ = std::thread([node, proposeC, commitC, errorC, tick_seconds]() {
+    std::atomic<bool> stop{false};
+    std::string err;
+    bool failed = false;
+    auto publish = [&](size_t g, const std::vector<std::string> &payloads) -> bool {  // raft.go:82-96
+      for (const auto &d : payloads) {
+        if (stop.load()) return false;
+        if (!commitC[g]->send(std::make_shared<std::string>(d), &stop)) return false;
+      }
+      return true;
+    };
+    // raft.go:211-218 for every group without a thread per group: take what is offered right now; the node shuts
+    // down once every ProposeC has been closed
+    auto feed = [&]() -> bool {
+      bool open_any = false;
+      for (size_t g = 0; g < proposeC.size(); ++g) {
+        for (;;) {
+          std::string p;
+          const int r = proposeC[g]->try_recv(p);
+          if (r == 0) {
+            open_any = true;
+            break;
+          }
+          if (r < 0) break;
+          node->propose(g, p);
+        }
+      }
+      return open_any;
+    };
+    try {
+      const auto replay = node->start();  // replayWAL per group (raft.go:122-134)
+      bool ok = true;
+      for (size_t g = 0; ok && g < replay.size(); ++g)
+        ok = publish(g, replay[g]) && commitC[g]->send(nullptr, &stop);  // nil: "commit channel is current"
+      auto next = std::chrono::steady_clock::now();
+      while (ok && !stop.load()) {
+        if (!feed()) break;
+        const auto out = node->step_tick();
+        for (size_t g = 0; ok && g < out.size(); ++g) ok = publish(g, out[g]);
+        next += std::chrono::duration_cast<std::chrono::steady_clock::duration>(std::chrono::duration<double>(tick_seconds));
+        const auto now = std::chrono::steady_clock::now();
+        if (next > now)
+          std::this_thread::sleep_for(next - now);
+        else
+          next = now;
+      }
+    } catch (const ChanClosed &) {
+    } catch (const std::exception &ex) {  // writeError (raft.go:136-142)
+      err = ex.what();
+      failed = true;
+    }
+    stop.store(true);
+    node->stop();
+    for (auto &c : commitC) c->close();
+    if (failed) {
+      try {
+        errorC->send(err);
+      } catch (const ChanClosed &) {
+      }
+    }
+    errorC->close();
+  });
+  return mp;
+}
+
 }  // namespace raftsql

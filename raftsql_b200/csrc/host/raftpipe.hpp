@@ -57,4 +57,38 @@ std::unique_ptr<Core> make_engine_core(uint32_t npeers, uint32_t id, int device 
 
 std::shared_ptr<LocalTransport> transport_for(const std::vector<std::string> &peers);
 
+// ---- the multi-group seam --------------------------------------------------------------------
+// G raft groups of one node behind per-group channels over ONE engine of G groups, ticked once per tick for all:
+//   mp->ProposeC[g] / mp->CommitC[g]  — each with the protocol above (replay, nil, live entries of group g in order)
+//   mp->ErrorC, mp->Close()           — one per node; Close() closes every ProposeC and returns <-ErrorC
+struct MultiRaftPipeOptions {
+  double tick_seconds = 0.1;
+  std::string waldir = "auto";  // "auto": raftsql-<id>/group-<g>; "": no WAL
+  std::shared_ptr<MultiLocalTransport> transport;  // required when several nodes share a process
+  // consensus core for (npeers, id, n_groups); default: one GPU engine of n_groups groups (make_engine_multicore)
+  std::function<std::unique_ptr<MultiCore>(uint32_t, uint32_t, size_t)> core_factory;
+};
+
+class MultiRaftPipe {
+ public:
+  std::vector<std::shared_ptr<StrChan>> ProposeC;
+  std::vector<std::shared_ptr<CommitChan>> CommitC;
+  std::shared_ptr<StrChan> ErrorC;
+  std::string Close();
+  ~MultiRaftPipe();
+  MultiHostNode *node() { return node_.get(); }
+
+ private:
+  friend std::unique_ptr<MultiRaftPipe> NewMultiRaftPipe(int, const std::vector<std::string> &, size_t,
+                                                         const MultiRaftPipeOptions &);
+  std::shared_ptr<MultiHostNode> node_;
+  std::thread thread_;
+};
+
+std::unique_ptr<MultiRaftPipe> NewMultiRaftPipe(int id, const std::vector<std::string> &peers, size_t n_groups,
+                                                const MultiRaftPipeOptions &opt = MultiRaftPipeOptions());
+
+// The product multi-group core: one engine (G = n_groups, R = npeers, self_id = id) behind include/mrq.h.
+std::unique_ptr<MultiCore> make_engine_multicore(uint32_t npeers, uint32_t id, size_t n_groups, int device = 0);
+
 }  // namespace raftsql

@@ -60,6 +60,59 @@ class OracleCore : public Core {
   uint32_t R_;
 };
 
+// TEST-ONLY multi-group core: the oracle with G groups behind the MultiCore interface.
+class OracleMultiCore : public MultiCore {
+ public:
+  OracleMultiCore(uint32_t npeers, uint32_t id, size_t n_groups) : G_(n_groups), R_(npeers) {
+    e_ = orc_create(n_groups, npeers, 0, 10, 1, 0x5EED + id, id);
+    if (!e_) throw std::runtime_error("orc_create failed");
+  }
+  ~OracleMultiCore() override { orc_destroy(e_); }
+  void import_hardstate(const std::vector<uint64_t> &term, const std::vector<uint64_t> &vote, const std::vector<uint64_t> &committed,
+                        const std::vector<uint64_t> &last_index, const std::vector<uint64_t> &last_term) override {
+    orc_import(e_, term.data(), vote.data(), committed.data(), last_index.data(), last_term.data(), nullptr, nullptr, nullptr,
+               nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+  }
+  std::vector<CoreState> tick(const std::vector<std::vector<CoreMsg>> &msgs, const std::vector<uint32_t> &nprop) override {
+    std::vector<uint8_t> type(R_ * G_, 0);
+    std::vector<uint64_t> term(R_ * G_, 0), index(R_ * G_, 0), logterm(R_ * G_, 0), commit(R_ * G_, 0);
+    for (size_t g = 0; g < G_; ++g)
+      for (const CoreMsg &m : msgs[g]) {
+        const size_t o = (size_t)(m.from - 1) * G_ + g;
+        type[o] = (uint8_t)m.type;
+        term[o] = m.term;
+        index[o] = m.index;
+        logterm[o] = m.logterm;
+        commit[o] = m.commit;
+      }
+    orc_tick(e_, type.data(), term.data(), index.data(), logterm.data(), commit.data(), nprop.data(), 1);
+    std::vector<uint64_t> t(G_), v(G_), c(G_), li(G_), lt(G_), match(R_ * G_);
+    std::vector<uint8_t> role(G_), lead(G_);
+    std::vector<uint32_t> out(G_);
+    orc_export(e_, t.data(), v.data(), c.data(), li.data(), lt.data(), nullptr, match.data(), role.data(), lead.data(), nullptr,
+               nullptr, nullptr, nullptr, nullptr, out.data());
+    std::vector<CoreState> s(G_);
+    for (size_t g = 0; g < G_; ++g) {
+      s[g].term = t[g];
+      s[g].vote = v[g];
+      s[g].committed = c[g];
+      s[g].last_index = li[g];
+      s[g].last_term = lt[g];
+      s[g].role = role[g];
+      s[g].lead = lead[g];
+      s[g].out = out[g];
+      s[g].match.resize(R_);
+      for (uint32_t r = 0; r < R_; ++r) s[g].match[r] = match[(size_t)r * G_ + g];
+    }
+    return s;
+  }
+
+ private:
+  orc_engine *e_;
+  size_t G_;
+  uint32_t R_;
+};
+
 int failures = 0;
 #define CHECK(cond, ...)                                   \
   do {                                                     \
@@ -286,6 +339,67 @@ void test_wal_recovery(const std::string &dir) {
   CHECK(threw, "start() must fail when the wal cannot be opened");
 }
 
+// The multi-group seam (raftpipe.hpp NewMultiRaftPipe): 3 nodes x G groups in one process, one core per node ticked
+// once per tick for all groups.  Every group replicates independently and in its own log order, nil once per group,
+// a stopped node replays every group's WAL and catches up (tests/test_multipipe_cpu.py is the Python twin).
+void test_multi_group_cluster(const std::string &core, const std::string &dir) {
+  const size_t G = 4;
+  const std::vector<std::string> peers = {"http://127.0.0.1:10000", "http://127.0.0.1:10001", "http://127.0.0.1:10002"};
+  auto tr = std::make_shared<MultiLocalTransport>(G);
+  std::vector<std::unique_ptr<MultiRaftPipe>> mp(3);
+  std::vector<std::vector<std::unique_ptr<Collector>>> col(3);
+  auto start = [&](int i) {
+    MultiRaftPipeOptions o;
+    o.tick_seconds = 0.005;
+    o.waldir = dir + "/multi/raftsql-" + std::to_string(i + 1);
+    o.transport = tr;
+    if (core == "oracle")
+      o.core_factory = [](uint32_t n, uint32_t id, size_t g) { return std::unique_ptr<MultiCore>(new OracleMultiCore(n, id, g)); };
+    mp[i] = NewMultiRaftPipe(i + 1, peers, G, o);
+    col[i].clear();
+    for (size_t g = 0; g < G; ++g) col[i].emplace_back(new Collector(mp[i]->CommitC[g]));
+  };
+  ::mkdir((dir + "/multi").c_str(), 0750);
+  for (int i = 0; i < 3; ++i) start(i);
+  // group g gets its own sequence through node g % 3; groups interleave in time
+  for (int k = 0; k < 4; ++k)
+    for (size_t g = 0; g < G; ++g) mp[g % 3]->ProposeC[g]->send("g" + std::to_string(g) + "-entry-" + std::to_string(k));
+  for (size_t g = 0; g < G; ++g)
+    for (int i = 0; i < 3; ++i) CHECK(col[i][g]->wait_for(4), "node %d group %zu committed %zu of 4", i, g, col[i][g]->size());
+  for (size_t g = 0; g < G; ++g) {
+    std::vector<std::string> want;
+    for (int k = 0; k < 4; ++k) want.push_back("g" + std::to_string(g) + "-entry-" + std::to_string(k));
+    for (int i = 0; i < 3; ++i) {
+      CHECK(col[i][g]->snapshot() == want, "node %d group %zu: wrong sequence (groups must not leak into each other)", i, g);
+      CHECK(col[i][g]->nils.load() == 1, "node %d group %zu: %d nil sentinels", i, g, col[i][g]->nils.load());
+    }
+  }
+  // stop node 2; every group re-elects among the other two; propose through whoever leads each group now
+  CHECK(mp[1]->Close().empty(), "clean stop of node 2");
+  col[1].clear();
+  for (size_t g = 0; g < G; ++g) {
+    int leader = -1;
+    for (int t = 0; t < 4000 && leader < 0; ++t) {
+      for (int i : {0, 2})
+        if (mp[i]->node()->group(g)->role() == MRQ_ROLE_LEADER) leader = i;
+      if (leader < 0) std::this_thread::sleep_for(std::chrono::milliseconds(5));
+    }
+    CHECK(leader >= 0, "group %zu must re-elect with 2 of 3 nodes", g);
+    if (leader >= 0) mp[leader]->ProposeC[g]->send("while-down-" + std::to_string(g));
+  }
+  for (size_t g = 0; g < G; ++g)
+    for (int i : {0, 2}) CHECK(col[i][g]->wait_for(5), "node %d group %zu must commit with 2 of 3 nodes", i, g);
+  start(1);
+  for (size_t g = 0; g < G; ++g) {
+    CHECK(col[1][g]->wait_for(5), "restarted node, group %zu: has %zu of 5", g, col[1][g]->size());
+    auto got = col[1][g]->snapshot();
+    CHECK(got.size() == 5 && got[0] == "g" + std::to_string(g) + "-entry-0" && got[4] == "while-down-" + std::to_string(g),
+          "restarted node, group %zu: replay + catch-up in order", g);
+    CHECK(col[1][g]->nils.load() == 1, "restarted node, group %zu: one nil after the replay", g);
+  }
+  for (int i = 0; i < 3; ++i) CHECK(mp[i]->Close().empty(), "Close node %d", i);
+}
+
 // upstream raft_test.go TestHandleMsgApp (recalled; each row re-derived from raftLog.maybeAppend / commitTo in
 // tests/test_hostnode_kat_cpu.py, which runs the same table over the Python host): follower of term 2 with the log
 // [1:t1, 2:t2], committed 0; the host resolves the append against its log, the core applies the outcome.
@@ -373,6 +487,8 @@ int main(int argc, char **argv) {
     test_handle_msgapp_table(dir);
     test_single_node(core, dir);
     test_cluster_and_restart(core, dir);
+    // over the GPU engine the multi-group scenario is opt-in until its first hardware run (tests/test_cpp_host.py)
+    if (core == "oracle" || std::getenv("MRQ_TEST_MULTI_GROUP")) test_multi_group_cluster(core, dir);
   } catch (const std::exception &ex) {
     std::printf("FAIL exception: %s\n", ex.what());
     ++failures;

@@ -18,9 +18,10 @@ def _build():
     assert os.path.exists(BIN)
 
 
-def _run(core, tmp_path):
+def _run(core, tmp_path, env=None):
     _build()
-    r = subprocess.run([BIN, core, str(tmp_path)], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([BIN, core, str(tmp_path)], capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, **(env or {})))
     assert r.returncode == 0 and "raftpipe_test: ok" in r.stdout, r.stdout + r.stderr
 
 
@@ -42,3 +43,10 @@ def test_cpp_raftpipe_scenarios_oracle_core(tmp_path):
 @pytest.mark.gpu
 def test_cpp_raftpipe_scenarios_gpu_engine(tmp_path):
     _run("engine", tmp_path)
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="C++ multi-group seam over the GPU engine (EngineMultiCore): first hardware run pending; "
+                                        "the same scenario passes over the oracle core in the CPU suite")
+def test_cpp_multi_group_seam_gpu_engine(tmp_path):
+    _run("engine", tmp_path, env={"MRQ_TEST_MULTI_GROUP": "1"})
