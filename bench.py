@@ -241,7 +241,7 @@ def run_ours(args):
     eng.import_state(st0)
     p = preset_trace(3)
 
-    if world > 1:  # the per-tick all-gather of committed[]: fused peer stores (default) or ncclAllGather
+    if world > 1 and args.gather != "none":  # the per-tick all-gather of committed[]: fused peer stores (default) or ncclAllGather
         from raftsql_b200 import multi
 
         multi.attach(eng, dist, args.gather)
@@ -328,7 +328,8 @@ def run_ours(args):
                    "groups_total": G_TOTAL, "groups_per_gpu": G, "replicas": R, "parallelism": f"groups sharded x{world}",
                    "collective": ("none" if world == 1 else
                                   "all-gather of committed[] per tick, fused into the tick kernel as peer stores over NVLink"
-                                  if args.gather == "fused" else "ncclAllGather(committed) per tick"),
+                                  if args.gather == "fused" else "ncclAllGather(committed) per tick" if args.gather == "nccl"
+                                  else "none in the timed region (--gather none: shards tick independently; SURVEY 8d config 4)"),
                    "l2": f"inputs larger than L2: {nslots} rotating inbox slots, per-step footprint "
                          f"{(tb['total'] * G) / 1e6:.0f} MB vs 126 MB L2"},
         "group_ticks_per_sec": ticks_per_s * G_TOTAL,
@@ -359,14 +360,17 @@ def run_ours(args):
         except Exception as ex:  # the baseline must never take the GPU numbers down with it
             line["cpu_baseline"] = {"value": None, "unit": "ticks/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
     if world > 1:
-        # correctness of the gather on every rank: it must equal the concatenation of all shards' commits
-        mine = torch.from_numpy(eng.sync_commits().view(np.int64)).cuda()
-        allc = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(allc, mine)
-        g = eng.sync_gathered().view(np.int64)
-        ok = torch.tensor([int(np.array_equal(g, torch.cat(allc).cpu().numpy()))], device="cuda")
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        line["gather_check"] = bool(ok.item())
+        if args.gather != "none":
+            # correctness of the gather on every rank: it must equal the concatenation of all shards' commits
+            mine = torch.from_numpy(eng.sync_commits().view(np.int64)).cuda()
+            allc = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allc, mine)
+            g = eng.sync_gathered().view(np.int64)
+            ok = torch.tensor([int(np.array_equal(g, torch.cat(allc).cpu().numpy()))], device="cuda")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            line["gather_check"] = bool(ok.item())
+        else:
+            line["gather_check"] = None
         # end to end at N GPUs: every rank ships its shard's packed inbox over its own PCIe link each tick
         e2e = bench_e2e(eng, st0, host_ib, K, W, dist=dist, torch=torch)
         if rank == 0:
@@ -652,8 +656,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
-                    help="N>1: how committed[] is all-gathered each tick")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl", "none"],
+                    help="N>1: how committed[] is all-gathered each tick (none: not at all — the scaling leg "
+                         "without the collective in the timed region)")
     ap.add_argument("--tick-mode", type=int, default=None, choices=[0, 2],
                     help="0: fast + slow kernels, 2: single fused launch (default: the engine's)")
     ap.add_argument("--l2", type=int, default=None, choices=[0, 1],
