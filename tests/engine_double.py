@@ -132,3 +132,43 @@ class FakeEngine:
 
     def close(self):
         pass
+
+
+class FakeBenchEngine(FakeEngine):
+    """+ the calls bench.py's main path makes around its timed region (no timing meaning: the double only lets the
+    orchestration and the JSON assembly run on the CPU)"""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.launches = 0
+        self._t0 = 0.0
+
+    def set_graph_mode(self, mode):
+        pass
+
+    def set_tick_mode(self, mode):
+        pass
+
+    def set_l2_policy(self, on):
+        pass
+
+    def tick(self, slot=0):
+        super().tick(slot)
+        self.launches += 2
+
+    def tick_many(self, slots):
+        for s in slots:
+            self.tick(s)
+
+    def counters(self):
+        return {"kernel_launches": self.launches, "ticks": self.o.tick_count}
+
+    def timer_start(self):
+        import time
+
+        self._t0 = time.perf_counter()
+
+    def timer_stop(self):
+        import time
+
+        return 1e3 * (time.perf_counter() - self._t0)

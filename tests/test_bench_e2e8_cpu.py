@@ -76,3 +76,59 @@ def test_rehearse_gpu_test_sliding_window(monkeypatch):
 
     monkeypatch.setattr(t, "Engine", FakeEngine)
     t.test_device_window_slides_by_itself_for_hundreds_of_ticks()
+
+
+def test_rehearse_bench_main_path_and_line_assembly(monkeypatch, capsys):
+    """`python bench.py` at N = 1, rehearsed: the real run_ours() — dry run, rehearsal, warm-up, timed region, post-roll,
+    roofline arithmetic, the legs' results merged, the engine closed BEFORE the byte-form child is consulted, one JSON
+    line printed — over the engine double, with the GPU-only legs stubbed.  Guards the driver-facing contract of the
+    line (keys, types) against edits made without a GPU at hand."""
+    import torch
+
+    import bench
+    import raftsql_b200
+    from engine_double import FakeBenchEngine
+
+    order = []
+
+    class Eng(FakeBenchEngine):
+        def close(self):
+            order.append("close")
+
+    def child(steps):
+        order.append("child")
+        return {"value": 9000.0, "unit": "ticks/s", "steps": steps, "h2d_bytes_per_step": 5 << 20, "d2h_bytes_per_step": 1 << 20,
+                "equals_wide_form": True, "escapes": 0, "api": "8-bit"}
+
+    monkeypatch.setattr(bench, "G_TOTAL", 2048)
+    monkeypatch.setattr(raftsql_b200, "Engine", Eng)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(bench, "bench_quorum_kernel", lambda *a: {"bound": "hbm", "achieved": 1.0, "peak": 2.0, "frac": 0.5})
+    monkeypatch.setattr(bench, "bench_e2e", lambda *a, **k: {"value": 4467.0, "unit": "ticks/s", "h2d_bytes_per_step": 11 << 20,
+                                                            "d2h_bytes_per_step": 1 << 20, "steps": 6, "api": "16-bit",
+                                                            "packed_equals_wide": True})
+    monkeypatch.setattr(bench, "cpu_reference_ticks", lambda *a, **k: (80.0, 8, 3, 0.04, None))
+    monkeypatch.setattr(bench, "e2e8_from_child", child)
+    monkeypatch.delenv("MRQ_BENCH_FAST", raising=False)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    args = argparse.Namespace(gpus=1, steps=6, warmup=3, impl="ours", gather="fused", tick_mode=None, l2=None, graph="auto")
+    bench.run_ours(args)
+    out = capsys.readouterr().out.strip().splitlines()
+    assert len(out) == 1, "exactly one JSON line"
+    line = json.loads(out[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "clocks", "gpu_launches"):
+        assert k in line, k
+    assert line["metric"] == "raft_ticks_per_sec_1Mx5" and line["unit"] == "ticks/s" and line["n_gpus"] == 1
+    assert line["steps"] == 6 and line["warmup"] == 3 and line["higher_is_better"] is True and line["vs_baseline"] is None
+    assert line["value"] > 0 and abs(line["value"] - 1e3 / line["ms_per_step"]) < 1e-6 * line["value"]
+    assert line["gpu_launches"] == 2 * 6  # the fast + slow kernel of each timed tick, counted by the engine
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(line["roofline"])
+    assert abs(line["roofline"]["frac"] - line["roofline"]["achieved"] / line["roofline"]["peak"]) < 1e-12
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(line["cpu_baseline"])
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(line["e2e"])
+    assert line["e2e"]["value"] == 9000.0 and line["e2e"]["api"] == "8-bit" and line["e2e"]["packed8"]["equals_wide_form"] is True
+    assert "workload" in line["config"] and "model" not in line["config"]
+    assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(line["clocks"])
+    assert order == ["close", "child"], "the engine must be gone before the byte-form child gets the GPU"
