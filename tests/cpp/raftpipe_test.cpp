@@ -6,6 +6,7 @@
 //   raftpipe_test engine <tmpdir>     consensus core = the GPU engine through the C-ABI (needs a B200)
 #include <sys/stat.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -361,39 +362,76 @@ void test_multi_group_cluster(const std::string &core, const std::string &dir) {
   };
   ::mkdir((dir + "/multi").c_str(), 0750);
   for (int i = 0; i < 3; ++i) start(i);
-  // group g gets its own sequence through node g % 3; groups interleave in time
+  // A raft client retries: an entry accepted by a leader that is deposed before replicating it is lost (upstream
+  // too), so proposals are at-least-once and the applied sequence is read modulo repeats.  Retries only ever fire
+  // when the machine stalls for seconds; they keep the scenario meaningful instead of flaky when it does.
+  auto uniq = [](const std::vector<std::string> &v) {
+    std::vector<std::string> out;
+    for (const auto &x : v)
+      if (std::find(out.begin(), out.end(), x) == out.end()) out.push_back(x);
+    return out;
+  };
+  auto has = [&](int i, size_t g, const std::string &text) {
+    const auto v = col[i][g]->snapshot();
+    return std::find(v.begin(), v.end(), text) != v.end();
+  };
+  auto leader_of = [&](size_t g, const std::vector<int> &alive) {
+    for (int i : alive)
+      if (mp[i]->node()->group(g)->role() == MRQ_ROLE_LEADER) return i;
+    return -1;
+  };
+  auto propose_until_committed = [&](size_t g, const std::string &text, int via, const std::vector<int> &alive) {
+    for (int attempt = 0; attempt < 8; ++attempt) {
+      const int ld = leader_of(g, alive);
+      mp[attempt == 0 || ld < 0 ? via : ld]->ProposeC[g]->send(text);
+      for (int t = 0; t < 1000; ++t) {  // 5 s
+        bool all = true;
+        for (int i : alive) all = all && has(i, g, text);
+        if (all) return true;
+        std::this_thread::sleep_for(std::chrono::milliseconds(5));
+      }
+    }
+    return false;
+  };
+  const std::vector<int> all3 = {0, 1, 2}, two = {0, 2};
+  // group g gets its own sequence, first through node g % 3 (forwarded to whoever leads); groups interleave in time
   for (int k = 0; k < 4; ++k)
-    for (size_t g = 0; g < G; ++g) mp[g % 3]->ProposeC[g]->send("g" + std::to_string(g) + "-entry-" + std::to_string(k));
-  for (size_t g = 0; g < G; ++g)
-    for (int i = 0; i < 3; ++i) CHECK(col[i][g]->wait_for(4), "node %d group %zu committed %zu of 4", i, g, col[i][g]->size());
+    for (size_t g = 0; g < G; ++g)
+      CHECK(propose_until_committed(g, "g" + std::to_string(g) + "-entry-" + std::to_string(k), (int)(g % 3), all3),
+            "group %zu entry %d never committed on all nodes", g, k);
   for (size_t g = 0; g < G; ++g) {
     std::vector<std::string> want;
     for (int k = 0; k < 4; ++k) want.push_back("g" + std::to_string(g) + "-entry-" + std::to_string(k));
     for (int i = 0; i < 3; ++i) {
-      CHECK(col[i][g]->snapshot() == want, "node %d group %zu: wrong sequence (groups must not leak into each other)", i, g);
+      CHECK(uniq(col[i][g]->snapshot()) == want, "node %d group %zu: wrong sequence (groups must not leak into each other)", i, g);
+      CHECK(col[i][g]->snapshot() == col[0][g]->snapshot(), "node %d group %zu: applied a different sequence than node 0", i, g);
       CHECK(col[i][g]->nils.load() == 1, "node %d group %zu: %d nil sentinels", i, g, col[i][g]->nils.load());
     }
   }
-  // stop node 2; every group re-elects among the other two; propose through whoever leads each group now
+  // stop node 2; every group re-elects among the other two and keeps committing with 2 of 3
   CHECK(mp[1]->Close().empty(), "clean stop of node 2");
   col[1].clear();
   for (size_t g = 0; g < G; ++g) {
     int leader = -1;
-    for (int t = 0; t < 4000 && leader < 0; ++t) {
-      for (int i : {0, 2})
-        if (mp[i]->node()->group(g)->role() == MRQ_ROLE_LEADER) leader = i;
+    for (int t = 0; t < 6000 && leader < 0; ++t) {
+      leader = leader_of(g, two);
       if (leader < 0) std::this_thread::sleep_for(std::chrono::milliseconds(5));
     }
     CHECK(leader >= 0, "group %zu must re-elect with 2 of 3 nodes", g);
-    if (leader >= 0) mp[leader]->ProposeC[g]->send("while-down-" + std::to_string(g));
+    CHECK(propose_until_committed(g, "while-down-" + std::to_string(g), leader < 0 ? 0 : leader, two),
+          "group %zu must commit with 2 of 3 nodes", g);
   }
-  for (size_t g = 0; g < G; ++g)
-    for (int i : {0, 2}) CHECK(col[i][g]->wait_for(5), "node %d group %zu must commit with 2 of 3 nodes", i, g);
   start(1);
   for (size_t g = 0; g < G; ++g) {
-    CHECK(col[1][g]->wait_for(5), "restarted node, group %zu: has %zu of 5", g, col[1][g]->size());
-    auto got = col[1][g]->snapshot();
-    CHECK(got.size() == 5 && got[0] == "g" + std::to_string(g) + "-entry-0" && got[4] == "while-down-" + std::to_string(g),
+    const std::string last = "while-down-" + std::to_string(g);
+    bool caught_up = false;
+    for (int t = 0; t < 6000 && !caught_up; ++t) {
+      caught_up = has(1, g, last);
+      if (!caught_up) std::this_thread::sleep_for(std::chrono::milliseconds(5));
+    }
+    CHECK(caught_up, "restarted node, group %zu: never caught up (has %zu entries)", g, col[1][g]->size());
+    const auto got = uniq(col[1][g]->snapshot());
+    CHECK(got.size() == 5 && got[0] == "g" + std::to_string(g) + "-entry-0" && got[4] == last,
           "restarted node, group %zu: replay + catch-up in order", g);
     CHECK(col[1][g]->nils.load() == 1, "restarted node, group %zu: one nil after the replay", g);
   }

@@ -47,6 +47,14 @@ def wait_until(pred, timeout=40.0):
     return False
 
 
+def uniq(v):
+    out = []
+    for x in v:
+        if x not in out:
+            out.append(x)
+    return out
+
+
 class Cluster:
     def __init__(self, G, tmp, tick=0.005):
         self.G, self.tmp, self.tick = G, str(tmp), tick
@@ -69,29 +77,44 @@ class Cluster:
             if self.mp[i] is not None:
                 self.stop(i)
 
-    def all_have(self, g, n, nodes=(0, 1, 2)):
-        return wait_until(lambda: all(len(self.col[i][g].snapshot()) >= n for i in nodes if self.mp[i] is not None))
+    def alive(self):
+        return [i for i in range(3) if self.mp[i] is not None]
+
+    def leader_of(self, g):
+        for i in self.alive():
+            role = self.mp[i]._thread.node.state.get("role")
+            if role is not None and int(role[g]) == 2:
+                return i
+        return None
+
+    def propose_until_committed(self, g, text, via):
+        """A raft client retries: an entry accepted by a leader that is deposed before replicating it is lost
+        (upstream too), so proposals are at-least-once and the applied sequence is read modulo repeats.  Retries
+        only ever fire when the machine stalls for seconds; they keep the scenario meaningful instead of flaky."""
+        for attempt in range(8):
+            ld = self.leader_of(g)
+            self.mp[via if attempt == 0 or ld is None else ld].ProposeC[g].send(text)
+            if wait_until(lambda: all(text in self.col[i][g].snapshot() for i in self.alive()), timeout=5.0):
+                return True
+        return False
 
 
 def test_every_group_replicates_independently_and_in_order(tmp_path):
     G = 6
     c = Cluster(G, tmp_path)
     try:
-        # through node g % 3, group g gets its own sequence; groups interleave in time
+        # group g gets its own sequence, first through node g % 3 (forwarded to whoever leads); groups interleave
         want = {g: [f"g{g}-entry-{k}" for k in range(5)] for g in range(G)}
         for k in range(5):
             for g in range(G):
-                c.mp[g % 3].ProposeC[g].send(want[g][k])
-        for g in range(G):
-            assert c.all_have(g, 5), f"group {g}: {[len(c.col[i][g].snapshot()) for i in range(3)]}"
+                assert c.propose_until_committed(g, want[g][k], g % 3), f"group {g} entry {k}"
         for g in range(G):
             for i in range(3):
-                assert c.col[i][g].snapshot() == want[g], f"node {i} group {g}"  # log order, nothing from other groups
+                assert uniq(c.col[i][g].snapshot()) == want[g], f"node {i} group {g}"  # log order, nothing from other groups
+                assert c.col[i][g].snapshot() == c.col[0][g].snapshot()  # every node applied the same sequence
                 assert c.col[i][g].nils == 1  # "commit channel is current", once per group
-        # one engine tick served all groups: every node's core saw G groups with a leader somewhere in the cluster
-        roles = [c.mp[i]._thread.node.state["role"] for i in range(3)]
-        for g in range(G):
-            assert sorted(int(r[g]) for r in roles).count(2) == 1, f"group {g} must have exactly one leader"
+        # one engine tick served all groups: every group has exactly one leader somewhere in the cluster
+        assert wait_until(lambda: all(sum(int(c.mp[i]._thread.node.state["role"][g]) == 2 for i in range(3)) == 1 for g in range(G)))
     finally:
         c.close()
 
@@ -101,29 +124,16 @@ def test_stopped_node_replays_every_groups_wal_and_catches_up(tmp_path):
     c = Cluster(G, tmp_path)
     try:
         for g in range(G):
-            c.mp[0].ProposeC[g].send(f"CREATE-{g}")
-        for g in range(G):
-            assert c.all_have(g, 1)
-        # stop node 2 (index 1): the groups it led re-elect among the remaining two.  A proposal forwarded to a dead
-        # leader is dropped by raft (upstream too), so propose through whoever leads each group NOW.
+            assert c.propose_until_committed(g, f"CREATE-{g}", 0)
+        # stop node 2 (index 1): the groups it led re-elect among the remaining two and keep committing with 2 of 3
         c.stop(1)
-
-        def leader_of(g):
-            for i in (0, 2):
-                role = c.mp[i]._thread.node.state.get("role")
-                if role is not None and int(role[g]) == 2:
-                    return i
-            return None
-
         for g in range(G):
-            assert wait_until(lambda: leader_of(g) is not None), f"group {g} must re-elect with 2 of 3 nodes"
-            c.mp[leader_of(g)].ProposeC[g].send(f"while-down-{g}")
-        for g in range(G):
-            assert c.all_have(g, 2, nodes=(0, 2)), f"group {g} must commit with 2 of 3 nodes"
+            assert wait_until(lambda: c.leader_of(g) is not None), f"group {g} must re-elect with 2 of 3 nodes"
+            assert c.propose_until_committed(g, f"while-down-{g}", c.leader_of(g) or 0), f"group {g} must commit with 2 of 3 nodes"
         c.start(1)
         for g in range(G):
-            assert wait_until(lambda: len(c.col[1][g].snapshot()) >= 2), f"group {g} on the restarted node: {c.col[1][g].snapshot()}"
-            assert c.col[1][g].snapshot()[:2] == [f"CREATE-{g}", f"while-down-{g}"]
+            assert wait_until(lambda: f"while-down-{g}" in c.col[1][g].snapshot()), f"group {g} on the restarted node: {c.col[1][g].snapshot()}"
+            assert uniq(c.col[1][g].snapshot()) == [f"CREATE-{g}", f"while-down-{g}"]  # replay, then catch-up, in order
             assert c.col[1][g].nils == 1
     finally:
         c.close()
