@@ -9,8 +9,6 @@ CPU: the oracle as the G-group core (tests/oracle_core.py).  The same host code 
 import threading
 import time
 
-import pytest
-
 from oracle_core import make_oracle_multicore
 from raftsql_b200.multipipe import MultiLocalTransport, NewMultiRaftPipe
 
