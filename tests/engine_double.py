@@ -71,9 +71,10 @@ class FakeL:
 
 
 class FakeEngine:
-    def __init__(self, G, R, seed=0, group_base=0, device=0, inbox_slots=2, self_id=0, **_):
+    def __init__(self, G, R, seed=0, group_base=0, device=0, inbox_slots=2, self_id=0, election_tick=10, heartbeat_tick=1, **_):
         self.G, self.R = G, R
-        self.o = Oracle(G, R, seed=seed, group_base=group_base, self_id=self_id)
+        self.o = Oracle(G, R, seed=seed, group_base=group_base, self_id=self_id, election_tick=election_tick,
+                        heartbeat_tick=heartbeat_tick)
         self.slots = [oracle.empty_inbox(G, R) for _ in range(inbox_slots)]
         self.base_index = np.zeros(G, np.uint64)
         self.base_term = np.zeros(G, np.uint64)
@@ -105,8 +106,27 @@ class FakeEngine:
         cols["prop_count"] = np.zeros(self.G, np.uint32) if prop8 is None else np.asarray(prop8).astype(np.uint32)
         self.slots[slot] = cols
 
+    def post_inbox_delta(self, msgs, slot=0, accumulate=False):
+        if not accumulate:
+            self.slots[slot] = oracle.empty_inbox(self.G, self.R)
+        _apply_wide(self.slots[slot], msgs)
+
+    def propose(self, groups, counts, slot=0):
+        for g, c in zip(groups, counts):
+            self.slots[slot]["prop_count"][g] += c
+
+    def clear_inbox(self, slot=0):
+        self.slots[slot] = oracle.empty_inbox(self.G, self.R)
+
     def tick(self, slot=0):
         self.o.tick(self.slots[slot])
+
+    def tick_idle(self, n=1):
+        for _ in range(n):
+            self.o.tick(None)
+
+    def sync_out(self):
+        return self.o.export()["out"]
 
     def sync_commits(self):
         c = self.o.export()["committed"].copy()

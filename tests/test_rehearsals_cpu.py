@@ -1,14 +1,16 @@
-"""Host-side code of the byte-form inbox rehearsed on the CPU against tests/engine_double.py (the CPU oracle
-behind the Engine methods / C-ABI calls involved, decoding posted frames with `mrq_unpack8`, the same inline decode
-the device kernel runs):
+"""Rehearsals: host-side code that will next run on a GPU, run here first against tests/engine_double.py (the CPU
+oracle behind the Engine methods / C-ABI calls involved, decoding posted byte-form frames with `mrq_unpack8`, the
+same inline decode the device kernel runs):
 
   * bench.py's byte-form end-to-end leg (`run_e2e8_child`): the REAL orchestration code — frame building with
     `mrq_pack8` as the trace is generated, the pipelined post / tick / drain loop, the commit-advance accumulation
-    and the equality verdict;
-  * the bodies of the byte-form GPU tests (tests/test_zz_packed8_gpu.py), so that when they first meet hardware a
-    failure implicates the device path alone, not the test code.
+    and the equality verdict (including a deliberately wrong decode, to show the verdict has teeth);
+  * bench.py's whole N = 1 main path (`run_ours`) and the driver-facing contract of the JSON line it prints;
+  * the bodies of the GPU tests written after round 1's GPU budget was spent (tests/test_zz_packed8_gpu.py,
+    tests/test_zz_kat_gpu.py), so that when they first meet hardware a failure implicates the device path alone,
+    not the test code.
 
-What this cannot cover is the device kernel itself and real PCIe timing."""
+What this cannot cover is the device kernels themselves and real PCIe timing."""
 import argparse
 import json
 
@@ -132,3 +134,39 @@ def test_rehearse_bench_main_path_and_line_assembly(monkeypatch, capsys):
     assert "workload" in line["config"] and "model" not in line["config"]
     assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(line["clocks"])
     assert order == ["close", "child"], "the engine must be gone before the byte-form child gets the GPU"
+
+
+def _engine_kat_cases():
+    import test_zz_kat_gpu as t
+
+    cases = []
+    for name in sorted(n for n in dir(t) if n.startswith("test_")):
+        fn = getattr(t, name)
+        marks = [m for m in getattr(fn, "pytestmark", []) if m.name == "parametrize"]
+        if not marks:
+            cases.append(pytest.param(name, (), id=name))
+            continue
+        # expand the parametrize marks the same way pytest does (outer product, innermost mark first)
+        import itertools
+
+        names, values = [], []
+        for m in marks:
+            ns = [x.strip() for x in m.args[0].split(",")]
+            names.append(ns)
+            values.append([v if isinstance(v, (tuple, list)) and len(ns) > 1 else (v,) for v in m.args[1]])
+        for combo in itertools.product(*values):
+            kw = {}
+            for ns, vs in zip(names, combo):
+                kw.update(dict(zip(ns, vs)))
+            cases.append(pytest.param(name, tuple(sorted(kw.items())), id=f"{name}-{'-'.join(str(v) for _, v in sorted(kw.items()))}"))
+    return cases
+
+
+@pytest.mark.parametrize("name,kwargs", _engine_kat_cases())
+def test_rehearse_engine_kats(monkeypatch, name, kwargs):
+    """the bodies of tests/test_zz_kat_gpu.py (upstream's tables through the engine, one message per tick) on the
+    engine double: the adapter's way of raising MsgHup / MsgProp through the ABI must reproduce every table row"""
+    import test_zz_kat_gpu as t
+
+    monkeypatch.setattr(t, "Engine", FakeEngine)
+    getattr(t, name)(**dict(kwargs))

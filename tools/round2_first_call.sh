@@ -26,7 +26,7 @@ echo "exit $?" | tee -a "$OUT/summary.txt"
 grep -E "ERROR SUMMARY|passed|failed" "$OUT/packed8_memcheck.log" | tail -3 | tee -a "$OUT/summary.txt"
 
 echo "== 1c. multi-group seam over the engine (xfail shield off)" | tee -a "$OUT/summary.txt"
-timeout 600 python -m pytest tests/test_zz_multipipe_gpu.py tests/test_cpp_host.py -m gpu --runxfail -q > "$OUT/multipipe_tests.log" 2>&1
+timeout 900 python -m pytest tests/test_zz_multipipe_gpu.py tests/test_zz_kat_gpu.py tests/test_cpp_host.py -m gpu --runxfail -q > "$OUT/multipipe_tests.log" 2>&1
 echo "exit $?" | tee -a "$OUT/summary.txt"
 tail -3 "$OUT/multipipe_tests.log" | tee -a "$OUT/summary.txt"
 
