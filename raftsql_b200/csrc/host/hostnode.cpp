@@ -124,6 +124,118 @@ void Wal::read_all(std::vector<Entry> *ents, bool *has_hs, uint64_t hs[3]) {
   std::fclose(f);
 }
 
+// ---- MultiWal ------------------------------------------------------------------------------------------------
+// records: [u8 kind][u32 group][u64 a][u64 b][u64 c][u32 len][len bytes]
+bool MultiWal::existed() const {
+  struct stat st;
+  return ::stat(path_.c_str(), &st) == 0;
+}
+
+bool MultiWal::open() {
+  if (f_) return true;
+  ::mkdir(dir_.c_str(), 0750);
+  f_ = std::fopen(path_.c_str(), "ab");
+  return f_ != nullptr;
+}
+
+void MultiWal::close() {
+  if (f_) {
+    sync();
+    std::fclose(f_);
+    f_ = nullptr;
+  }
+}
+
+void MultiWal::put(uint32_t g, char kind, uint64_t a, uint64_t b, uint64_t c, const std::string &payload) {
+  if (!f_) return;
+  const uint32_t len = (uint32_t)payload.size();
+  std::fwrite(&kind, 1, 1, f_);
+  std::fwrite(&g, 4, 1, f_);
+  std::fwrite(&a, 8, 1, f_);
+  std::fwrite(&b, 8, 1, f_);
+  std::fwrite(&c, 8, 1, f_);
+  std::fwrite(&len, 4, 1, f_);
+  if (len) std::fwrite(payload.data(), 1, len, f_);
+  dirty_ = true;
+}
+
+void MultiWal::sync() {
+  if (!f_ || !dirty_) return;
+  std::fflush(f_);
+  ::fsync(fileno(f_));
+  dirty_ = false;
+  ++syncs_;
+}
+
+const MultiWal::Replayed &MultiWal::replayed(uint32_t g) {
+  if (!parsed_) {
+    parsed_ = true;
+    FILE *f = std::fopen(path_.c_str(), "rb");
+    if (f) {
+      std::fseek(f, 0, SEEK_END);
+      const long file_size = std::ftell(f);
+      std::fseek(f, 0, SEEK_SET);
+      for (;;) {
+        char kind;
+        uint32_t grp, len;
+        uint64_t a, b, c;
+        if (std::fread(&kind, 1, 1, f) != 1 || std::fread(&grp, 4, 1, f) != 1 || std::fread(&a, 8, 1, f) != 1 ||
+            std::fread(&b, 8, 1, f) != 1 || std::fread(&c, 8, 1, f) != 1 || std::fread(&len, 4, 1, f) != 1)
+          break;
+        if ((long)len > file_size - std::ftell(f)) break;  // torn tail record
+        std::string payload(len, '\0');
+        if (len && std::fread(&payload[0], 1, len, f) != len) break;
+        Replayed &r = groups_[grp];
+        if (kind == 'H') {
+          r.has_hs = true;
+          r.hs[0] = a;
+          r.hs[1] = b;
+          r.hs[2] = c;
+        } else if (kind == 'E') {
+          if (a >= 1 && a <= r.ents.size() + 1) {
+            r.ents.resize(a - 1);
+            Entry e;
+            e.term = b;
+            e.data = payload;
+            r.ents.push_back(e);
+          }
+        } else if (kind == 'T') {
+          if (a < r.ents.size()) r.ents.resize(a);
+        }
+      }
+      std::fclose(f);
+    }
+  }
+  return groups_[g];
+}
+
+// Wal's interface for one group of a MultiWal: appends only, the owner syncs once per tick.
+class GroupWal : public Wal {
+ public:
+  GroupWal(MultiWal *w, uint32_t g) : Wal(w->dir()), w_(w), g_(g) {}
+  bool existed() const override { return w_->existed(); }
+  bool open() override { return w_->open(); }
+  void close() override {}  // the owner closes the shared file
+  void read_all(std::vector<Entry> *ents, bool *has_hs, uint64_t hs[3]) override {
+    const MultiWal::Replayed &r = w_->replayed(g_);
+    *ents = r.ents;
+    *has_hs = r.has_hs;
+    for (int k = 0; k < 3; ++k) hs[k] = r.hs[k];
+  }
+  void save(const uint64_t *hs, const std::vector<Entry> &new_entries, uint64_t first_index, bool truncate,
+            uint64_t truncate_after) override {
+    if (truncate) w_->put(g_, 'T', truncate_after, 0, 0, std::string());
+    for (size_t k = 0; k < new_entries.size(); ++k) w_->put(g_, 'E', first_index + k, new_entries[k].term, 0, new_entries[k].data);
+    if (hs) w_->put(g_, 'H', hs[0], hs[1], hs[2], std::string());
+  }
+
+ private:
+  MultiWal *w_;
+  uint32_t g_;
+};
+
+std::unique_ptr<Wal> MultiWal::view(uint32_t g) { return std::unique_ptr<Wal>(new GroupWal(this, g)); }
+
 // ---- LocalTransport ------------------------------------------------------------------------------------------
 void LocalTransport::add(uint32_t id) {
   std::lock_guard<std::mutex> lk(mu_);
@@ -157,6 +269,12 @@ HostNode::HostNode(std::unique_ptr<Core> core, uint32_t id, uint32_t npeers, std
   tr_->add(id_);
 }
 
+HostNode::HostNode(std::unique_ptr<Core> core, uint32_t id, uint32_t npeers, std::shared_ptr<LocalTransport> tr,
+                   std::unique_ptr<Wal> wal)
+    : core_(std::move(core)), id_(id), n_(npeers), tr_(std::move(tr)), wal_(std::move(wal)), next_(npeers + 1, 1) {
+  tr_->add(id_);
+}
+
 HostNode::~HostNode() { stop(); }
 
 void HostNode::stop() {
@@ -176,7 +294,7 @@ std::vector<uint32_t> HostNode::peers() const {
 std::vector<std::string> HostNode::start() {
   std::vector<std::string> replay;
   if (!wal_) return replay;
-  const bool old = Wal::exist(wal_->dir());
+  const bool old = wal_->existed();
   bool has_hs = false;
   uint64_t hs[3] = {0, 0, 0};
   std::vector<Entry> ents;
@@ -437,13 +555,29 @@ std::vector<std::string> HostNode::ready(const CoreState &s, std::map<uint32_t, 
 }
 
 // ---- MultiHostNode ------------------------------------------------------------------------------------------------
+namespace {
+// A group's transport whose sends wait in the node's outbox until the tick's WAL records are durable.
+class DeferredTransport : public LocalTransport {
+ public:
+  DeferredTransport(std::shared_ptr<LocalTransport> tr, MultiHostNode *owner) : tr_(std::move(tr)), owner_(owner) {}
+  void add(uint32_t id) override { tr_->add(id); }
+  void remove(uint32_t id) override { tr_->remove(id); }
+  std::vector<Message> drain(uint32_t id) override { return tr_->drain(id); }
+  void send(const std::vector<Message> &msgs) override { owner_->outbox.emplace_back(tr_, msgs); }
+
+ private:
+  std::shared_ptr<LocalTransport> tr_;
+  MultiHostNode *owner_;
+};
+}  // namespace
+
 MultiHostNode::MultiHostNode(std::unique_ptr<MultiCore> core, uint32_t id, uint32_t npeers, size_t n_groups,
                              std::shared_ptr<MultiLocalTransport> tr, const std::string &waldir)
     : core_(std::move(core)) {
-  if (!waldir.empty()) ::mkdir(waldir.c_str(), 0750);  // one sub-directory per group below it
+  if (!waldir.empty()) wal_ = std::make_shared<MultiWal>(waldir);  // group commit: one file, one fsync per tick
   for (size_t g = 0; g < n_groups; ++g)
-    nodes_.emplace_back(new HostNode(nullptr, id, npeers, tr->groups.at(g),
-                                     waldir.empty() ? std::string() : waldir + "/group-" + std::to_string(g)));
+    nodes_.emplace_back(new HostNode(nullptr, id, npeers, std::make_shared<DeferredTransport>(tr->groups.at(g), this),
+                                     wal_ ? wal_->view((uint32_t)g) : std::unique_ptr<Wal>()));
 }
 
 std::vector<std::vector<std::string>> MultiHostNode::start() {
@@ -473,11 +607,21 @@ std::vector<std::vector<std::string>> MultiHostNode::step_tick() {
   const std::vector<CoreState> st = core_->tick(msgs, nprop);  // ONE tick for all groups
   std::vector<std::vector<std::string>> out(G);
   for (size_t g = 0; g < G; ++g) out[g] = nodes_[g]->finish_tick(st.at(g), prep[g]);
+  flush();
   return out;
+}
+
+// make this tick's WAL records of every group durable with one fsync, THEN let the messages out
+void MultiHostNode::flush() {
+  if (wal_) wal_->sync();
+  auto pending = std::move(outbox);
+  outbox.clear();
+  for (auto &p : pending) p.first->send(p.second);
 }
 
 void MultiHostNode::stop() {
   for (auto &n : nodes_) n->stop();
+  if (wal_) wal_->close();
 }
 
 }  // namespace raftsql

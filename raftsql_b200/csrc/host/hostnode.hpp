@@ -75,14 +75,15 @@ class Log {
 class Wal {
  public:
   explicit Wal(const std::string &dir) : dir_(dir), path_(dir + "/wal.bin") {}
-  ~Wal() { close(); }
+  virtual ~Wal() { close(); }
   static bool exist(const std::string &dir);  // wal.Exist (raft.go:100,145)
-  bool open();
-  void close();
+  virtual bool existed() const { return exist(dir_); }
+  virtual bool open();
+  virtual void close();
   // wal.ReadAll (raft.go:124): entries and the last hardstate (has_hs false if none)
-  void read_all(std::vector<Entry> *ents, bool *has_hs, uint64_t hs[3]);
-  void save(const uint64_t *hs /*nullable [3]*/, const std::vector<Entry> &new_entries, uint64_t first_index, bool truncate,
-            uint64_t truncate_after);  // wal.Save (raft.go:228): fsync'ed
+  virtual void read_all(std::vector<Entry> *ents, bool *has_hs, uint64_t hs[3]);
+  virtual void save(const uint64_t *hs /*nullable [3]*/, const std::vector<Entry> &new_entries, uint64_t first_index, bool truncate,
+                    uint64_t truncate_after);  // wal.Save (raft.go:228): fsync'ed
   const std::string &dir() const { return dir_; }
 
  private:
@@ -91,13 +92,47 @@ class Wal {
   FILE *f_ = nullptr;
 };
 
+// Group-commit write-ahead log of a multi-group node: ONE append-only file for all groups (<dir>/multiwal.bin,
+// Wal's records with a u32 group tag after the kind byte), made durable with ONE fsync per tick however many groups
+// wrote.  view(g) is the Wal interface scoped to group g: its save() only appends; MultiHostNode calls sync() once per
+// tick before anything is sent.
+class MultiWal {
+ public:
+  explicit MultiWal(const std::string &dir) : dir_(dir), path_(dir + "/multiwal.bin") {}
+  ~MultiWal() { close(); }
+  bool existed() const;
+  bool open();
+  void close();
+  void sync();  // the tick's one fsync (wal.Save's durability point, raft.go:228, for every group at once)
+  uint64_t syncs() const { return syncs_; }
+  bool dirty() const { return dirty_; }
+  std::unique_ptr<Wal> view(uint32_t g);
+  const std::string &dir() const { return dir_; }
+
+ private:
+  friend class GroupWal;
+  struct Replayed {
+    std::vector<Entry> ents;
+    bool has_hs = false;
+    uint64_t hs[3] = {0, 0, 0};
+  };
+  void put(uint32_t g, char kind, uint64_t a, uint64_t b, uint64_t c, const std::string &payload);
+  const Replayed &replayed(uint32_t g);  // parses the file once
+  std::string dir_, path_;
+  FILE *f_ = nullptr;
+  bool dirty_ = false, parsed_ = false;
+  uint64_t syncs_ = 0;
+  std::map<uint32_t, Replayed> groups_;
+};
+
 // In-process stand-in for rafthttp.Transport (reference raft.go:170-184,230,259).
 class LocalTransport {
  public:
-  void add(uint32_t id);
-  void remove(uint32_t id);
-  void send(const std::vector<Message> &msgs);  // unknown / stopped peers lose messages, like a dead TCP peer
-  std::vector<Message> drain(uint32_t id);
+  virtual ~LocalTransport() {}
+  virtual void add(uint32_t id);
+  virtual void remove(uint32_t id);
+  virtual void send(const std::vector<Message> &msgs);  // unknown / stopped peers lose messages, like a dead TCP peer
+  virtual std::vector<Message> drain(uint32_t id);
 
  private:
   std::mutex mu_;
@@ -108,6 +143,8 @@ class LocalTransport {
 class HostNode {
  public:
   HostNode(std::unique_ptr<Core> core, uint32_t id, uint32_t npeers, std::shared_ptr<LocalTransport> tr, const std::string &waldir);
+  // with a WAL object of the caller's (a group's view of a shared group-commit WAL); nullptr = no WAL
+  HostNode(std::unique_ptr<Core> core, uint32_t id, uint32_t npeers, std::shared_ptr<LocalTransport> tr, std::unique_ptr<Wal> wal);
   ~HostNode();
   // replayWAL (raft.go:122-134): rebuild the log, restore HardState; returns the committed payloads to replay
   std::vector<std::string> start();
@@ -177,16 +214,24 @@ struct MultiLocalTransport {
 class MultiHostNode {
  public:
   MultiHostNode(std::unique_ptr<MultiCore> core, uint32_t id, uint32_t npeers, size_t n_groups,
-                std::shared_ptr<MultiLocalTransport> tr, const std::string &waldir /* "" = none; else <waldir>/group-<g> */);
+                std::shared_ptr<MultiLocalTransport> tr, const std::string &waldir /* "" = none; else one MultiWal there */);
   std::vector<std::vector<std::string>> start();  // replayWAL for every group; committed payloads per group
   void propose(size_t g, const std::string &data) { nodes_[g]->propose(data); }
-  std::vector<std::vector<std::string>> step_tick();  // newly committed payloads per group, in log order
+  // newly committed payloads per group, in log order.  Durability is batched like the arithmetic: the groups' WAL
+  // records of the tick become durable with ONE fsync, and only then do the tick's messages leave the node
+  // (persist before send: wal.Save precedes transport.Send, raft.go:228-230).
+  std::vector<std::vector<std::string>> step_tick();
   void stop();
   size_t n_groups() const { return nodes_.size(); }
   HostNode *group(size_t g) { return nodes_[g].get(); }
+  MultiWal *wal() { return wal_.get(); }
+  // messages waiting for the tick's fsync: (group's transport, messages)
+  std::vector<std::pair<std::shared_ptr<LocalTransport>, std::vector<Message>>> outbox;
 
  private:
+  void flush();
   std::unique_ptr<MultiCore> core_;
+  std::shared_ptr<MultiWal> wal_;
   std::vector<std::unique_ptr<HostNode>> nodes_;
 };
 

@@ -63,7 +63,7 @@ std::shared_ptr<LocalTransport> transport_for(const std::vector<std::string> &pe
 //   mp->ErrorC, mp->Close()           — one per node; Close() closes every ProposeC and returns <-ErrorC
 struct MultiRaftPipeOptions {
   double tick_seconds = 0.1;
-  std::string waldir = "auto";  // "auto": raftsql-<id>/group-<g>; "": no WAL
+  std::string waldir = "auto";  // "auto": raftsql-<id> (one group-commit file for all groups, MultiWal); "": no WAL
   std::shared_ptr<MultiLocalTransport> transport;  // required when several nodes share a process
   // consensus core for (npeers, id, n_groups); default: one GPU engine of n_groups groups (make_engine_multicore)
   std::function<std::unique_ptr<MultiCore>(uint32_t, uint32_t, size_t)> core_factory;

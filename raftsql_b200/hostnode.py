@@ -198,7 +198,8 @@ class HostNode:
         self.core, self.id, self.n = core, nid, npeers
         self.tr = transport
         self.log = Log()
-        self.wal = Wal(waldir) if waldir else None
+        # a directory name (this node's own WAL) or an object with the Wal interface (a group's view of a shared one)
+        self.wal = waldir if hasattr(waldir, "save") else (Wal(waldir) if waldir else None)
         self.pending: list[bytes] = []       # proposals not yet accepted by the state machine
         self.inflight: list[bytes] = []      # proposals posted to the engine this tick
         self.next = [1] * (npeers + 1)       # Progress.Next per peer id (leader only)

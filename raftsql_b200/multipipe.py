@@ -11,11 +11,15 @@ per-tick arithmetic of all G groups is ONE `mrq_tick` (one kernel pass), not G o
 validated single-group host logic (`hostnode.HostNode`: log, maybeAppend, Progress.Next, Ready.Messages, WAL), wired
 to a per-group VIEW of the shared engine: the views collect every group's inbox messages and proposals, the node
 posts them in one `mrq_post_inbox_delta` + one `mrq_propose`, ticks once, exports the state columns once, and each
-group finishes its Ready handling from its own slice.
+group finishes its Ready handling from its own slice.  Durability is batched the same way: the groups append to ONE
+write-ahead file (`MultiWal`), the node fsyncs it ONCE per tick, and only then do that tick's messages leave
+(persist before send, raft.go:228-230) — a group-commit WAL instead of one fsync per writing group.
 """
 from __future__ import annotations
 
+import json
 import os
+import struct
 import threading
 import time
 
@@ -67,6 +71,123 @@ class _GroupTransport:
             return out
 
 
+class MultiWal:
+    """Group-commit write-ahead log: ONE append-only file for all groups of a node (`<dir>/wal.log`, the records of
+    hostnode.Wal tagged with their group), made durable with ONE fsync per tick however many groups wrote — a
+    per-group WAL would cost one fsync per writing group per tick.  `view(g)` is the hostnode.Wal interface scoped
+    to group g; its `save()` only appends, `MultiHostNode` calls `sync()` once per tick before anything is sent."""
+
+    def __init__(self, dirname: str):
+        self.dir = dirname
+        self.path = os.path.join(dirname, "wal.log")
+        self.f = None
+        self.dirty = False
+        self.syncs = 0
+        self._parsed = None
+
+    def open(self):
+        if self.f is None:
+            os.makedirs(self.dir, mode=0o750, exist_ok=True)
+            self.f = open(self.path, "ab")
+
+    def parse(self) -> dict:
+        """-> {g: (hardstate or None, [(term, data)])}, tolerant of a torn tail like hostnode.Wal.read_all"""
+        if self._parsed is not None:
+            return self._parsed
+        out: dict = {}
+        if os.path.exists(self.path):
+            with open(self.path, "rb") as f:
+                buf = f.read()
+            off = 0
+            while off + 4 <= len(buf):
+                (n,) = struct.unpack_from("<I", buf, off)
+                if off + 4 + n > len(buf):
+                    break
+                try:
+                    rec = json.loads(buf[off + 4: off + 4 + n])
+                except ValueError:
+                    break
+                off += 4 + n
+                hs, ents = out.setdefault(rec["g"], [None, []])
+                if "hs" in rec:
+                    out[rec["g"]][0] = tuple(rec["hs"])
+                elif "e" in rec:
+                    i, t, d = rec["e"]
+                    del ents[i - 1:]
+                    ents.append((t, bytes.fromhex(d)))
+                elif "t" in rec:
+                    del ents[rec["t"]:]
+        self._parsed = {g: (v[0], v[1]) for g, v in out.items()}
+        return self._parsed
+
+    def put(self, rec: dict):
+        b = json.dumps(rec, separators=(",", ":")).encode()
+        self.f.write(struct.pack("<I", len(b)) + b)
+        self.dirty = True
+
+    def sync(self):
+        """the one fsync of the tick (wal.Save's durability point, raft.go:228, for every group at once)"""
+        if self.f is not None and self.dirty:
+            self.f.flush()
+            os.fsync(self.f.fileno())
+            self.dirty = False
+            self.syncs += 1
+
+    def close(self):
+        if self.f is not None:
+            self.sync()
+            self.f.close()
+            self.f = None
+
+    def view(self, g: int):
+        return _GroupWal(self, g)
+
+
+class _GroupWal:
+    """hostnode.Wal's interface for one group of a MultiWal"""
+
+    def __init__(self, wal: MultiWal, g: int):
+        self.wal, self.g, self.dir = wal, g, wal.dir
+
+    def open(self):
+        self.wal.open()
+
+    def read_all(self):
+        hs, ents = self.wal.parse().get(self.g, (None, []))
+        return hs, list(ents)
+
+    def save(self, hardstate, new_entries, first_index, truncate_after=None):
+        if truncate_after is not None:
+            self.wal.put({"g": self.g, "t": truncate_after})
+        for k, (t, d) in enumerate(new_entries):
+            self.wal.put({"g": self.g, "e": [first_index + k, t, d.hex()]})
+        if hardstate is not None:
+            self.wal.put({"g": self.g, "hs": list(hardstate)})
+
+    def close(self):
+        pass  # the owner closes the shared file
+
+
+class _DeferredTransport:
+    """A group's transport whose sends wait in the node's outbox until the tick's WAL records are durable
+    (persist before send: wal.Save precedes transport.Send, raft.go:228-230)."""
+
+    def __init__(self, tr, owner: "MultiHostNode"):
+        self.tr, self.owner = tr, owner
+
+    def register(self, nid):
+        self.tr.register(nid)
+
+    def unregister(self, nid):
+        self.tr.unregister(nid)
+
+    def drain(self, nid):
+        return self.tr.drain(nid)
+
+    def send(self, msgs):
+        self.owner.outbox.append((self.tr, list(msgs)))
+
+
 class _GroupCore:
     """What HostNode needs from its consensus core, for ONE group of the shared engine: posts are collected by the
     owning MultiHostNode, reads come from the columns it exported after the shared tick."""
@@ -105,14 +226,14 @@ class MultiHostNode:
         self.state: dict = {}
         self.out = np.zeros(n_groups, np.uint32)
         self.views = [_GroupCore(self, g) for g in range(n_groups)]
-        self.nodes = [HostNode(self.views[g], nid, npeers, transport.group(g),
-                               os.path.join(waldir, f"group-{g}") if waldir else None) for g in range(n_groups)]
+        self.outbox: list = []
+        self.wal = MultiWal(waldir) if waldir else None  # group commit: one file, one fsync per tick
+        self.nodes = [HostNode(self.views[g], nid, npeers, _DeferredTransport(transport.group(g), self),
+                               self.wal.view(g) if self.wal else None) for g in range(n_groups)]
 
     def start(self) -> list[list[bytes]]:
         """replayWAL for every group (raft.go:122-134), then ONE import of the restored columns into the engine.
         Returns the committed payloads to replay, per group."""
-        if any(n.wal is not None for n in self.nodes):
-            os.makedirs(os.path.dirname(self.nodes[0].wal.dir), mode=0o750, exist_ok=True)
         cols = {k: np.zeros(self.G, np.uint64) for k in ("term", "vote", "committed", "last_index", "last_term")}
         for g, n in enumerate(self.nodes):
             n.start()
@@ -138,11 +259,23 @@ class MultiHostNode:
         self.core.tick(0)
         self.state = self.core.export_state(STATE_COLS)
         self.out = self.core.sync_out()
-        return [n.finish_tick(r) for n, r in zip(self.nodes, replies)]
+        published = [n.finish_tick(r) for n, r in zip(self.nodes, replies)]
+        self.flush()
+        return published
+
+    def flush(self):
+        """make this tick's WAL records of every group durable with one fsync, THEN let the messages out"""
+        if self.wal is not None:
+            self.wal.sync()
+        outbox, self.outbox = self.outbox, []
+        for tr, msgs in outbox:
+            tr.send(msgs)
 
     def stop(self):
         for n in self.nodes:
             n.stop()
+        if self.wal is not None:
+            self.wal.close()
 
 
 class MultiRaftPipe:
@@ -181,7 +314,7 @@ def NewMultiRaftPipe(id: int, peers, n_groups: int, proposeCs=None, *, tick_seco
     errorC = Chan()
     tr = transport or _shared_transport(tuple(peers), n_groups)
     core = core_factory(len(peers), id, n_groups, **core_kw)
-    wd = f"raftsql-{id}" if waldir == "auto" else waldir  # raft.go:69, one sub-directory per group
+    wd = f"raftsql-{id}" if waldir == "auto" else waldir  # raft.go:69; one group-commit file for all groups (MultiWal)
     node = MultiHostNode(core, id, len(peers), n_groups, tr, wd)
     stop = threading.Event()
 

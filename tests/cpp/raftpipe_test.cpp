@@ -438,6 +438,69 @@ void test_multi_group_cluster(const std::string &core, const std::string &dir) {
   for (int i = 0; i < 3; ++i) CHECK(mp[i]->Close().empty(), "Close node %d", i);
 }
 
+// The multi-group node's WAL is ONE file for all groups, made durable once per tick, and nothing leaves the node
+// before that fsync (wal.Save precedes transport.Send, raft.go:228-230).  tests/test_multipipe_cpu.py is the twin.
+void test_group_commit_wal(const std::string &dir) {
+  const size_t G = 5;
+  struct Checked : LocalTransport {
+    MultiHostNode **node;
+    int *violations;
+    void send(const std::vector<raftsql::Message> &msgs) override {
+      if (!msgs.empty() && *node && (*node)->wal()->dirty()) ++*violations;
+      LocalTransport::send(msgs);
+    }
+  };
+  MultiHostNode *nodep = nullptr;
+  int violations = 0;
+  auto tr = std::make_shared<MultiLocalTransport>(0);
+  for (size_t g = 0; g < G; ++g) {
+    auto c = std::make_shared<Checked>();
+    c->node = &nodep;
+    c->violations = &violations;
+    c->add(2);  // peers 2 and 3 exist as mailboxes only
+    c->add(3);
+    tr->groups.push_back(c);
+  }
+  const std::string wdir = dir + "/groupcommit";
+  MultiHostNode node(std::unique_ptr<MultiCore>(new OracleMultiCore(3, 1, G)), 1, 3, G, tr, wdir);
+  nodep = &node;
+  node.start();
+  int ticks = 0;
+  for (int t = 0; t < 60; ++t) {  // every group times out and campaigns at its own tick: HardState changes -> records
+    const uint64_t before = node.wal()->syncs();
+    node.step_tick();
+    ++ticks;
+    CHECK(node.wal()->syncs() - before <= 1, "at most one fsync per tick, however many groups wrote");
+    for (size_t g = 0; g < G; ++g) {  // node 2 grants every vote request it sees
+      for (const raftsql::Message &m : tr->groups[g]->drain(2))
+        if (m.type == kMsgVote) {
+          raftsql::Message r;
+          r.type = kMsgVoteResp;
+          r.to = 1;
+          r.from = 2;
+          r.term = m.term;
+          tr->groups[g]->send({r});
+        }
+      tr->groups[g]->drain(3);
+    }
+  }
+  for (size_t g = 0; g < G; ++g) CHECK(node.group(g)->role() == MRQ_ROLE_LEADER, "group %zu must have elected this node", g);
+  CHECK(violations == 0, "%d messages left the node before their tick's WAL records were durable", violations);
+  CHECK(node.wal()->syncs() > 0 && node.wal()->syncs() <= (uint64_t)ticks && node.wal()->syncs() < G * 3,
+        "%llu fsyncs for %zu groups over %d ticks", (unsigned long long)node.wal()->syncs(), G, ticks);
+  node.stop();
+  nodep = nullptr;
+  // and the one file replays every group: term, vote for self, the leader's empty entry
+  MultiWal again(wdir);
+  for (size_t g = 0; g < G; ++g) {
+    std::vector<Entry> ents;
+    bool has_hs = false;
+    uint64_t hs[3] = {0, 0, 0};
+    again.view((uint32_t)g)->read_all(&ents, &has_hs, hs);
+    CHECK(has_hs && hs[0] >= 1 && hs[1] == 1 && !ents.empty() && ents[0].data.empty(), "group %zu: replay of the shared file", g);
+  }
+}
+
 // upstream raft_test.go TestHandleMsgApp (recalled; each row re-derived from raftLog.maybeAppend / commitTo in
 // tests/test_hostnode_kat_cpu.py, which runs the same table over the Python host): follower of term 2 with the log
 // [1:t1, 2:t2], committed 0; the host resolves the append against its log, the core applies the outcome.
@@ -523,6 +586,7 @@ int main(int argc, char **argv) {
     test_chan_semantics();
     test_wal_recovery(dir);
     test_handle_msgapp_table(dir);
+    test_group_commit_wal(dir);
     test_single_node(core, dir);
     test_cluster_and_restart(core, dir);
     // over the GPU engine the multi-group scenario is opt-in until its first hardware run (tests/test_cpp_host.py)

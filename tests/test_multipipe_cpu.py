@@ -137,6 +137,58 @@ def test_stopped_node_replays_every_groups_wal_and_catches_up(tmp_path):
         c.close()
 
 
+def test_group_commit_wal_one_fsync_per_tick_and_persist_before_send(tmp_path, monkeypatch):
+    """The node's WAL is ONE file for all groups, made durable once per tick (a per-group WAL would fsync once per
+    writing group), and nothing leaves the node before that fsync (wal.Save precedes transport.Send, raft.go:228-230)."""
+    import os
+
+    from raftsql_b200 import multipipe
+    from raftsql_b200.hostnode import Message
+    from raftsql_b200 import _ffi as F
+
+    G = 5
+    fsyncs = []
+    real_fsync = os.fsync
+    monkeypatch.setattr(os, "fsync", lambda fd: (fsyncs.append(fd), real_fsync(fd))[1])
+    tr = MultiLocalTransport()
+    for g in range(G):  # peers 2 and 3 exist as mailboxes only
+        tr.group(g).register(2), tr.group(g).register(3)
+    core = make_oracle_multicore(3, 1, G)
+    node = multipipe.MultiHostNode(core, 1, 3, G, tr, str(tmp_path / "raftsql-1"))
+    sent_while_dirty = []
+    real_send = multipipe._GroupTransport.send
+
+    def checked_send(self, msgs):
+        if msgs and node.wal.dirty:
+            sent_while_dirty.append(msgs)
+        return real_send(self, msgs)
+
+    monkeypatch.setattr(multipipe._GroupTransport, "send", checked_send)
+    node.start()
+    ticks = 0
+    for _ in range(60):  # every group times out and campaigns at its own tick: HardState changes -> WAL records
+        before = len(fsyncs)
+        node.step_tick()
+        ticks += 1
+        assert len(fsyncs) - before <= 1, "at most one fsync per tick, however many groups wrote"
+        for g in range(G):  # node 2 grants every vote request it sees
+            for m in tr.group(g).drain(2):
+                if m.type == F.MSG_VOTE:
+                    tr.group(g).send([Message(F.MSG_VOTE_RESP, 1, 2, term=m.term)])
+            tr.group(g).drain(3)
+    roles = node.state["role"]
+    assert all(int(r) == 2 for r in roles), "every group elected this node with node 2's vote"
+    assert not sent_while_dirty, "a message left the node before its tick's WAL records were durable"
+    assert 0 < len(fsyncs) <= ticks and len(fsyncs) < G * 3, f"{len(fsyncs)} fsyncs for {G} groups over {ticks} ticks"
+    node.stop()
+    # and the one file replays every group: term, vote for self, the leader's empty entry
+    again = multipipe.MultiWal(str(tmp_path / "raftsql-1")).parse()
+    assert sorted(again) == list(range(G))
+    for g in range(G):
+        hs, ents = again[g]
+        assert hs[0] >= 1 and hs[1] == 1 and len(ents) >= 1 and ents[0][1] == b""
+
+
 def test_close_protocol(tmp_path):
     """Close() closes every ProposeC; every CommitC is closed; ErrorC closes with no value -> None"""
     c = Cluster(3, tmp_path)
