@@ -29,7 +29,21 @@ $(CPPTEST): tests/cpp/raftpipe_test.cpp $(HOSTLIB) oracle
 	$(CXX) $(CXXFLAGS) -o $@ tests/cpp/raftpipe_test.cpp -L$(ROOT)/raftsql_b200 -lraftpipe -lmrq -L$(ROOT)/oracle -loracle \
 	  -Wl,-rpath,$(ROOT)/raftsql_b200 -Wl,-rpath,$(ROOT)/oracle
 
+# The C++ host side and its scenario test under the sanitizers (CPU suite; oracle core only — no device code runs).
+# SAN_CXX: the first of $(CXX), g++, /usr/bin/g++ that ships the sanitizer runtimes (`make san_cxx` prints it).
+SAN_CXX := $(shell for c in $(CXX) g++ /usr/bin/g++; do f=`$$c -print-file-name=libtsan.so 2>/dev/null`; \
+	if [ -n "$$f" ] && [ "$$f" != libtsan.so ]; then echo $$c; break; fi; done)
+SAN_SRC := tests/cpp/raftpipe_test.cpp $(HOSTSRC) oracle/raft_oracle.c
+san_cxx:
+	@echo $(SAN_CXX)
+tests/cpp/raftpipe_test_asan: $(SAN_SRC) $(HOSTHDR) $(LIB)
+	$(SAN_CXX) -O1 -g -std=c++17 -pthread -fsanitize=address,undefined -fno-sanitize-recover=undefined -o $@ $(SAN_SRC) \
+	  -L$(ROOT)/raftsql_b200 -lmrq -Wl,-rpath,$(ROOT)/raftsql_b200
+tests/cpp/raftpipe_test_tsan: $(SAN_SRC) $(HOSTHDR) $(LIB)
+	$(SAN_CXX) -O1 -g -std=c++17 -pthread -fsanitize=thread -o $@ $(SAN_SRC) \
+	  -L$(ROOT)/raftsql_b200 -lmrq -Wl,-rpath,$(ROOT)/raftsql_b200
+
 clean:
-	rm -f $(LIB) $(HOSTLIB) $(CPPTEST) build_ptxas.log
+	rm -f $(LIB) $(HOSTLIB) $(CPPTEST) tests/cpp/raftpipe_test_asan tests/cpp/raftpipe_test_tsan build_ptxas.log
 	$(MAKE) -C oracle clean
-.PHONY: all oracle clean
+.PHONY: all oracle clean san_cxx

@@ -10,6 +10,7 @@
 
 #include <stdint.h>
 
+#include <atomic>
 #include <cstdio>
 #include <map>
 #include <memory>
@@ -182,8 +183,11 @@ class HostNode {
   std::vector<uint64_t> next_;
   std::set<uint32_t> behind_;
   std::vector<Message> backlog_;
-  uint64_t applied_ = 0, term_ = 0, vote_ = 0, commit_ = 0;
-  uint32_t role_ = 0, lead_ = 0;
+  uint64_t applied_ = 0, vote_ = 0;
+  uint32_t lead_ = 0;
+  // read by role() / term() / commit() from other threads (operators, tests) while the node's thread advances them
+  std::atomic<uint64_t> term_{0}, commit_{0};
+  std::atomic<uint32_t> role_{0};
   bool stopped_ = false;
 };
 

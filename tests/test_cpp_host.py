@@ -40,6 +40,22 @@ def test_cpp_raftpipe_scenarios_oracle_core(tmp_path):
     _run("oracle", tmp_path)
 
 
+@pytest.mark.parametrize("san,env", [("asan", {"ASAN_OPTIONS": "detect_leaks=1"}), ("tsan", {"TSAN_OPTIONS": "halt_on_error=1"})])
+def test_cpp_host_under_sanitizers(tmp_path, san, env):
+    """The same scenarios with the C++ host compiled under AddressSanitizer + UBSan (+ leak check) and under
+    ThreadSanitizer: the seam is threads and channels, so memory errors and data races are what to look for.
+    (Oracle core: no device code runs in these builds.)"""
+    cxx = subprocess.run(["make", "-s", "--no-print-directory", "-C", ROOT, "san_cxx"], capture_output=True, text=True).stdout.strip()
+    if not cxx:
+        pytest.skip("no C++ compiler with the sanitizer runtimes on this machine")
+    exe = os.path.join(ROOT, "tests", "cpp", f"raftpipe_test_{san}")
+    subprocess.check_call(["make", "-C", ROOT, f"tests/cpp/raftpipe_test_{san}"], stdout=subprocess.DEVNULL)
+    r = subprocess.run([exe, "oracle", str(tmp_path)], capture_output=True, text=True, timeout=900, env=dict(os.environ, **env))
+    out = r.stdout + r.stderr
+    assert r.returncode == 0 and "raftpipe_test: ok" in out, out[-3000:]
+    assert "ThreadSanitizer" not in out and "AddressSanitizer" not in out and "runtime error" not in out, out[-3000:]
+
+
 @pytest.mark.gpu
 def test_cpp_raftpipe_scenarios_gpu_engine(tmp_path):
     _run("engine", tmp_path)
