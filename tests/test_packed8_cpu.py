@@ -138,6 +138,55 @@ def test_window_follows_a_steady_state_leader_without_escapes():
     assert word.nbytes + p8.nbytes == G * R  # (R-1) sender bytes + 1 proposal byte per group
 
 
+@pytest.mark.parametrize("G,R", [(1, 2), (7, 3), (1000, 5), (33333, 8), (65, 1)])
+def test_frame_builder_writes_only_inside_its_output_buffers(G, R):
+    """canaries around word_out / prop8_out / the decode's output columns: mrq_pack8 and mrq_unpack8 must not write a
+    byte outside [R-1][G] / [G] / [R][G] (the library is C: numpy would not notice)"""
+    rng = np.random.default_rng(G + R)
+    PAD = 4096
+
+    def guarded(shape, dtype):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        raw = np.full(n + 2 * PAD, 0xA5, np.uint8)
+        return raw, raw[PAD:PAD + n].view(dtype).reshape(shape)
+
+    self_id = rng.integers(1, R + 1, size=G).astype(np.uint8)
+    base_i = rng.integers(100, 1 << 40, size=G).astype(np.uint64)
+    base_t = rng.integers(1, 9, size=G).astype(np.uint64)
+    ib = oracle.empty_inbox(G, R)
+    ib["type"][:] = rng.choice(np.array([0, 4, 4, 4, 8, 9, 6, 5, 3], np.uint8), size=(R, G))
+    ib["term"][:] = base_t[None, :]
+    ib["index"][:] = base_i[None, :] + rng.integers(0, 80, size=(R, G)).astype(np.uint64)
+    ib["commit"][:] = base_i[None, :] + rng.integers(0, 80, size=(R, G)).astype(np.uint64)
+    ib["prop_count"][:] = rng.integers(0, 200, size=G)
+    raw_w, word = guarded((max(R - 1, 0), G), np.uint8)
+    raw_p, p8 = guarded((G,), np.uint8)
+    pk = Pack8(self_id, base_i, base_t, R)
+    before = pk.base_index.copy()
+    for _ in range(3):
+        _, _, wide = pk.frame(ib, word_out=word, prop8_out=p8)
+    for raw in (raw_w, raw_p):
+        assert (raw[:PAD] == 0xA5).all() and (raw[-PAD:] == 0xA5).all(), "mrq_pack8 wrote outside its output buffer"
+    # the decode side, through the raw ABI with guarded columns
+    L = F.load()
+    cols, raws = {}, []
+    for k, dt in (("type", np.uint8), ("term", np.uint64), ("index", np.uint64), ("logterm", np.uint64), ("commit", np.uint64)):
+        raw, cols[k] = guarded((R, G), dt)
+        raws.append(raw)
+    raw_b, base = guarded((G,), np.uint64)
+    base[:] = before
+    import ctypes as C
+
+    view = F.InboxOut(*(cols[k].ctypes.data_as(t) for k, t in (("type", F.u8p), ("term", F.u64p), ("index", F.u64p),
+                                                              ("logterm", F.u64p), ("commit", F.u64p))), None)
+    word0, _, _ = Pack8(self_id, before, base_t, R).frame(ib)
+    rc = L.mrq_unpack8(word0.ctypes.data_as(F.u8p) if word0.size else None, self_id.ctypes.data_as(F.u8p), G, R,
+                       base.ctypes.data_as(F.u64p), base_t.ctypes.data_as(F.u64p), C.byref(view))
+    assert rc == F.MRQ_OK
+    for raw in raws + [raw_b]:
+        assert (raw[:PAD] == 0xA5).all() and (raw[-PAD:] == 0xA5).all(), "mrq_unpack8 wrote outside its output buffer"
+
+
 def test_frame_is_the_same_on_one_and_on_many_host_threads(monkeypatch):
     """mrq_pack8 splits large frames into contiguous group ranges on host threads: bytes, escape order (group
     order) and the slid bases must not depend on how many."""
