@@ -226,7 +226,9 @@ def run_ours(args):
         torch.cuda.set_device(local)
     dev = local
     assert G_TOTAL % world == 0
-    G = G_TOTAL // world
+    weak = bool(getattr(args, "weak", False)) and world > 1  # --weak: every GPU keeps 1,048,576 groups (job = N x that)
+    G = G_TOTAL if weak else G_TOTAL // world
+    groups_job = G * world
     base = rank * G
     K, W = args.steps, max(3, args.warmup)
     nslots = min(K + W, MAX_SLOTS)
@@ -322,17 +324,17 @@ def run_ours(args):
     tick_gbs = tb["total"] * G / (tick_kernel_ms * 1e-3) / 1e9
     line = {
         "metric": "raft_ticks_per_sec_1Mx5", "value": ticks_per_s, "unit": "ticks/s", "n_gpus": world, "steps": K,
-        "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
         "config": {"workload": "1,048,576 groups x 5 replicas, steady-state append/ack trace (BASELINE configs[2]/[3])",
-                   "groups_total": G_TOTAL, "groups_per_gpu": G, "replicas": R, "parallelism": f"groups sharded x{world}",
+                   "groups_total": groups_job, "groups_per_gpu": G, "replicas": R, "parallelism": f"groups sharded x{world}",
                    "collective": ("none" if world == 1 else
                                   "all-gather of committed[] per tick, fused into the tick kernel as peer stores over NVLink"
                                   if args.gather == "fused" else "ncclAllGather(committed) per tick" if args.gather == "nccl"
                                   else "none in the timed region (--gather none: shards tick independently; SURVEY 8d config 4)"),
                    "l2": f"inputs larger than L2: {nslots} rotating inbox slots, per-step footprint "
                          f"{(tb['total'] * G) / 1e6:.0f} MB vs 126 MB L2"},
-        "group_ticks_per_sec": ticks_per_s * G_TOTAL,
+        "group_ticks_per_sec": ticks_per_s * groups_job,
         "roofline": {"bound": "hbm", "kernel": "tick_fast_kernel<5> (+ tick_slow_kernel<5> over the slow list, empty on this trace)",
                      "achieved": tick_gbs, "peak": peak, "unit": "GB/s",
                      "frac": tick_gbs / peak, "traffic": ncu_traffic("tick_fast_kernel<5>") if world == 1 else None,
@@ -665,6 +667,9 @@ def main():
                     help="L2 residency hints of the tick kernel (default: the engine's, on)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="CUDA-graph replay of the tick sequence (auto: only for small shards)")
+    ap.add_argument("--weak", action="store_true",
+                    help="N>1: weak scaling — every GPU keeps 1,048,576 groups, the job is N times that (default: the job "
+                         "stays 1,048,576 groups, BASELINE configs[3]); compare group_ticks_per_sec across N")
     ap.add_argument("--e2e8-child", action="store_true", help=argparse.SUPPRESS)  # internal: see run_e2e8_child
     args = ap.parse_args()
     if args.e2e8_child:
