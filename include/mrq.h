@@ -215,7 +215,8 @@ int mrq_post_inbox_packed(mrq_engine *e, uint32_t slot, const mrq_inbox_packed *
 /* Dense [G] decode bases for the packed form (NULL keeps the current column).  Blocking. */
 int mrq_set_packed_base(mrq_engine *e, const uint64_t *base_index, const uint64_t *base_term);
 
-/* Host-side frame builder for the byte form: PURE CPU CODE (no engine, no device; usable from any thread).
+/* Host-side frame builder for the byte form — the batched stand-in for rafthttp handing messages to
+ * node.Step one at a time (reference raft.go:268-270): PURE CPU CODE (no engine, no device; usable from any thread).
  * Encodes the wide dense inbox `in` ([R][G] columns; prop_count may be NULL) of groups whose own ids are
  * self_id[G] (1..R) into word_out[R-1][G] (+ prop8_out[G] if not NULL), appends what does not fit to wide_out
  * (at most wide_cap entries; *n_wide = how many were needed) and slides base_index[G] exactly as the device
