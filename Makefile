@@ -43,7 +43,18 @@ tests/cpp/raftpipe_test_tsan: $(SAN_SRC) $(HOSTHDR) $(LIB)
 	$(SAN_CXX) -O1 -g -std=c++17 -pthread -fsanitize=thread -o $@ $(SAN_SRC) \
 	  -L$(ROOT)/raftsql_b200 -lmrq -Wl,-rpath,$(ROOT)/raftsql_b200
 
+# The per-group tick functions of mrq_kernels.cuh compiled for the HOST and run against the oracle (CPU suite):
+# the device arithmetic, same source, checked where there is no GPU.  The _san build adds ASan + UBSan.
+CUDA_INC ?= /usr/local/cuda/include
+TICKHOST_SRC := tests/cpp/tick_host_test.cpp oracle/raft_oracle.c
+TICKHOST_DEP := $(TICKHOST_SRC) tests/cpp/device_on_host.hpp oracle/raft_oracle.h $(HDR)
+tests/cpp/tick_host_test: $(TICKHOST_DEP)
+	$(CXX) -std=c++17 -O1 -I$(CUDA_INC) -pthread -o $@ $(TICKHOST_SRC)
+tests/cpp/tick_host_test_san: $(TICKHOST_DEP)
+	$(SAN_CXX) -std=c++17 -O0 -fsanitize=address,undefined -fno-sanitize-recover=undefined -I$(CUDA_INC) -pthread -o $@ $(TICKHOST_SRC)
+
 clean:
-	rm -f $(LIB) $(HOSTLIB) $(CPPTEST) tests/cpp/raftpipe_test_asan tests/cpp/raftpipe_test_tsan build_ptxas.log
+	rm -f $(LIB) $(HOSTLIB) $(CPPTEST) tests/cpp/raftpipe_test_asan tests/cpp/raftpipe_test_tsan build_ptxas.log \
+	  tests/cpp/tick_host_test tests/cpp/tick_host_test_san
 	$(MAKE) -C oracle clean
 .PHONY: all oracle clean san_cxx

@@ -97,6 +97,10 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- cache-hinted accessors ---------------------------------------------------------------------
+// (MRQ_HOST_EMULATION is defined only by tests/cpp/tick_host_test.cpp, which compiles the per-group tick
+// functions of this header for the HOST and runs them over host arrays against the oracle; product builds
+// never define it, so the block below is what they have always compiled.)
+#ifndef MRQ_HOST_EMULATION
 // Inbox columns are read exactly once per tick: stream them (read-only path, no L1 allocation).
 __device__ __forceinline__ uint64_t ld_stream(const uint64_t *p) {
   uint64_t v;
@@ -168,6 +172,21 @@ __device__ __forceinline__ void st_state_p(uint64_t *p, uint64_t v, uint64_t pol
 __device__ __forceinline__ void st_state_u32_p(uint32_t *p, uint32_t v, uint64_t pol) {
   asm volatile("st.global.L1::no_allocate.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
 }
+#else  // MRQ_HOST_EMULATION: the same accessors as plain memory operations
+inline uint64_t ld_stream(const uint64_t *p) { return *p; }
+inline uint32_t ld_stream_u8(const uint8_t *p) { return *p; }
+inline uint32_t ld_stream_u32(const uint32_t *p) { return *p; }
+inline uint64_t ld_state(const uint64_t *p) { return *p; }
+inline void st_state(uint64_t *p, uint64_t v) { *p = v; }
+inline void st_state_u32(uint32_t *p, uint32_t v) { *p = v; }
+inline uint64_t l2_policy(uint32_t) { return 0; }
+inline uint64_t ld_stream_p(const uint64_t *p, uint64_t) { return *p; }
+inline uint32_t ld_stream_u8_p(const uint8_t *p, uint64_t) { return *p; }
+inline uint32_t ld_stream_u32_p(const uint32_t *p, uint64_t) { return *p; }
+inline uint64_t ld_state_p(const uint64_t *p, uint64_t) { return *p; }
+inline void st_state_p(uint64_t *p, uint64_t v, uint64_t) { *p = v; }
+inline void st_state_u32_p(uint32_t *p, uint32_t v, uint64_t) { *p = v; }
+#endif
 
 // ---- q-th largest of R values held in registers (a15: mis[q()-1] after a descending sort) -------
 // 64-bit form: partial selection by bubbling maxima (q passes; R=5: 9 compare-exchanges, each
@@ -231,11 +250,18 @@ __device__ __forceinline__ uint32_t quorum_index32(const uint32_t (&d)[R]) {
 // b = all-ones iff m < c (behind: clamps to 0 whatever the distance), hi != 0 otherwise means too far ahead.
 __device__ __forceinline__ void delta32(uint64_t m, uint64_t c, uint32_t &d, uint32_t &bad) {
   uint32_t lo, hi, b;
+#ifndef MRQ_HOST_EMULATION
   asm("sub.cc.u32 %0, %3, %5;\n\t"
       "subc.cc.u32 %1, %4, %6;\n\t"
       "subc.u32 %2, 0, 0;"
       : "=r"(lo), "=r"(hi), "=r"(b)
       : "r"((uint32_t)m), "r"((uint32_t)(m >> 32)), "r"((uint32_t)c), "r"((uint32_t)(c >> 32)));
+#else  // the same borrow chain in C
+  const uint64_t diff = m - c;
+  lo = (uint32_t)diff;
+  hi = (uint32_t)(diff >> 32);
+  b = m < c ? 0xFFFFFFFFu : 0u;
+#endif
   d = ((b | hi) == 0u) ? lo : 0u;
   bad |= ~b & hi;
 }

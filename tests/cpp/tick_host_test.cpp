@@ -1,0 +1,250 @@
+// tick_host_test.cpp — the DEVICE source of the tick, compiled for the host and run against the oracle.
+//
+// raftsql_b200/csrc/mrq_kernels.cuh is included as it is (tests/cpp/device_on_host.hpp supplies the CUDA vocabulary;
+// MRQ_HOST_EMULATION turns the cache-hinted PTX accessors into plain loads/stores and the borrow-chain asm of
+// delta32 into the same arithmetic in C).  What runs here is, line for line, what one GPU thread runs for one group:
+//
+//     fast_group_tick<R>(args, g, slow, ev);   if (slow) general_group_tick<R>(args, g);
+//
+// over host arrays in the engine's layout ([R][gs] replica-major columns, packed meta word), for every group, every
+// tick, on the synthetic traces — and after every tick all state columns and the out word must equal the oracle's.
+// This does not replace the GPU parity tests (it cannot see launch geometry, warp collectives or memory ordering);
+// it lets the arithmetic of BOTH tick paths be checked on a machine without a GPU, which is where device code is
+// written between GPU sessions.
+//
+//   tick_host_test                 all cases;   exit code 0 and "tick_host_test: ok" on success
+#include "device_on_host.hpp"
+
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../../raftsql_b200/csrc/mrq_kernels.cuh"
+#include "../../oracle/raft_oracle.h"
+
+using namespace mrq;
+
+namespace {
+
+int failures = 0;
+
+struct HostEngine {  // the engine's state and one inbox slot, in host memory, engine layout
+  uint64_t G, gs;
+  uint32_t R;
+  std::vector<uint64_t> term, meta, last_index, last_term, committed, term_start, match;
+  std::vector<uint32_t> out;
+  std::vector<uint8_t> itype;
+  std::vector<uint64_t> iterm, iindex, ilogterm, icommit;
+  std::vector<uint32_t> iprop;
+  uint64_t tick_no[2] = {0, 0};
+  uint64_t fast_groups = 0, slow_groups = 0;
+
+  HostEngine(uint64_t G_, uint32_t R_) : G(G_), gs(((G_ + 127) / 128) * 128), R(R_) {
+    for (auto *v : {&term, &meta, &last_index, &last_term, &committed, &term_start}) v->assign(gs, 0);
+    match.assign(gs * R, 0);
+    out.assign(gs, 0);
+    itype.assign(gs * R, 0);
+    for (auto *v : {&iterm, &iindex, &ilogterm, &icommit}) v->assign(gs * R, 0);
+    iprop.assign(gs, 0);
+  }
+
+  TickArgs args(uint64_t group_base, uint64_t seed, uint32_t et, uint32_t ht, bool with_inbox) {
+    TickArgs a{};
+    a.s = StateView{term.data(), meta.data(), last_index.data(), last_term.data(), committed.data(), term_start.data(),
+                    match.data(), out.data()};
+    if (with_inbox) a.in = InboxView{itype.data(), iterm.data(), iindex.data(), ilogterm.data(), icommit.data(), iprop.data()};
+    a.G = G;
+    a.gs = gs;
+    a.group_base = group_base;
+    a.seed = seed;
+    a.tick_cur = &tick_no[0];
+    a.tick_next = &tick_no[1];
+    a.election_tick = et;
+    a.heartbeat_tick = ht;
+    a.world = 1;
+    a.l2_policy = 1;
+    return a;
+  }
+};
+
+// what tick_fast_kernel + tick_slow_kernel do, one "thread" at a time (mode 0), or tick_general_kernel (mode 1)
+template <int R>
+void host_tick(HostEngine &e, const TickArgs &a, int mode) {
+  for (uint64_t i = 0; i < e.G; ++i) {
+    if (mode == 1) {
+      general_group_tick<R>(a, i);
+      ++e.slow_groups;
+      continue;
+    }
+    bool slow = false;
+    uint32_t ev = 0;
+    fast_group_tick<R>(a, i, slow, ev);
+    if (slow) {
+      general_group_tick<R>(a, i);
+      ++e.slow_groups;
+    } else {
+      ++e.fast_groups;
+    }
+  }
+  e.tick_no[0] += 1;
+}
+
+void dispatch_tick(HostEngine &e, const TickArgs &a, int mode) {
+  switch (e.R) {
+    case 1: host_tick<1>(e, a, mode); break;
+    case 2: host_tick<2>(e, a, mode); break;
+    case 3: host_tick<3>(e, a, mode); break;
+    case 4: host_tick<4>(e, a, mode); break;
+    case 5: host_tick<5>(e, a, mode); break;
+    case 6: host_tick<6>(e, a, mode); break;
+    case 7: host_tick<7>(e, a, mode); break;
+    case 8: host_tick<8>(e, a, mode); break;
+  }
+}
+
+struct OracleCols {
+  std::vector<uint64_t> term, vote, committed, last_index, last_term, term_start, match;
+  std::vector<uint8_t> role, lead, self_id, votes;
+  std::vector<uint16_t> el, hb, rto;
+  std::vector<uint32_t> out;
+  OracleCols(uint64_t G, uint32_t R)
+      : term(G), vote(G), committed(G), last_index(G), last_term(G), term_start(G), match(G * R), role(G), lead(G), self_id(G),
+        votes(G * R), el(G), hb(G), rto(G), out(G) {}
+  void load(orc_engine *o) {
+    orc_export(o, term.data(), vote.data(), committed.data(), last_index.data(), last_term.data(), term_start.data(), match.data(),
+               role.data(), lead.data(), self_id.data(), votes.data(), el.data(), hb.data(), rto.data(), out.data());
+  }
+};
+
+// oracle state -> engine layout (what mrq_import_state + pack_meta_kernel + fix_strict_kernel do)
+void import_from_oracle(HostEngine &e, const OracleCols &c) {
+  for (uint64_t g = 0; g < e.G; ++g) {
+    e.term[g] = c.term[g];
+    e.last_index[g] = c.last_index[g];
+    e.last_term[g] = c.last_term[g];
+    e.committed[g] = c.committed[g];
+    e.term_start[g] = c.term_start[g];
+    Meta m{};
+    m.role = c.role[g];
+    m.lead = c.lead[g];
+    m.vote = (uint32_t)c.vote[g];
+    m.self = c.self_id[g];
+    m.elapsed = c.el[g];
+    m.rto = c.rto[g];
+    m.hb = c.hb[g];
+    m.votes = 0;
+    m.strict = 0;
+    for (uint32_t r = 0; r < e.R; ++r) {
+      e.match[(uint64_t)r * e.gs + g] = c.match[(uint64_t)r * e.G + g];
+      m.votes |= (uint32_t)(c.votes[(uint64_t)r * e.G + g] & 3u) << (2 * r);
+      if (c.match[(uint64_t)r * e.G + g] > c.last_index[g]) m.strict = 1;
+    }
+    m.ltok = c.last_term[g] == c.term[g] ? 1u : 0u;
+    e.meta[g] = meta_pack(m);
+  }
+}
+
+bool compare(const HostEngine &e, const OracleCols &c, const char *where, uint64_t tick) {
+  for (uint64_t g = 0; g < e.G; ++g) {
+    const Meta m = meta_unpack(e.meta[g]);
+    const uint64_t lt = m.ltok ? e.term[g] : e.last_term[g];
+    bool ok = e.term[g] == c.term[g] && m.vote == c.vote[g] && e.committed[g] == c.committed[g] &&
+              e.last_index[g] == c.last_index[g] && lt == c.last_term[g] && m.role == c.role[g] && m.lead == c.lead[g] &&
+              m.elapsed == c.el[g] && m.hb == c.hb[g] && m.rto == c.rto[g] && e.out[g] == c.out[g];
+    for (uint32_t r = 0; ok && r < e.R; ++r) {
+      ok = ((m.votes >> (2 * r)) & 3u) == c.votes[(uint64_t)r * e.G + g];
+      if (ok && c.role[g] == MRQ_ROLE_LEADER) ok = e.match[(uint64_t)r * e.gs + g] == c.match[(uint64_t)r * e.G + g];
+    }
+    if (ok && c.role[g] == MRQ_ROLE_LEADER) ok = e.term_start[g] == c.term_start[g];
+    if (!ok) {
+      std::printf("FAIL %s tick %llu group %llu: term %llu/%llu commit %llu/%llu li %llu/%llu role %u/%u lead %u/%u el %u/%u rto %u/%u "
+                  "out %08x/%08x\n",
+                  where, (unsigned long long)tick, (unsigned long long)g, (unsigned long long)e.term[g], (unsigned long long)c.term[g],
+                  (unsigned long long)e.committed[g], (unsigned long long)c.committed[g], (unsigned long long)e.last_index[g],
+                  (unsigned long long)c.last_index[g], m.role, c.role[g], m.lead, c.lead[g], m.elapsed, c.el[g], m.rto, c.rto[g],
+                  e.out[g], c.out[g]);
+      ++failures;
+      return false;
+    }
+  }
+  return true;
+}
+
+mrq_trace_params preset(uint32_t cfg) {
+  mrq_trace_params p = mrq_trace_preset(cfg);
+  if (cfg == 6) {  // follower heavy: deposed by heartbeats, then heart-beaten (tests/test_oracle_vs_pymodel.py)
+    p = mrq_trace_preset(5);
+    p.seed = 0x5EED0006ull;
+    p.p_grant_256 = 150;
+    p.p_reject_256 = 60;
+    p.churn_65536 = 900;
+    p.p_heartbeat_256 = 235;
+    p.lagging_pct = 0;
+  }
+  return p;
+}
+
+void run_case(uint64_t G, uint32_t R, uint32_t cfg, int T, int mode, uint32_t self_id, uint64_t group_base) {
+  char where[96];
+  std::snprintf(where, sizeof where, "G=%llu R=%u cfg=%u mode=%d", (unsigned long long)G, R, cfg, mode);
+  const uint64_t seed = 0x5EED0000ull + cfg * 131 + R;
+  orc_engine *o = orc_create(G, R, group_base, 10, 1, seed, self_id);
+  HostEngine e(G, R);
+  OracleCols c(G, R);
+  c.load(o);
+  import_from_oracle(e, c);
+  const mrq_trace_params p = preset(cfg);
+  std::vector<uint8_t> type(G * R);
+  std::vector<uint64_t> term(G * R), index(G * R), logterm(G * R), commit(G * R);
+  std::vector<uint32_t> prop(G);
+  for (int t = 0; t < T; ++t) {
+    orc_gen_trace(o, &p, (uint64_t)t, type.data(), term.data(), index.data(), logterm.data(), commit.data(), prop.data(), 1);
+    const bool idle = (t % 17) == 16;  // every so often an idle tick (no inbox at all: timers only)
+    if (!idle) {
+      for (uint32_t r = 0; r < R; ++r) {  // dense [R][G] -> engine [R][gs]
+        std::memcpy(&e.itype[(uint64_t)r * e.gs], &type[(uint64_t)r * G], G);
+        std::memcpy(&e.iterm[(uint64_t)r * e.gs], &term[(uint64_t)r * G], G * 8);
+        std::memcpy(&e.iindex[(uint64_t)r * e.gs], &index[(uint64_t)r * G], G * 8);
+        std::memcpy(&e.ilogterm[(uint64_t)r * e.gs], &logterm[(uint64_t)r * G], G * 8);
+        std::memcpy(&e.icommit[(uint64_t)r * e.gs], &commit[(uint64_t)r * G], G * 8);
+      }
+      std::memcpy(e.iprop.data(), prop.data(), G * 4);
+      orc_tick(o, type.data(), term.data(), index.data(), logterm.data(), commit.data(), prop.data(), 1);
+    } else {
+      orc_tick(o, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1);
+    }
+    const TickArgs a = e.args(group_base, seed, 10, 1, !idle);
+    dispatch_tick(e, a, mode);
+    c.load(o);
+    if (!compare(e, c, where, (uint64_t)t)) break;
+  }
+  if (orc_errors(o) != 0) {
+    std::printf("FAIL %s: the oracle counted %llu errors\n", where, (unsigned long long)orc_errors(o));
+    ++failures;
+  }
+  std::printf("  %-34s %4d ticks  fast %9llu  general %9llu\n", where, T, (unsigned long long)e.fast_groups,
+              (unsigned long long)e.slow_groups);
+  orc_destroy(o);
+}
+
+}  // namespace
+
+int main(int argc, char **) {
+  const bool quick = argc > 1;  // any argument: the sanitizer builds run a smaller matrix (they are ~20x slower)
+  const uint64_t k = quick ? 4 : 1;
+  // election + replication (cfg 2), lag + churn (5), follower/heartbeat heavy (6), steady state (3); every R;
+  // mode 0 = fast path with the general path for the rest (the product's default), mode 1 = general path only
+  for (uint32_t R = 1; R <= 8; ++R) {
+    run_case(257 / k + 1, R, 2, 220, 0, 0, 0);
+    run_case(200 / k, R, 5, 260, 0, 0, 1000);
+  }
+  run_case(300 / k, 3, 6, 300, 0, 0, 0);
+  run_case(300 / k, 5, 6, 300, 0, 0, 7);
+  run_case(300 / k, 7, 6, 300, 1, 0, 0);
+  run_case(513 / k, 5, 5, 300, 1, 0, 0);
+  run_case(400 / k, 5, 2, 200, 0, 3, 0);  // a fixed self id (the G = 1 per node shape, many at once)
+  run_case(400 / k, 5, 3, 120, 0, 0, 0);  // steady-state preset of the bench (from a cold start)
+  if (!quick) run_case(1000, 3, 2, 1024, 0, 0, 0);  // BASELINE configs[1] shape, all 1,024 ticks
+  std::printf(failures ? "tick_host_test: %d failure(s)\n" : "tick_host_test: ok\n", failures);
+  return failures ? 1 : 0;
+}
