@@ -98,8 +98,8 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 
 // ---- cache-hinted accessors ---------------------------------------------------------------------
 // (MRQ_HOST_EMULATION is defined only by tests/cpp/tick_host_test.cpp, which compiles the per-group tick
-// functions of this header for the HOST and runs them over host arrays against the oracle; product builds
-// never define it, so the block below is what they have always compiled.)
+// functions of this header for the HOST and runs them over host arrays against the CPU checker; product
+// builds never define it, so the block below is what they have always compiled.)
 #ifndef MRQ_HOST_EMULATION
 // Inbox columns are read exactly once per tick: stream them (read-only path, no L1 allocation).
 __device__ __forceinline__ uint64_t ld_stream(const uint64_t *p) {
