@@ -1241,11 +1241,10 @@ __global__ void __launch_bounds__(256) unpack16_inbox_kernel(InboxView in, const
 // left out (the own id is the static `self` field of meta: it never changes while the engine runs, so the
 // decode is still independent of anything a pipelined host could be behind on).  Also slides the window:
 // base_index is read, used for this frame, and advanced for the next one.
-__global__ void __launch_bounds__(256) unpack8_inbox_kernel(InboxView in, const uint64_t *meta, uint64_t *base_index,
-                                                             const uint64_t *base_term, uint64_t gs, uint64_t G,
-                                                             uint32_t R, const uint8_t *word, const uint8_t *prop8) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= G) return;
+// (the per-group body is a function of its own so that tests/cpp/tick_host_test.cpp can run it on the host)
+__device__ __forceinline__ void unpack8_group(const InboxView &in, const uint64_t *meta, uint64_t *base_index,
+                                              const uint64_t *base_term, uint64_t gs, uint32_t R, const uint8_t *word,
+                                              const uint8_t *prop8, const uint64_t i) {
   const uint32_t self = meta_unpack(meta[i]).self;
   const uint64_t bi = base_index[i], bt = base_term[i];
   uint32_t min_ack = MRQ_P8_NO_ACK;
@@ -1272,6 +1271,13 @@ __global__ void __launch_bounds__(256) unpack8_inbox_kernel(InboxView in, const 
   const uint64_t nb = mrq_p8_next_base(bi, min_ack);
   if (nb != bi) base_index[i] = nb;
   if (in.prop) in.prop[i] = prop8 ? prop8[i] : 0u;
+}
+__global__ void __launch_bounds__(256) unpack8_inbox_kernel(InboxView in, const uint64_t *meta, uint64_t *base_index,
+                                                             const uint64_t *base_term, uint64_t gs, uint64_t G,
+                                                             uint32_t R, const uint8_t *word, const uint8_t *prop8) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G) return;
+  unpack8_group(in, meta, base_index, base_term, gs, R, word, prop8, i);
 }
 
 // Compact commit drain: delta = committed - prev (saturated to 255), prev = committed.

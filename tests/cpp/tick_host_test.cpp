@@ -8,6 +8,9 @@
 //
 // over host arrays in the engine's layout ([R][gs] replica-major columns, packed meta word), for every group, every
 // tick, on the synthetic traces — and after every tick all state columns and the out word must equal the oracle's.
+// The byte-form inbox goes the same way: unpack8_group — the body of unpack8_inbox_kernel — decodes frames built
+// with the shared inline codec, the ticks run on what it wrote, and the device's sliding window must stay in step
+// with the frame builder's (run_case8).
 // This does not replace the GPU parity tests (it cannot see launch geometry, warp collectives or memory ordering);
 // it lets the arithmetic of BOTH tick paths be checked on a machine without a GPU, which is where device code is
 // written between GPU sessions.
@@ -227,6 +230,93 @@ void run_case(uint64_t G, uint32_t R, uint32_t cfg, int T, int mode, uint32_t se
   orc_destroy(o);
 }
 
+// The byte form of the packed inbox (include/mrq_packed8.h) through the DEVICE decode: every tick's wide inbox is
+// encoded to R-1 bytes per group with the shared inline codec (escapes to a wide list), decoded into the engine's
+// inbox columns by unpack8_group — the body of unpack8_inbox_kernel — the escapes scattered over it as
+// scatter_msgs_kernel does, and the tick functions run on the result; state must still equal the oracle's, which
+// was fed the wide inbox, and the device's sliding window must stay in step with the encoder's.
+void run_case8(uint64_t G, uint32_t R, uint32_t cfg, int T, int rebase_every, int also_rebase_at = -1) {
+  char where[96];
+  std::snprintf(where, sizeof where, "byte form G=%llu R=%u cfg=%u", (unsigned long long)G, R, cfg);
+  const uint64_t seed = 0x5EED8000ull + cfg * 131 + R;
+  orc_engine *o = orc_create(G, R, 0, 10, 1, seed, 0);
+  HostEngine e(G, R);
+  OracleCols c(G, R);
+  c.load(o);
+  import_from_oracle(e, c);
+  const mrq_trace_params p = preset(cfg);
+  std::vector<uint8_t> type(G * R), word(e.gs * (R > 1 ? R - 1 : 1)), prop8(e.gs);
+  std::vector<uint64_t> term(G * R), index(G * R), logterm(G * R), commit(G * R);
+  std::vector<uint32_t> prop(G);
+  std::vector<uint64_t> dev_base(e.gs, 0), enc_base(G, 0), base_term(e.gs, 0);
+  uint64_t n_bytes = 0, n_escapes = 0;
+  for (int t = 0; t < T; ++t) {
+    if (t % rebase_every == 0 || t == also_rebase_at) {  // the host re-bases now and then (terms move), as a real one would
+      c.load(o);
+      for (uint64_t g = 0; g < G; ++g) {
+        enc_base[g] = dev_base[g] = c.last_index[g] > 30 ? c.last_index[g] - 30 : 0;
+        base_term[g] = c.term[g];
+      }
+    }
+    orc_gen_trace(o, &p, (uint64_t)t, type.data(), term.data(), index.data(), logterm.data(), commit.data(), prop.data(), 1);
+    struct Esc {
+      uint64_t g;
+      uint32_t r;
+    };
+    std::vector<Esc> esc;
+    for (uint64_t g = 0; g < G; ++g) {  // the frame builder (what mrq_pack8 does), on the shared inline codec
+      const uint32_t self = c.self_id[g];
+      uint32_t min_ack = MRQ_P8_NO_ACK;
+      for (uint32_t r = 0; r < R; ++r) {
+        const uint32_t row = mrq_p8_row(r, self, R);
+        if (row >= R - 1u) continue;
+        const uint64_t w = (uint64_t)r * G + g;
+        const uint8_t b = mrq_p8_encode(type[w], term[w], index[w], commit[w], enc_base[g], base_term[g]);
+        word[(uint64_t)row * e.gs + g] = b;
+        if (b == MRQ_P8_ESCAPE) {
+          esc.push_back({g, r});
+          ++n_escapes;
+        } else if (b != 0) {
+          ++n_bytes;
+          if ((b & 3u) == 1u && (uint32_t)(b >> 2) < min_ack) min_ack = b >> 2;
+        }
+      }
+      enc_base[g] = mrq_p8_next_base(enc_base[g], min_ack);
+      prop8[g] = (uint8_t)prop[g];
+    }
+    const TickArgs a = e.args(0, seed, 10, 1, true);
+    for (uint64_t g = 0; g < G; ++g)  // the DEVICE decode, one "thread" per group
+      unpack8_group(a.in, e.meta.data(), dev_base.data(), base_term.data(), e.gs, R, word.data(), prop8.data(), g);
+    for (const Esc &x : esc) {  // scatter_msgs_kernel: wide messages override their slot
+      const uint64_t w = (uint64_t)x.r * G + x.g, d = (uint64_t)x.r * e.gs + x.g;
+      e.itype[d] = type[w];
+      e.iterm[d] = term[w];
+      e.iindex[d] = index[w];
+      e.ilogterm[d] = logterm[w];
+      e.icommit[d] = commit[w];
+    }
+    for (uint64_t g = 0; g < G; ++g)
+      if (dev_base[g] != enc_base[g]) {
+        std::printf("FAIL %s tick %d group %llu: device window %llu, frame builder's %llu\n", where, t, (unsigned long long)g,
+                    (unsigned long long)dev_base[g], (unsigned long long)enc_base[g]);
+        ++failures;
+        orc_destroy(o);
+        return;
+      }
+    orc_tick(o, type.data(), term.data(), index.data(), logterm.data(), commit.data(), prop.data(), 1);
+    dispatch_tick(e, a, 0);
+    c.load(o);
+    if (!compare(e, c, where, (uint64_t)t)) break;
+  }
+  std::printf("  %-34s %4d ticks  bytes %9llu  escapes %9llu\n", where, T, (unsigned long long)n_bytes, (unsigned long long)n_escapes);
+  if (R > 1 && n_bytes < 3 * (n_escapes + 1)) {
+    std::printf("FAIL %s: the byte form carried too little (%llu bytes, %llu escapes)\n", where, (unsigned long long)n_bytes,
+                (unsigned long long)n_escapes);
+    ++failures;
+  }
+  orc_destroy(o);
+}
+
 }  // namespace
 
 int main(int argc, char **) {
@@ -245,6 +335,10 @@ int main(int argc, char **) {
   run_case(400 / k, 5, 2, 200, 0, 3, 0);  // a fixed self id (the G = 1 per node shape, many at once)
   run_case(400 / k, 5, 3, 120, 0, 0, 0);  // steady-state preset of the bench (from a cold start)
   if (!quick) run_case(1000, 3, 2, 1024, 0, 0, 0);  // BASELINE configs[1] shape, all 1,024 ticks
+  // the byte-form inbox through the device decode (unpack8_group), then the ticks
+  for (uint32_t R : {1u, 2u, 3u, 5u, 7u, 8u}) run_case8(300 / k, R, 5, 200, 25);
+  run_case8(400 / k, 5, 2, 300, 40);   // elections: votes and vote responses ride the bytes / the escapes
+  run_case8(400 / k, 5, 3, 400, 1000, 60);  // steady state: one base once the leaders stand, then the window slides by itself
   std::printf(failures ? "tick_host_test: %d failure(s)\n" : "tick_host_test: ok\n", failures);
   return failures ? 1 : 0;
 }

@@ -4,9 +4,10 @@ slide the device's window in step with the frame builder's, and the ticks that c
 the oracle.
 
 STATUS: this form was written after round 1's GPU budget was spent — the codec, the frame builder and the decode
-are verified on the CPU, the device kernel and the ABI branch have not yet run on hardware.  Until they have, the
-tests are non-strict xfail: a pass is reported as XPASS, a failure cannot take the validated suite down with it.
-Round 2 removes the marker.
+are verified on the CPU, including the kernel's own per-group body (`unpack8_group`, compiled for the host and run
+against the oracle in tests/cpp/tick_host_test.cpp); the kernel's launch wrapper and the `word_bits = 8` branch of
+`mrq_post_inbox_packed` have not yet run on hardware.  Until they have, the tests are non-strict xfail: a pass is
+reported as XPASS, a failure cannot take the validated suite down with it.  Round 2 removes the marker.
 """
 import numpy as np
 import pytest
