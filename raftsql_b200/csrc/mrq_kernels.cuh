@@ -812,6 +812,208 @@ __device__ __forceinline__ void fast_group_tick(const TickArgs &a, const uint64_
   }
 }
 
+// ---- the tick on the BYTE FORM of the inbox (include/mrq_packed8.h), without the unpack pass -------------------
+// NOT YET LAUNCHED BY THE LIBRARY: the per-group arithmetic below is verified on the host against the CPU checker
+// (tests/cpp/tick_host_test.cpp); kernels and engine plumbing around it come with the first GPU session.
+// Reads 4 sender bytes + 1 proposal byte + the two base words per group instead of the 73 B of wide inbox
+// columns.  Same split as above: the fast function handles what needs none of the role machinery and leaves every
+// other group untouched; the general one materialises that group's bytes into its wide inbox slot (escaped
+// messages are already there: the host's wide list is scattered at post time) and runs general_group_tick.
+// Whoever decodes a group slides its window (base_index), exactly once per frame.
+struct Inbox8 {
+  const uint8_t *word;        // [R-1][gs] one byte per remote sender
+  const uint8_t *prop8;       // [gs] proposals, or nullptr
+  uint64_t *base_index;       // [gs] window base, slid by the decode
+  const uint64_t *base_term;  // [gs]
+};
+static constexpr uint32_t kTypeEscaped = 0xFFu;  // decode marker: "see the wide inbox slot" (never a message type)
+
+// one sender byte -> (type, term, index | commit); `pay` of acks feeds the window rule
+__device__ __forceinline__ void decode8(uint32_t w, uint64_t bi, uint64_t bt, uint32_t &ty, uint64_t &mt, uint64_t &mx,
+                                        uint32_t &min_ack) {
+  const mrq_p8_cell c = mrq_p8_decode(w, bi);
+  ty = c.type;
+  mt = c.type ? bt : 0ull;
+  mx = (c.is_ack || c.is_hb) ? c.value : 0ull;
+  if (c.is_ack) min_ack = c.pay < min_ack ? c.pay : min_ack;
+  if (w == MRQ_P8_ESCAPE) ty = kTypeEscaped;
+}
+
+template <int R>
+__device__ __forceinline__ void fast_group_tick8(const TickArgs &a, const Inbox8 &b, const uint64_t i, bool &slow, uint32_t &ev) {
+  const bool valid = i < a.G;
+  const uint64_t pol_stream = l2_policy(a.l2_policy ? 1u : 0u);
+  const uint64_t pol_keep = l2_policy(a.l2_policy ? 2u : 0u);
+  {
+    const uint64_t w_meta = ld_state_p(a.s.meta + i, pol_keep);
+    const uint64_t term = ld_state_p(a.s.term + i, pol_keep);
+    uint64_t last_index = ld_state_p(a.s.last_index + i, pol_keep);
+    uint64_t committed = ld_state_p(a.s.committed + i, pol_keep);
+    const uint64_t committed0 = committed;
+    const uint64_t gate = ld_state_p(a.s.term_start + i, pol_keep);
+    const uint64_t bi = ld_state_p(b.base_index + i, pol_keep), bt = ld_state_p(b.base_term + i, pol_keep);
+    uint32_t wb[R];  // the frame's bytes of this group, indexed by compact row (R-1 of them are used)
+#pragma unroll
+    for (int j = 0; j < R - 1; ++j) wb[j] = ld_stream_u8_p(b.word + (uint64_t)j * a.gs + i, pol_stream);
+    const uint32_t nprop = b.prop8 ? ld_stream_u8_p(b.prop8 + i, pol_stream) : 0u;
+    uint64_t match[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) match[r] = ld_state_p(a.s.match + (uint64_t)r * a.gs + i, pol_keep);
+    Meta m = meta_unpack(w_meta);
+    uint32_t ty[R];
+    uint64_t mt[R], mx[R];
+    uint32_t min_ack = MRQ_P8_NO_ACK;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      ty[r] = 0;
+      mt[r] = mx[r] = 0;
+      const uint32_t row = mrq_p8_row((uint32_t)r, m.self, (uint32_t)R);
+      if (row >= (uint32_t)R - 1u) continue;  // the group's own slot: a node does not message itself
+      uint32_t w = 0;
+#pragma unroll
+      for (int j = 0; j < R - 1; ++j)
+        if ((uint32_t)j == row) w = wb[j];
+      decode8(w, bi, bt, ty[r], mt[r], mx[r], min_ack);
+    }
+    uint32_t out = 0;
+    uint32_t dirty = 0;
+    if (m.role == MRQ_ROLE_LEADER) {
+      bool ok = !m.strict && m.ltok;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        ok = ok && (ty[r] == 0u || (ty[r] == MRQ_MSG_APP_RESP && mt[r] == term && mx[r] <= last_index));
+      slow = !ok;
+      if (ok) {
+        bool changed = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (ty[r] != 0u && match[r] < mx[r]) {  // Progress.maybeUpdate
+            match[r] = mx[r];
+            dirty |= D_MATCH0 << r;
+            changed = true;
+          }
+        if (nprop) {  // appendEntry: lastTerm already equals Term (ltok), self Match = lastIndex
+          last_index += nprop;
+          dirty |= D_LI;
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if ((uint32_t)(r + 1) == m.self) {
+              match[r] = last_index;
+              dirty |= D_MATCH0 << r;
+            }
+          out |= MRQ_OUT_BCAST_APPEND;
+          changed = true;
+        }
+        if (changed) {  // maybeCommit, once (see Group::flushCommit for why once is exact)
+          const uint64_t mci = quorum_index<R>(match, committed);
+          if (mci > committed && mci >= gate && mci <= last_index) {
+            committed = mci;
+            dirty |= D_COMMIT;
+            out |= MRQ_OUT_COMMIT_ADVANCED | MRQ_OUT_BCAST_APPEND;
+            ev |= Group<R>::EV_COMMIT;
+          }
+        }
+        ++m.hb;  // tickHeartbeat
+        ++m.elapsed;
+        if (m.elapsed >= a.election_tick) m.elapsed = 0;
+        if (m.hb >= a.heartbeat_tick) {
+          m.hb = 0;
+          out |= MRQ_OUT_BCAST_HEARTBEAT;
+        }
+      }
+    } else if (m.role == MRQ_ROLE_FOLLOWER) {
+      bool ok = nprop == 0;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        ok = ok && (ty[r] == 0u || (ty[r] == MRQ_MSG_HEARTBEAT && (uint32_t)(r + 1) == m.lead && mt[r] == term &&
+                                    mx[r] <= last_index));
+      bool heard = false;
+#pragma unroll
+      for (int r = 0; r < R; ++r) heard = heard || ty[r] != 0u;
+      ok = ok && ((heard ? 1u : m.elapsed + 1u) < m.rto);  // the election timer must not fire this tick
+      slow = !ok;
+      if (ok) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (ty[r] != 0u) {  // stepFollower MsgHeartbeat: electionElapsed = 0, lead = From, commitTo, reply
+            if (committed < mx[r]) {
+              committed = mx[r];
+              dirty |= D_COMMIT;
+              out |= MRQ_OUT_COMMIT_ADVANCED;
+              ev |= Group<R>::EV_COMMIT;
+            }
+            out |= 1u << (MRQ_OUT_ACK_REPLY_SHIFT + r);
+          }
+        m.elapsed = heard ? 1u : m.elapsed + 1u;
+      }
+    } else {
+      slow = true;
+    }
+    const uint64_t w_new = meta_pack(m);
+    slow = slow && valid;
+    const bool mine = valid && !slow;
+    if (!mine) ev = 0;
+    // the window: slid by this function only for the groups it handles (the general path slides its own)
+    const uint64_t nb = mrq_p8_next_base(bi, min_ack);
+    uint32_t wdirty = mine ? (dirty | (w_new != w_meta ? D_TERM : 0u) | (nb != bi ? D_GATE : 0u)) : 0u;  // D_GATE bit reused: "base moved"
+    wdirty = __reduce_or_sync(0xFFFFFFFFu, wdirty);
+    if (mine) {
+      if (wdirty & D_TERM) st_state_p(a.s.meta + i, w_new, pol_keep);
+      if (wdirty & D_LI) st_state_p(a.s.last_index + i, last_index, pol_keep);
+      if (wdirty & D_COMMIT) st_state_p(a.s.committed + i, committed, pol_keep);
+      if (wdirty & D_GATE) st_state_p(b.base_index + i, nb, pol_keep);
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (wdirty & (D_MATCH0 << r)) st_state_p(a.s.match + (uint64_t)r * a.gs + i, match[r], pol_keep);
+      st_state_u32_p(a.s.out + i, out, pol_stream);
+      if (a.world > 1) {
+#pragma unroll 1
+        for (uint32_t p = 0; p < a.world; ++p) {
+          a.peer_lo[p][(uint64_t)a.rank * a.G + i] = (uint32_t)committed;
+          if (a.gather_prime || (committed >> 32) != (committed0 >> 32))
+            a.peer_hi[p][(uint64_t)a.rank * a.G + i] = (uint32_t)(committed >> 32);
+        }
+      }
+    }
+  }
+}
+
+// The general path on the byte form: write this group's decoded messages into its wide inbox slot (an escaped
+// sender keeps what the host's wide list scattered there), slide the window, then the unchanged general tick.
+template <int R>
+__device__ __forceinline__ uint32_t general_group_tick8(const TickArgs &a, const Inbox8 &b, const uint64_t i) {
+  const uint32_t self = meta_unpack(ld_state(a.s.meta + i)).self;
+  const uint64_t bi = ld_state(b.base_index + i), bt = ld_state(b.base_term + i);
+  uint32_t min_ack = MRQ_P8_NO_ACK;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const uint64_t o = (uint64_t)r * a.gs + i;
+    const uint32_t row = mrq_p8_row((uint32_t)r, self, (uint32_t)R);
+    if (row >= (uint32_t)R - 1u) {
+      a.in.type[o] = 0;
+      continue;
+    }
+    const uint32_t w = ld_stream_u8(b.word + (uint64_t)row * a.gs + i);
+    if (w == MRQ_P8_ESCAPE) continue;  // the wide message is already in the slot
+    const mrq_p8_cell c = mrq_p8_decode(w, bi);
+    a.in.type[o] = c.type;
+    if (c.type == 0) continue;
+    a.in.term[o] = bt;
+    if (c.is_ack) {
+      a.in.index[o] = c.value;
+      min_ack = c.pay < min_ack ? c.pay : min_ack;
+    } else if (c.is_hb) {
+      a.in.commit[o] = c.value;
+    } else {
+      a.in.index[o] = 0;
+    }
+  }
+  if (a.in.prop) a.in.prop[i] = b.prop8 ? ld_stream_u8(b.prop8 + i) : 0u;
+  const uint64_t nb = mrq_p8_next_base(bi, min_ack);
+  if (nb != bi) st_state(b.base_index + i, nb);
+  return general_group_tick<R>(a, i);
+}
+
 template <int R>
 __global__ void __launch_bounds__(kTickThreads, (R <= 5 ? 8 : (R == 6 ? 7 : 6))) tick_fast_kernel(const TickArgs a) {
   pdl_launch_dependents();

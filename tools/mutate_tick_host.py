@@ -33,6 +33,15 @@ MUTANTS = [
     ("delta32: a match behind the commit index is not clamped to zero",
      "  d = ((b | hi) == 0u) ? lo : 0u;",
      "  d = lo;"),
+    ("byte-form tick: an escaped sender is taken for 'no message' by the fast path",
+     "  if (w == MRQ_P8_ESCAPE) ty = kTypeEscaped;",
+     ""),
+    ("byte-form tick: the fast path forgets to slide the window",
+     "(nb != bi ? D_GATE : 0u)",
+     "0u"),
+    ("byte-form tick: the general path clobbers an escaped sender's wide message",
+     "    if (w == MRQ_P8_ESCAPE) continue;  // the wide message is already in the slot",
+     ""),
     ("leader timers: heartbeat flag never raised on the fast path",
      "          out |= MRQ_OUT_BCAST_HEARTBEAT;\n        }\n      }\n    } else if (m.role == MRQ_ROLE_FOLLOWER) {",
      "        }\n      }\n    } else if (m.role == MRQ_ROLE_FOLLOWER) {"),
