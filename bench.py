@@ -563,6 +563,9 @@ def run_e2e8_child(args):
     eng = Engine(G, Rr, seed=SEED, group_base=0, device=int(os.environ.get("LOCAL_RANK", "0")), inbox_slots=2)
     st0 = steady_state(G, Rr, 0, SEED)
     eng.import_state(st0)
+    tick_mode = os.environ.get("MRQ_E2E8_TICK_MODE")  # "3": the tick reads the bytes itself, no unpack pass (experiment)
+    if tick_mode:
+        eng.set_tick_mode(int(tick_mode))
     p = preset_trace(3)
     base0 = (st0["last_index"] - np.uint64(40)).astype(np.uint64)
     pk = Pack8(st0["self_id"], base0, st0["term"], Rr)
@@ -621,7 +624,7 @@ def run_e2e8_child(args):
            "equals_wide_form": same, "escapes": escapes, "h2d_GBps_per_gpu": h2d * S / el / 1e9,
            "inputs": f"{S} distinct consecutive ticks of the trace, one per step",
            "api": "mrq_pack8 frames (pinned, 8-bit form, copy stream) + mrq_post_inbox_packed + mrq_tick + "
-                  "mrq_drain_commit_deltas/mrq_drain_wait (1 B/group)"}
+                  "mrq_drain_commit_deltas/mrq_drain_wait (1 B/group)", "tick_mode": int(tick_mode) if tick_mode else 0}
     try:
         eng.close()
     finally:

@@ -264,7 +264,10 @@ int mrq_tick_idle(mrq_engine *e, uint32_t n);
  * (steady-state leaders, quiet / heart-beaten followers) + a general kernel over the compacted list of
  * the remaining groups (two launches); 2 = one launch doing both (each CTA compacts its stragglers in
  * shared memory and runs the general path on them); 1 = one general kernel over every group
- * (differential testing).  All give identical results.                                          */
+ * (differential testing); 3 = mode 0 on the BYTE FORM of the inbox: a slot posted with word_bits = 8 is not
+ * unpacked — the fast kernel reads the frame's bytes where the copy left them and the general kernel
+ * materialises only the groups the fast one declines (a slot posted in any other form ticks as in mode 0;
+ * no graph replay in this mode).  All give identical results.                                    */
 int mrq_set_tick_mode(mrq_engine *e, int mode);
 
 /* The standalone quorum kernel (K3; SURVEY §8a rows a15–a16): for every leader group,

@@ -66,6 +66,9 @@ struct PackedStage {
   size_t bytes = 0;
   cudaEvent_t copied = nullptr, consumed = nullptr;
   bool used = false;
+  // tick mode 3: the byte frame of this slot stays in the staging buffer and the tick reads it there
+  const uint8_t *word8 = nullptr, *prop8 = nullptr;
+  bool frame8 = false;  // a byte frame is waiting for its tick
 };
 
 struct InboxBuf {
@@ -250,7 +253,22 @@ int launch_tick(mrq_engine *e, const InboxBuf *ib) {
   a.slow_count_next = e->slow_count + ((e->slow_parity + 1u) & 1u);
   const unsigned nb = nblocks(e->G, kTickThreads);
   cudaError_t lst = cudaErrorInvalidValue;
-  if (e->tick_mode == 1) {  // single launch, every group through the general path (differential testing)
+  const size_t slot = ib ? (size_t)(ib - e->inbox.data()) : 0;
+  if (e->tick_mode == 3 && ib && slot < e->pk_stage.size() && e->pk_stage[slot].frame8) {
+    // the tick on the byte form: the kernels read the frame where the copy left it (no unpack pass)
+    PackedStage &sg = e->pk_stage[slot];
+    Tick8Args a8{a, Inbox8{sg.word8, sg.prop8, e->pk_base_index, e->pk_base_term}};
+    MRQ_DISPATCH_R(e->R, lst = launch_pdl(tick_fast8_kernel<kR>, nb, kTickThreads, 0, e->stream, a8));
+    CK(e, lst);
+    unsigned nslow = (unsigned)g_sm_count * 6u;
+    if (nslow > nb) nslow = nb;
+    MRQ_DISPATCH_R(e->R, lst = launch_pdl(tick_slow8_kernel<kR>, nslow, kTickThreads, 0, e->stream, a8));
+    CK(e, lst);
+    e->launches += 2;
+    e->slow_parity ^= 1u;
+    sg.frame8 = false;
+    CK(e, cudaEventRecord(sg.consumed, e->stream));  // only now may the next frame overwrite the staging buffer
+  } else if (e->tick_mode == 1) {  // single launch, every group through the general path (differential testing)
     MRQ_DISPATCH_R(e->R, lst = launch_pdl(tick_general_kernel<kR>, nb, kTickThreads, 0, e->stream, a));
     CK(e, lst);
     e->launches++;
@@ -335,6 +353,11 @@ int check_slot(mrq_engine *e, uint32_t slot) {
   if (!e) return MRQ_E_INVAL;
   if (slot >= e->inbox.size()) return fail(e, MRQ_E_INVAL, "inbox slot %u out of range (%zu slots)", slot, e->inbox.size());
   return MRQ_OK;
+}
+
+// a wide-form post (or a clear) supersedes a byte frame that was waiting for its tick in this slot (tick mode 3)
+void drop_frame8(mrq_engine *e, uint32_t slot) {
+  if (slot < e->pk_stage.size()) e->pk_stage[slot].frame8 = false;
 }
 
 }  // namespace
@@ -632,6 +655,7 @@ int mrq_export_next(mrq_engine *e, uint64_t *next_out) {
 int mrq_clear_inbox(mrq_engine *e, uint32_t slot) {
   int r = check_slot(e, slot);
   if (r) return r;
+  drop_frame8(e, slot);
   CK(e, cudaSetDevice(e->device));
   InboxBuf &ib = e->inbox[slot];
   CK(e, cudaMemsetAsync(ib.type, 0, e->gs * e->R, e->stream));
@@ -642,6 +666,7 @@ int mrq_clear_inbox(mrq_engine *e, uint32_t slot) {
 int mrq_post_inbox_dense(mrq_engine *e, uint32_t slot, const mrq_inbox *in) {
   int r = check_slot(e, slot);
   if (r) return r;
+  drop_frame8(e, slot);
   if (!in) return fail(e, MRQ_E_INVAL, "null inbox");
   CK(e, cudaSetDevice(e->device));
   if (e->G == 0) return MRQ_OK;
@@ -658,6 +683,7 @@ int mrq_post_inbox_dense(mrq_engine *e, uint32_t slot, const mrq_inbox *in) {
 int mrq_post_inbox_delta(mrq_engine *e, uint32_t slot, const mrq_msg *msgs, size_t n, int accumulate) {
   int r = check_slot(e, slot);
   if (r) return r;
+  drop_frame8(e, slot);
   CK(e, cudaSetDevice(e->device));
   if (!accumulate && (r = mrq_clear_inbox(e, slot))) return r;
   if (n == 0) return MRQ_OK;
@@ -675,6 +701,7 @@ int mrq_post_inbox_delta(mrq_engine *e, uint32_t slot, const mrq_msg *msgs, size
 int mrq_post_inbox_packed(mrq_engine *e, uint32_t slot, const mrq_inbox_packed *in) {
   int r = check_slot(e, slot);
   if (r) return r;
+  drop_frame8(e, slot);
   if (!in || !in->word) return fail(e, MRQ_E_INVAL, "null packed inbox");
   CK(e, cudaSetDevice(e->device));
   if (e->G == 0) return MRQ_OK;
@@ -717,6 +744,19 @@ int mrq_post_inbox_packed(mrq_engine *e, uint32_t slot, const mrq_inbox_packed *
   if (bits == 32u) {
     unpack_inbox_kernel<<<nblocks(e->G), 256, 0, e->stream>>>(e->inbox[slot].view(), e->pk_base_index, e->pk_base_term, e->gs,
                                                             e->G, e->R, (const uint32_t *)d_word, in->prop_count8 ? d_prop : nullptr);
+  } else if (bits == 8u && e->tick_mode == 3) {
+    // tick mode 3: no unpack pass — the tick kernels read the frame in the staging buffer (launch_tick records
+    // `consumed` after them); only the escapes are scattered into the slot's wide columns, below
+    sg.word8 = d_word;
+    sg.prop8 = in->prop_count8 ? d_prop : nullptr;
+    sg.frame8 = true;
+    if (in->n_wide) {
+      scatter_msgs_kernel<<<nblocks(in->n_wide), 256, 0, e->stream>>>(e->inbox[slot].view(), e->gs, e->G, e->R, d_wide, in->n_wide);
+      CK(e, cudaGetLastError());
+      e->launches++;
+    }
+    sg.used = true;
+    return MRQ_OK;
   } else if (bits == 8u) {
     unpack8_inbox_kernel<<<nblocks(e->G), 256, 0, e->stream>>>(e->inbox[slot].view(), e->s.meta, e->pk_base_index, e->pk_base_term,
                                                              e->gs, e->G, e->R, d_word, in->prop_count8 ? d_prop : nullptr);
@@ -914,6 +954,7 @@ int mrq_read_inbox(mrq_engine *e, uint32_t slot, mrq_inbox_out *o) {
 int mrq_gen_trace(mrq_engine *e, uint32_t slot, const struct mrq_trace_params *p, uint64_t tick) {
   int r = check_slot(e, slot);
   if (r) return r;
+  drop_frame8(e, slot);
   if (!p) return MRQ_E_INVAL;
   CK(e, cudaSetDevice(e->device));
   if (e->G == 0) return MRQ_OK;
@@ -948,7 +989,8 @@ int mrq_tick_many(mrq_engine *e, const uint32_t *slots, uint32_t n) {
   // graph_mode: 0 never, 1 always, 2 (default) only for small shards, where the host's launch rate rather than
   // the kernels bounds the tick rate (measured on B200: at 1M groups per GPU PDL stream launches are faster)
   const bool want_graph = e->graph_mode == 1 || (e->graph_mode == 2 && e->G <= kGraphAutoMaxGroups);
-  const bool can_graph = want_graph && n >= 2 && !e->graphs_disabled && !nccl_gather && !e->gather_prime && e->G > 0;
+  const bool can_graph = want_graph && n >= 2 && !e->graphs_disabled && !nccl_gather && !e->gather_prime && e->G > 0 &&
+                         e->tick_mode != 3;  // mode 3 ticks read per-post staging buffers: not replayable
   if (!can_graph) {
     for (uint32_t k = 0; k < n; ++k) {
       int r = launch_tick(e, &e->inbox[slots[k]]);
@@ -1031,7 +1073,7 @@ int mrq_set_graph_mode(mrq_engine *e, int mode) {
 }
 
 int mrq_set_tick_mode(mrq_engine *e, int mode) {
-  if (!e || mode < 0 || mode > 2) return MRQ_E_INVAL;
+  if (!e || mode < 0 || mode > 3) return MRQ_E_INVAL;
   e->tick_mode = mode;
   return MRQ_OK;
 }

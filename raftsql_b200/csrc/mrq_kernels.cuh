@@ -1052,6 +1052,49 @@ __global__ void __launch_bounds__(kTickThreads, (R <= 5 ? 6 : 5)) tick_slow_kern
   }
 }
 
+// The same two launches on the byte form (tick mode 3; opt-in, first hardware run pending): identical wrappers
+// around fast_group_tick8 / general_group_tick8.
+struct Tick8Args {
+  TickArgs t;
+  Inbox8 b;
+};
+template <int R>
+__global__ void __launch_bounds__(kTickThreads, (R <= 5 ? 8 : (R == 6 ? 7 : 6))) tick_fast8_kernel(const Tick8Args a8) {
+  const TickArgs &a = a8.t;
+  pdl_launch_dependents();
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t ev = 0;
+  bool slow = false;
+  pdl_wait();
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.tick_next = *a.tick_cur + 1;  // the next tick's number
+  fast_group_tick8<R>(a, a8.b, i, slow, ev);
+  const unsigned smask = __ballot_sync(0xFFFFFFFFu, slow);
+  if (smask != 0) {  // hand the groups this kernel did not touch to the slow kernel: one atomic per warp
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(a.slow_count, (unsigned)__popc(smask));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (slow) a.slow_list[base + __popc(smask & ((1u << lane) - 1u))] = (uint32_t)i;
+  }
+  if (__any_sync(0xFFFFFFFFu, ev != 0)) count_events(a.ctr, ev);
+}
+template <int R>
+__global__ void __launch_bounds__(kTickThreads, (R <= 5 ? 6 : 5)) tick_slow8_kernel(const Tick8Args a8) {
+  const TickArgs &a = a8.t;
+  pdl_launch_dependents();
+  pdl_wait();
+  const unsigned n = *a.slow_count;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.slow_count_next = 0;
+  const unsigned stride = gridDim.x * blockDim.x;
+  const unsigned rounds = (n + stride - 1) / stride;
+  unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  for (unsigned it = 0; it < rounds; ++it, k += stride) {
+    uint32_t ev = 0;
+    if (k < n) ev = general_group_tick8<R>(a, a8.b, (uint64_t)a.slow_list[k]);
+    if (__any_sync(0xFFFFFFFFu, ev != 0)) count_events(a.ctr, ev);
+  }
+}
+
 // Single-launch form of the same split: every lane runs the fast tick; the CTA then compacts the few lanes
 // that need the general path into shared memory and runs general_group_tick on them with converged warps.
 // One launch per tick instead of two (the second launch costs ~3 us even on an empty list, which matters

@@ -150,6 +150,12 @@ class FakeEngine:
     def synchronize(self):
         pass
 
+    def set_tick_mode(self, mode):
+        pass  # every tick mode computes the same thing: that is what the GPU tests check
+
+    def counters(self):
+        return {"errors": self.o.errors, "ticks": self.o.tick_count}
+
     def close(self):
         pass
 
@@ -181,7 +187,7 @@ class FakeBenchEngine(FakeEngine):
             self.tick(s)
 
     def counters(self):
-        return {"kernel_launches": self.launches, "ticks": self.o.tick_count}
+        return {"kernel_launches": self.launches, "ticks": self.o.tick_count, "errors": self.o.errors}
 
     def timer_start(self):
         import time

@@ -73,6 +73,14 @@ def test_rehearse_gpu_test_byte_form_decode_and_ticks(monkeypatch, G, R, cfg):
     t.test_byte_form_decodes_like_the_host_and_ticks_like_the_oracle(G, R, cfg)
 
 
+@pytest.mark.parametrize("G,R,cfg", [(1200, 7, 5), (900, 5, 3), (300, 2, 5), (800, 3, 2)])
+def test_rehearse_gpu_test_tick_mode_3(monkeypatch, G, R, cfg):
+    import test_zz_packed8_gpu as t
+
+    monkeypatch.setattr(t, "Engine", FakeEngine)
+    t.test_tick_mode_3_consumes_the_bytes_itself(G, R, cfg)
+
+
 def test_rehearse_gpu_test_sliding_window(monkeypatch):
     import test_zz_packed8_gpu as t
 

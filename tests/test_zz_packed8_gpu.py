@@ -89,6 +89,40 @@ def test_byte_form_decodes_like_the_host_and_ticks_like_the_oracle(G, R, cfg):
     eng.close()
 
 
+@pytest.mark.parametrize("G,R,cfg", [(4000, 7, 5), (3001, 5, 3), (777, 2, 5), (2500, 8, 5), (3000, 3, 2)])
+def test_tick_mode_3_consumes_the_bytes_itself(G, R, cfg):
+    """tick mode 3: no unpack pass — tick_fast8_kernel reads the frame in the staging buffer, tick_slow8_kernel
+    materialises only the groups the fast kernel declines (escaped senders keep what the wide list scattered).  The
+    per-group arithmetic of both is verified on the host (tests/cpp/tick_host_test.cpp, 'byte form direct'); here
+    the launch wrappers, the slow list and the staging-buffer lifetime meet hardware: state must equal the oracle's
+    after every tick, and the device's window must end where the frame builder's does."""
+    eng, orc, p = _warm(G, R, 41 + R, 60, cfg)
+    eng.set_tick_mode(3)
+    cur = orc.export()
+    self_id = cur["self_id"].copy()
+
+    def rebase():
+        c = orc.export()
+        pk = Pack8(self_id, np.where(c["last_index"] > 30, c["last_index"] - np.uint64(30), 0).astype(np.uint64), c["term"], R)
+        eng.set_packed_base(pk.base_index, pk.base_term)
+        return pk
+
+    pk = rebase()
+    for t in range(60, 160):
+        if t % 25 == 0:
+            pk = rebase()
+        ib = orc.gen_trace(_orc_params(p), t)
+        word, prop8, wide = pk.frame(ib)
+        eng.post_inbox_packed(word, prop8, wide, slot=t % 3)
+        eng.tick(t % 3)
+        orc.tick(ib)
+        assert_state_equal(eng.export_state(), orc.export(), f"mode 3 tick {t}")
+        np.testing.assert_array_equal(eng.sync_out(), orc.export()["out"], err_msg=f"out word, tick {t}")
+    c = eng.counters()
+    assert c["errors"] == 0 and orc.errors == 0
+    eng.close()
+
+
 def test_device_window_slides_by_itself_for_hundreds_of_ticks():
     """steady-state leaders (bench shape): one set_packed_base, then 300 frames with no host re-base, no escapes"""
     G, R = 8192, 5

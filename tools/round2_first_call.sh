@@ -44,6 +44,11 @@ except Exception as ex:
     print("could not read the bench line:", ex)
 EOF
 
+echo "== 2b. byte-form e2e with the tick reading the bytes itself (tick mode 3: no unpack pass)" | tee -a "$OUT/summary.txt"
+MRQ_E2E8_TICK_MODE=3 timeout 600 python bench.py --e2e8-child --steps 20 > "$OUT/e2e8_mode3.json" 2> "$OUT/e2e8_mode3.err"
+echo "exit $?" | tee -a "$OUT/summary.txt"
+tail -1 "$OUT/e2e8_mode3.json" | cut -c1-400 | tee -a "$OUT/summary.txt"
+
 echo "== 3. persisting-L2 limit raised (MRQ_L2_PERSIST_MB=80), kernels only" | tee -a "$OUT/summary.txt"
 for mb in 80 48; do
   MRQ_L2_PERSIST_MB=$mb MRQ_BENCH_FAST=1 timeout 600 python bench.py > "$OUT/bench_l2_$mb.json" 2> "$OUT/bench_l2_$mb.err"
