@@ -66,11 +66,17 @@ def steady_state(G: int, Rr: int, group_base: int, seed: int) -> dict:
     return st
 
 
-def tick_bytes_per_group(Rr: int) -> dict:
+def tick_bytes_per_group(Rr: int, inbox: str = "wide") -> dict:
     """Algorithmic HBM bytes of one fused tick per group on the steady-state trace: every
-    follower acks, proposals arrive on 3 of 4 ticks."""
-    read = 8 * 5 + 8 * Rr + Rr + 4 + 16 * (Rr - 1)  # meta,term,last_index,committed,term_start + match + types + prop + ack term/index
-    write = 8 + 4 + 8 * (Rr - 1) + 8 + 12           # meta, out, acked match, committed, (last_index + self match) x 3/4
+    follower acks, proposals arrive on 3 of 4 ticks.  inbox = "bytes": the tick on the byte form (tick mode 3) reads
+    R-1 sender bytes + 1 proposal byte + the two base words instead of the wide inbox columns, and slides the base."""
+    state = 8 * 5 + 8 * Rr  # meta,term,last_index,committed,term_start + match
+    if inbox == "bytes":
+        read = state + (Rr - 1) + 1 + 16
+        write = 8 + 4 + 8 * (Rr - 1) + 8 + 12 + 8  # ... + the slid window base
+    else:
+        read = state + Rr + 4 + 16 * (Rr - 1)      # + types + prop + ack term/index
+        write = 8 + 4 + 8 * (Rr - 1) + 8 + 12      # meta, out, acked match, committed, (last_index + self match) x 3/4
     return {"read": read, "write": write, "total": read + write}
 
 
@@ -256,8 +262,28 @@ def run_ours(args):
     eng.synchronize()
     e2e_slots = min(4, nslots)
     host_ib = [eng.read_inbox(s) for s in range(e2e_slots)]  # every rank runs the e2e leg on its own shard
-    eng.import_state(st0)
-    eng.tick_count = 0
+
+    # --inbox bytes (experiment, tick mode 3): the same trace re-encoded as byte frames (include/mrq_packed8.h), one
+    # per slot, resident in HBM; the tick kernels read the bytes themselves (no wide inbox, no unpack pass)
+    bytes_mode = getattr(args, "inbox", "wide") == "bytes"
+    base0 = (st0["last_index"] - np.uint64(40)).astype(np.uint64)
+    if bytes_mode:
+        from raftsql_b200.packed import Pack8
+
+        pk = Pack8(st0["self_id"], base0, st0["term"], R)
+        frames = [pk.frame(eng.read_inbox(t)) for t in range(nslots)]  # in tick order: the window only moves forward
+        eng.set_tick_mode(3)
+        for t, (w8, p8, wide8) in enumerate(frames):
+            eng.post_inbox_packed(w8, p8, wide8, slot=t, keep=True)
+        n_escapes = sum(len(f[2]) for f in frames)
+
+    def rewind():
+        eng.import_state(st0)
+        eng.tick_count = 0
+        if bytes_mode:
+            eng.set_packed_base(base0, st0["term"])
+
+    rewind()
 
     def barrier():
         if dist is not None:
@@ -278,8 +304,7 @@ def run_ours(args):
     run_ticks(K, W)
     eng.synchronize()
     barrier()
-    eng.import_state(st0)
-    eng.tick_count = 0
+    rewind()
     if world > 1 and args.gather == "fused":
         # the rewind changed committed[] behind the peers' backs: have the next tick republish the high words
         eng.comm_set_mode(1)
@@ -319,7 +344,7 @@ def run_ours(args):
     peak, peak_src = measured_peak_gbs()
 
     # ---- roofline of the dominant kernel (the fused tick) -------------------------------------------
-    tb = tick_bytes_per_group(R)
+    tb = tick_bytes_per_group(R, "bytes" if bytes_mode else "wide")
     tick_kernel_ms = ms / K  # back-to-back launches on one stream: event time / K is the per-launch duration
     tick_gbs = tb["total"] * G / (tick_kernel_ms * 1e-3) / 1e9
     line = {
@@ -332,12 +357,19 @@ def run_ours(args):
                                   "all-gather of committed[] per tick, fused into the tick kernel as peer stores over NVLink"
                                   if args.gather == "fused" else "ncclAllGather(committed) per tick" if args.gather == "nccl"
                                   else "none in the timed region (--gather none: shards tick independently; SURVEY 8d config 4)"),
-                   "l2": f"inputs larger than L2: {nslots} rotating inbox slots, per-step footprint "
-                         f"{(tb['total'] * G) / 1e6:.0f} MB vs 126 MB L2"},
+                   "inbox": (f"byte form resident in HBM, one frame per slot, {n_escapes} escaped messages (tick mode 3)" if bytes_mode
+                             else "wide columns resident in HBM, one inbox slot per tick"),
+                   "l2": (f"{nslots} rotating byte frames ({nslots * G * R / 1e6:.0f} MB in all); the engine state "
+                          f"({(8 * 5 + 8 * R) * G / 1e6:.0f} MB) is re-used every tick by design and is L2-resident" if bytes_mode else
+                          f"inputs larger than L2: {nslots} rotating inbox slots, per-step footprint "
+                          f"{(tb['total'] * G) / 1e6:.0f} MB vs 126 MB L2")},
         "group_ticks_per_sec": ticks_per_s * groups_job,
-        "roofline": {"bound": "hbm", "kernel": "tick_fast_kernel<5> (+ tick_slow_kernel<5> over the slow list, empty on this trace)",
+        "roofline": {"bound": "hbm",
+                     "kernel": ("tick_fast8_kernel<5> (+ tick_slow8_kernel<5>): the tick on the byte form, tick mode 3" if bytes_mode else
+                                "tick_fast_kernel<5> (+ tick_slow_kernel<5> over the slow list, empty on this trace)"),
                      "achieved": tick_gbs, "peak": peak, "unit": "GB/s",
-                     "frac": tick_gbs / peak, "traffic": ncu_traffic("tick_fast_kernel<5>") if world == 1 else None,
+                     "frac": tick_gbs / peak,
+                     "traffic": ncu_traffic("tick_fast_kernel<5>") if world == 1 and not bytes_mode else None,
                      "traffic_source": "profiles/r01_traffic.json (ncu --set full, cold cache, isolated launch)",
                      "peak_source": peak_src, "algorithmic_bytes_per_group": tb,
                      "algorithmic_bytes_per_launch": tb["total"] * G},
@@ -670,6 +702,9 @@ def main():
                     help="L2 residency hints of the tick kernel (default: the engine's, on)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="CUDA-graph replay of the tick sequence (auto: only for small shards)")
+    ap.add_argument("--inbox", default="wide", choices=["wide", "bytes"],
+                    help="form of the HBM-resident inbox of the timed ticks: wide columns (default) or byte frames "
+                         "read by the tick kernels themselves (tick mode 3; experiment until validated on hardware)")
     ap.add_argument("--weak", action="store_true",
                     help="N>1: weak scaling — every GPU keeps 1,048,576 groups, the job is N times that (default: the job "
                          "stays 1,048,576 groups, BASELINE configs[3]); compare group_ticks_per_sec across N")

@@ -209,8 +209,11 @@ typedef struct mrq_inbox_packed {
   const mrq_msg *wide;        /* escape list */
   size_t n_wide;
   uint32_t word_bits;         /* 0 or 32: 32-bit words; 16: 16-bit words; 8: the byte form */
-  uint32_t reserved;
+  uint32_t reserved;          /* flags: MRQ_PACKED_KEEP, else 0 */
 } mrq_inbox_packed;
+/* tick mode 3 only: the byte frame stays in its slot after the tick that read it, so a sequence of slots can be
+ * replayed (after restoring the state and the packed base) without posting again.                          */
+#define MRQ_PACKED_KEEP 1u
 int mrq_post_inbox_packed(mrq_engine *e, uint32_t slot, const mrq_inbox_packed *in);
 /* Dense [G] decode bases for the packed form (NULL keeps the current column).  Blocking. */
 int mrq_set_packed_base(mrq_engine *e, const uint64_t *base_index, const uint64_t *base_term);

@@ -69,6 +69,7 @@ struct PackedStage {
   // tick mode 3: the byte frame of this slot stays in the staging buffer and the tick reads it there
   const uint8_t *word8 = nullptr, *prop8 = nullptr;
   bool frame8 = false;  // a byte frame is waiting for its tick
+  bool keep8 = false;   // MRQ_PACKED_KEEP: the frame stays valid after its tick (replayable sequences)
 };
 
 struct InboxBuf {
@@ -266,7 +267,7 @@ int launch_tick(mrq_engine *e, const InboxBuf *ib) {
     CK(e, lst);
     e->launches += 2;
     e->slow_parity ^= 1u;
-    sg.frame8 = false;
+    if (!sg.keep8) sg.frame8 = false;
     CK(e, cudaEventRecord(sg.consumed, e->stream));  // only now may the next frame overwrite the staging buffer
   } else if (e->tick_mode == 1) {  // single launch, every group through the general path (differential testing)
     MRQ_DISPATCH_R(e->R, lst = launch_pdl(tick_general_kernel<kR>, nb, kTickThreads, 0, e->stream, a));
@@ -750,6 +751,7 @@ int mrq_post_inbox_packed(mrq_engine *e, uint32_t slot, const mrq_inbox_packed *
     sg.word8 = d_word;
     sg.prop8 = in->prop_count8 ? d_prop : nullptr;
     sg.frame8 = true;
+    sg.keep8 = (in->reserved & MRQ_PACKED_KEEP) != 0;
     if (in->n_wide) {
       scatter_msgs_kernel<<<nblocks(in->n_wide), 256, 0, e->stream>>>(e->inbox[slot].view(), e->gs, e->G, e->R, d_wide, in->n_wide);
       CK(e, cudaGetLastError());

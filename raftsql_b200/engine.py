@@ -152,7 +152,7 @@ class Engine:
             arr[i].term, arr[i].index, arr[i].logterm, arr[i].commit = term, index, logterm, commit
         self._ck(self.L.mrq_post_inbox_delta(self.h, slot, arr, len(msgs), int(accumulate)))
 
-    def post_inbox_packed(self, word: np.ndarray, prop8: np.ndarray | None = None, wide=(), slot: int = 0):
+    def post_inbox_packed(self, word: np.ndarray, prop8: np.ndarray | None = None, wide=(), slot: int = 0, keep: bool = False):
         """word: uint32 or uint16 [R][G] (raftsql_b200.packed.pack_inbox / pack_inbox16), or uint8 [R-1][G] (the
         byte form, raftsql_b200.packed.Pack8).  The copy is asynchronous: this convenience wrapper synchronises
         before returning so numpy temporaries are safe; hosts that pipeline call mrq_post_inbox_packed directly
@@ -164,6 +164,7 @@ class Engine:
         keep = word if word.size else np.zeros(1, np.uint8)  # R = 1 in the byte form: no sender rows at all
         v.word, v.prop_count8 = keep.ctypes.data, _p(prop8, F.u8p)
         v.word_bits = 8 * word.dtype.itemsize
+        v.reserved = 1 if keep else 0  # MRQ_PACKED_KEEP (tick mode 3: the frame stays in its slot after its tick)
         arr = (F.Msg * max(1, len(wide)))()
         for i, m in enumerate(wide):
             g, frm, ty, term, index, logterm, commit = m

@@ -80,6 +80,7 @@ class FakeEngine:
         self.base_term = np.zeros(G, np.uint64)
         self.prev = np.zeros(G, np.uint64)
         self.L, self.h = FakeL(self), 1
+        self.tick_mode, self.frames = 0, {}
 
     def _self_id(self):
         return self.o.export()["self_id"]
@@ -91,6 +92,7 @@ class FakeEngine:
         return self.o.export()
 
     def gen_trace(self, p, t, slot=0):
+        self.frames.pop(slot, None)
         q = oracle.TraceParams()
         for n, _ in F.TraceParams._fields_:
             setattr(q, n, getattr(p, n))
@@ -99,14 +101,24 @@ class FakeEngine:
     def read_inbox(self, slot=0):
         return {k: v.copy() for k, v in self.slots[slot].items()}
 
-    def post_inbox_packed(self, word, prop8=None, wide=(), slot=0):
+    def post_inbox_packed(self, word, prop8=None, wide=(), slot=0, keep=False):
         assert word.dtype == np.uint8 and word.shape == (max(self.R - 1, 0), self.G)
+        frame = (np.array(word), None if prop8 is None else np.array(prop8), list(wide), bool(keep))
+        if self.tick_mode == 3:  # the frame waits in its slot; the TICK decodes it, against the base of that moment
+            self.frames[slot] = frame
+        else:  # the unpack pass runs at post time
+            self.frames.pop(slot, None)
+            self._decode(frame, slot)
+
+    def _decode(self, frame, slot):
+        word, prop8, wide, _ = frame
         cols, self.base_index = unpack8(word, self._self_id(), self.base_index, self.base_term, self.R)
         _apply_wide(cols, wide)
         cols["prop_count"] = np.zeros(self.G, np.uint32) if prop8 is None else np.asarray(prop8).astype(np.uint32)
         self.slots[slot] = cols
 
     def post_inbox_delta(self, msgs, slot=0, accumulate=False):
+        self.frames.pop(slot, None)
         if not accumulate:
             self.slots[slot] = oracle.empty_inbox(self.G, self.R)
         _apply_wide(self.slots[slot], msgs)
@@ -119,6 +131,11 @@ class FakeEngine:
         self.slots[slot] = oracle.empty_inbox(self.G, self.R)
 
     def tick(self, slot=0):
+        if self.tick_mode == 3 and slot in self.frames:
+            frame = self.frames[slot]
+            self._decode(frame, slot)
+            if not frame[3]:  # MRQ_PACKED_KEEP not set: one tick per post
+                del self.frames[slot]
         self.o.tick(self.slots[slot])
 
     def tick_idle(self, n=1):
@@ -151,7 +168,7 @@ class FakeEngine:
         pass
 
     def set_tick_mode(self, mode):
-        pass  # every tick mode computes the same thing: that is what the GPU tests check
+        self.tick_mode = mode  # every mode computes the same thing; mode 3 differs in WHEN a byte frame is decoded
 
     def counters(self):
         return {"errors": self.o.errors, "ticks": self.o.tick_count}
@@ -170,9 +187,6 @@ class FakeBenchEngine(FakeEngine):
         self._t0 = 0.0
 
     def set_graph_mode(self, mode):
-        pass
-
-    def set_tick_mode(self, mode):
         pass
 
     def set_l2_policy(self, on):

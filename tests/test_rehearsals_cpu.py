@@ -144,6 +144,51 @@ def test_rehearse_bench_main_path_and_line_assembly(monkeypatch, capsys):
     assert order == ["close", "child"], "the engine must be gone before the byte-form child gets the GPU"
 
 
+def test_rehearse_bench_inbox_bytes_replays_the_same_ticks(monkeypatch, capsys):
+    """`bench.py --inbox bytes` (tick mode 3, byte frames kept in their slots and replayed after each rewind) must
+    drive the engine through exactly the ticks of the default run: same commit indices at the end of the timed region,
+    no escapes on the steady-state trace, and the byte-form byte count in the roofline."""
+    import torch
+
+    import bench
+    import raftsql_b200
+    from engine_double import FakeBenchEngine
+
+    finals = {}
+    for inbox in ("wide", "bytes"):
+        made = []
+
+        class Eng(FakeBenchEngine):
+            def timer_stop(self, _inbox=inbox):  # the end of the timed region (the untimed post-roll ticks on after it)
+                finals[_inbox] = self.o.export()["committed"].copy()
+                return super().timer_stop()
+
+        def make(*a, **kw):
+            made.append(Eng(*a, **kw))
+            return made[-1]
+
+        monkeypatch.setattr(bench, "G_TOTAL", 2048)
+        monkeypatch.setattr(raftsql_b200, "Engine", make)
+        monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+        monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+        monkeypatch.setenv("MRQ_BENCH_FAST", "1")  # kernels only: no e2e / cpu legs, no child
+        monkeypatch.setattr(bench, "bench_quorum_kernel", lambda *a: {"bound": "hbm"})
+        args = argparse.Namespace(gpus=1, steps=6, warmup=3, impl="ours", gather="fused", tick_mode=None, l2=None, graph="auto",
+                                  inbox=inbox)
+        bench.run_ours(args)
+        line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+        if inbox == "bytes":
+            assert "0 escaped" in line["config"]["inbox"] and "tick mode 3" in line["config"]["inbox"]
+            assert line["roofline"]["algorithmic_bytes_per_group"]["total"] == 173
+            assert "tick_fast8_kernel" in line["roofline"]["kernel"] and line["roofline"]["traffic"] is None
+        else:
+            assert line["roofline"]["algorithmic_bytes_per_group"]["total"] == 217
+    import numpy as np
+
+    assert np.array_equal(finals["wide"], finals["bytes"]), "the byte-form run must commit exactly what the wide run commits"
+    assert (finals["wide"] > bench.steady_state(2048, bench.R, 0, bench.SEED)["committed"]).mean() > 0.9
+
+
 def _engine_kat_cases():
     import test_zz_kat_gpu as t
 

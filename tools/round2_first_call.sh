@@ -49,6 +49,19 @@ MRQ_E2E8_TICK_MODE=3 timeout 600 python bench.py --e2e8-child --steps 20 > "$OUT
 echo "exit $?" | tee -a "$OUT/summary.txt"
 tail -1 "$OUT/e2e8_mode3.json" | cut -c1-400 | tee -a "$OUT/summary.txt"
 
+echo "== 2c. the HBM-resident tick on byte frames (bench --inbox bytes, tick mode 3), kernels only" | tee -a "$OUT/summary.txt"
+MRQ_BENCH_FAST=1 timeout 600 python bench.py --inbox bytes > "$OUT/bench_inbox_bytes.json" 2> "$OUT/bench_inbox_bytes.err"
+echo "exit $?" | tee -a "$OUT/summary.txt"
+python - "$OUT/bench_inbox_bytes.json" <<'EOF' | tee -a "$OUT/summary.txt"
+import json, sys
+try:
+    l = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print("bytes inbox: ticks/s", round(l["value"]), "us/step", round(1e3 * l["ms_per_step"], 2), "frac", round(l["roofline"]["frac"], 3),
+          "|", l["config"]["inbox"])
+except Exception as ex:
+    print("could not read the bench line:", ex)
+EOF
+
 echo "== 3. persisting-L2 limit raised (MRQ_L2_PERSIST_MB=80), kernels only" | tee -a "$OUT/summary.txt"
 for mb in 80 48; do
   MRQ_L2_PERSIST_MB=$mb MRQ_BENCH_FAST=1 timeout 600 python bench.py > "$OUT/bench_l2_$mb.json" 2> "$OUT/bench_l2_$mb.err"
