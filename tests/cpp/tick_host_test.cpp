@@ -356,11 +356,52 @@ void run_case8(uint64_t G, uint32_t R, uint32_t cfg, int T, int rebase_every, in
   orc_destroy(o);
 }
 
+// The standalone quorum kernel's arithmetic (quorum_commit_one<R>: a15 + a16 on the 32-bit delta network with its
+// 64-bit fallback) against the oracle's independent definition max{x : |{r : m[r] >= x}| >= q}: ties, zeros,
+// 2^64-1, values exactly 2^32 around the commit index (the fallback boundary), closed and open gates.
+template <int R>
+void quorum_cases(uint64_t seed, int n) {
+  uint64_t x = seed;
+  auto rnd = [&]() { return x = mrq_mix64(x + 0x9E3779B97F4A7C15ull); };
+  for (int it = 0; it < n; ++it) {
+    const uint64_t around = (rnd() % 3 == 0) ? (rnd() >> (rnd() % 64)) : (1ull << 40) + (rnd() & 0xFFFF);
+    auto pick = [&]() -> uint64_t {
+      switch (rnd() % 8) {
+        case 0: return rnd() % 4;
+        case 1: return ~0ull - (rnd() % 3);
+        case 2: return around + (rnd() % 11) - 5;
+        case 3: return around + (1ull << 32) + (rnd() % 5) - 2;
+        case 4: return around - (1ull << 32) + (rnd() % 5) - 2;
+        case 5: return rnd();
+        default: return around + (rnd() & 0xFFFFF);
+      }
+    };
+    uint64_t m[R], mm[R];
+    for (int r = 0; r < R; ++r) mm[r] = m[r] = pick();
+    const uint64_t committed = pick();
+    const uint64_t gate = (rnd() % 4 == 0) ? ~0ull : (rnd() % 2 ? committed : pick());
+    const uint64_t mci = orc_quorum_index_bruteforce(mm, R);
+    const bool want_moved = mci > committed && mci >= gate;
+    bool moved = false;
+    const uint64_t got = quorum_commit_one<R>(m, committed, gate, moved);
+    if (moved != want_moved || got != (want_moved ? mci : committed)) {
+      std::printf("FAIL quorum_commit_one<%d>: committed %llu gate %llu mci %llu -> got %llu moved %d\n", R,
+                  (unsigned long long)committed, (unsigned long long)gate, (unsigned long long)mci, (unsigned long long)got, (int)moved);
+      ++failures;
+      return;
+    }
+  }
+}
+
 }  // namespace
 
 int main(int argc, char **) {
   const bool quick = argc > 1;  // any argument: the sanitizer builds run a smaller matrix (they are ~20x slower)
   const uint64_t k = quick ? 4 : 1;
+  const int nq = quick ? 20000 : 200000;
+  quorum_cases<1>(11, nq), quorum_cases<2>(12, nq), quorum_cases<3>(13, nq), quorum_cases<4>(14, nq);
+  quorum_cases<5>(15, nq), quorum_cases<6>(16, nq), quorum_cases<7>(17, nq), quorum_cases<8>(18, nq);
+  std::printf("  quorum_commit_one<1..8>             %d adversarial cases each vs the brute-force definition\n", nq);
   // election + replication (cfg 2), lag + churn (5), follower/heartbeat heavy (6), steady state (3); every R;
   // mode 0 = fast path with the general path for the rest (the product's default), mode 1 = general path only
   for (uint32_t R = 1; R <= 8; ++R) {
