@@ -14,12 +14,12 @@ OUT=gpurun_out/r02_first
 mkdir -p "$OUT"
 
 echo "== 1. byte-form GPU tests (xfail shield off)" | tee "$OUT/summary.txt"
-timeout 900 python -m pytest tests/test_zz_packed8_gpu.py -m gpu --runxfail -x -q > "$OUT/packed8_tests.log" 2>&1
+MRQ_PACKED8_INPROC=1 timeout 900 python -m pytest tests/test_zz_packed8_gpu.py -m gpu --runxfail -q > "$OUT/packed8_tests.log" 2>&1
 echo "exit $?" | tee -a "$OUT/summary.txt"
 tail -5 "$OUT/packed8_tests.log" | tee -a "$OUT/summary.txt"
 
 echo "== 1b. memcheck on one byte-form case" | tee -a "$OUT/summary.txt"
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 \
+MRQ_PACKED8_INPROC=1 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 \
   python -m pytest "tests/test_zz_packed8_gpu.py::test_byte_form_decodes_like_the_host_and_ticks_like_the_oracle[777-2-5]" \
   -m gpu --runxfail -x -q > "$OUT/packed8_memcheck.log" 2>&1
 echo "exit $?" | tee -a "$OUT/summary.txt"
