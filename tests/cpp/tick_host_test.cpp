@@ -356,6 +356,96 @@ void run_case8(uint64_t G, uint32_t R, uint32_t cfg, int T, int rebase_every, in
   orc_destroy(o);
 }
 
+// The fused all-gather of the tick (multi-GPU mode 1): every group's commit index is stored into every rank's gather
+// buffer as a low word every tick and a high word only when it changes (or when priming).  Steady-state leaders
+// whose commit indices sit just below a multiple of 2^32, so that they CROSS it during the run: after every tick the
+// stitched (hi << 32 | lo) view in both "ranks'" buffers must equal committed[] — a stale high word would show here.
+void run_gather_case(uint64_t G, uint32_t R, int T) {
+  const char *where = "fused gather across a 2^32 boundary";
+  const uint64_t seed = 0x5EED6A7Eull;
+  orc_engine *o = orc_create(G, R, 0, 10, 1, seed, 0);
+  OracleCols c(G, R);
+  c.load(o);
+  uint64_t x = 99;
+  auto rnd = [&]() { return x = mrq_mix64(x + 0x9E3779B97F4A7C15ull); };
+  for (uint64_t g = 0; g < G; ++g) {  // steady-state leaders (bench.py steady_state), placed under the boundary
+    const uint32_t self = (uint32_t)(g % R) + 1;
+    c.self_id[g] = (uint8_t)self;
+    c.role[g] = MRQ_ROLE_LEADER;
+    c.lead[g] = (uint8_t)self;
+    c.term[g] = 1 + rnd() % 8;
+    c.vote[g] = self;
+    c.last_index[g] = ((3 + g % 3) << 32) - 1 - rnd() % 40;
+    c.last_term[g] = c.term[g];
+    for (uint32_t r = 0; r < R; ++r) c.match[(uint64_t)r * G + g] = c.last_index[g] - 1 - rnd() % 6;
+    c.match[(uint64_t)(self - 1) * G + g] = c.last_index[g];
+    c.committed[g] = c.last_index[g] - 8;
+    c.term_start[g] = c.committed[g] - 5;
+    c.rto[g] = 10;
+  }
+  orc_import(o, c.term.data(), c.vote.data(), c.committed.data(), c.last_index.data(), c.last_term.data(), c.term_start.data(),
+             c.match.data(), c.role.data(), c.lead.data(), c.self_id.data(), nullptr, nullptr, nullptr, c.rto.data());
+  c.load(o);
+  HostEngine e(G, R);
+  import_from_oracle(e, c);
+  const mrq_trace_params p = preset(3);
+  std::vector<uint8_t> type(G * R);
+  std::vector<uint64_t> term(G * R), index(G * R), logterm(G * R), commit(G * R);
+  std::vector<uint32_t> prop(G);
+  const uint32_t world = 2, rank = 1;  // this shard is rank 1 of 2: its words land at [rank * G + g]
+  std::vector<uint32_t> lo0(world * G, 0xDEADBEEFu), hi0(world * G, 0xDEADBEEFu), lo1(world * G, 0xDEADBEEFu), hi1(world * G, 0xDEADBEEFu);
+  uint64_t crossed = 0;
+  for (int t = 0; t < T; ++t) {
+    orc_gen_trace(o, &p, (uint64_t)t, type.data(), term.data(), index.data(), logterm.data(), commit.data(), prop.data(), 1);
+    for (uint32_t r = 0; r < R; ++r) {
+      std::memcpy(&e.itype[(uint64_t)r * e.gs], &type[(uint64_t)r * G], G);
+      std::memcpy(&e.iterm[(uint64_t)r * e.gs], &term[(uint64_t)r * G], G * 8);
+      std::memcpy(&e.iindex[(uint64_t)r * e.gs], &index[(uint64_t)r * G], G * 8);
+      std::memcpy(&e.ilogterm[(uint64_t)r * e.gs], &logterm[(uint64_t)r * G], G * 8);
+      std::memcpy(&e.icommit[(uint64_t)r * e.gs], &commit[(uint64_t)r * G], G * 8);
+    }
+    std::memcpy(e.iprop.data(), prop.data(), G * 4);
+    orc_tick(o, type.data(), term.data(), index.data(), logterm.data(), commit.data(), prop.data(), 1);
+    TickArgs a = e.args(0, seed, 10, 1, true);
+    a.world = world;
+    a.rank = rank;
+    a.gather_prime = t == 0 ? 1u : 0u;  // the first tick publishes every high word, later ticks only the changed ones
+    a.peer_lo[0] = lo0.data();
+    a.peer_hi[0] = hi0.data();
+    a.peer_lo[1] = lo1.data();
+    a.peer_hi[1] = hi1.data();
+    const std::vector<uint64_t> before(e.committed.begin(), e.committed.begin() + G);
+    dispatch_tick(e, a, t % 2);  // alternate: fast + general, general only
+    c.load(o);
+    if (!compare(e, c, where, (uint64_t)t)) break;
+    for (uint64_t g = 0; g < G; ++g) {
+      crossed += (before[g] >> 32) != (e.committed[g] >> 32);
+      for (const auto &bufs : {std::make_pair(&lo0, &hi0), std::make_pair(&lo1, &hi1)}) {
+        const uint64_t got = ((uint64_t)(*bufs.second)[rank * G + g] << 32) | (*bufs.first)[rank * G + g];
+        if (got != e.committed[g]) {
+          std::printf("FAIL %s tick %d group %llu: gathered %llx, committed %llx\n", where, t, (unsigned long long)g,
+                      (unsigned long long)got, (unsigned long long)e.committed[g]);
+          ++failures;
+          orc_destroy(o);
+          return;
+        }
+      }
+    }
+  }
+  for (uint64_t k = 0; k < G; ++k)  // and nothing was written into the other rank's half
+    if (lo0[k] != 0xDEADBEEFu || hi1[k] != 0xDEADBEEFu) {
+      std::printf("FAIL %s: a word outside this rank's range was written\n", where);
+      ++failures;
+      break;
+    }
+  std::printf("  %-34s %4d ticks  groups that crossed a 2^32 boundary: %llu\n", where, T, (unsigned long long)crossed);
+  if (crossed < G / 2) {
+    std::printf("FAIL %s: only %llu crossings — the case does not exercise the high-word path\n", where, (unsigned long long)crossed);
+    ++failures;
+  }
+  orc_destroy(o);
+}
+
 // The standalone quorum kernel's arithmetic (quorum_commit_one<R>: a15 + a16 on the 32-bit delta network with its
 // 64-bit fallback) against the oracle's independent definition max{x : |{r : m[r] >= x}| >= q}: ties, zeros,
 // 2^64-1, values exactly 2^32 around the commit index (the fallback boundary), closed and open gates.
@@ -415,6 +505,7 @@ int main(int argc, char **) {
   run_case(400 / k, 5, 2, 200, 0, 3, 0);  // a fixed self id (the G = 1 per node shape, many at once)
   run_case(400 / k, 5, 3, 120, 0, 0, 0);  // steady-state preset of the bench (from a cold start)
   if (!quick) run_case(1000, 3, 2, 1024, 0, 0, 0);  // BASELINE configs[1] shape, all 1,024 ticks
+  run_gather_case(600 / k, 5, 80);
   // the byte-form inbox through the device decode (unpack8_group), then the ticks
   for (uint32_t R : {1u, 2u, 3u, 5u, 7u, 8u}) run_case8(300 / k, R, 5, 200, 25);
   run_case8(400 / k, 5, 2, 300, 40);   // elections: votes and vote responses ride the bytes / the escapes
