@@ -143,7 +143,10 @@ int mrq_set_tick_count(mrq_engine *e, uint64_t t);
  *   MSG_APP         term; HOST-RESOLVED: the host keeps the log, ran maybeAppend, and reports the
  *                   outcome: index/logterm = the log's (lastIndex,lastTerm) after the append,
  *                   commit = min(m.Commit, lastnewi).  With REJECT the log did not match: only
- *                   the term rule, electionElapsed=0 and lead=From apply.
+ *                   the term rule, electionElapsed=0 and lead=From apply.  What is reported must be a
+ *                   log: logterm = 0 exactly when index = 0, and logterm <= term (no entry is newer
+ *                   than the leader that sent it) — the engine keeps no per-entry terms and relies on
+ *                   a new leader's own entries being the only ones of its term.
  * Slots are Step()ped in sender order r = 0..R-1, then proposals, then the tick — the
  * canonical per-tick serialisation.                                           */
 typedef struct mrq_inbox {

@@ -161,11 +161,19 @@ bool compare(const HostEngine &e, const OracleCols &c, const char *where, uint64
     if (ok && c.role[g] == MRQ_ROLE_LEADER) ok = e.term_start[g] == c.term_start[g];
     if (!ok) {
       std::printf("FAIL %s tick %llu group %llu: term %llu/%llu commit %llu/%llu li %llu/%llu role %u/%u lead %u/%u el %u/%u rto %u/%u "
-                  "out %08x/%08x\n",
+                  "out %08x/%08x vote %u/%llu lt %llu/%llu hb %u/%u ltok %u\n",
                   where, (unsigned long long)tick, (unsigned long long)g, (unsigned long long)e.term[g], (unsigned long long)c.term[g],
                   (unsigned long long)e.committed[g], (unsigned long long)c.committed[g], (unsigned long long)e.last_index[g],
                   (unsigned long long)c.last_index[g], m.role, c.role[g], m.lead, c.lead[g], m.elapsed, c.el[g], m.rto, c.rto[g],
-                  e.out[g], c.out[g]);
+                  e.out[g], c.out[g], m.vote, (unsigned long long)c.vote[g], (unsigned long long)lt, (unsigned long long)c.last_term[g], m.hb,
+                  c.hb[g], m.ltok);
+      std::printf("     term_start %llu/%llu strict %u self %u; match", (unsigned long long)e.term_start[g],
+                  (unsigned long long)c.term_start[g], m.strict, m.self);
+      for (uint32_t r = 0; r < e.R; ++r)
+        std::printf(" %llu/%llu", (unsigned long long)e.match[(uint64_t)r * e.gs + g], (unsigned long long)c.match[(uint64_t)r * e.G + g]);
+      std::printf("; votes");
+      for (uint32_t r = 0; r < e.R; ++r) std::printf(" %u/%u", (m.votes >> (2 * r)) & 3u, c.votes[(uint64_t)r * e.G + g]);
+      std::printf("\n");
       ++failures;
       return false;
     }
@@ -356,6 +364,75 @@ void run_case8(uint64_t G, uint32_t R, uint32_t cfg, int T, int rebase_every, in
   orc_destroy(o);
 }
 
+// Nothing protocol-shaped about it (tests/test_oracle_vs_pymodel.py's message soup, here against the DEVICE source): any
+// type from any sender with terms around the receiver's, rejects, indices below / at / beyond the log, commits a
+// little beyond it (upstream would panic: both sides count an error and skip), bursts of proposals.
+void run_soup(uint64_t G, uint32_t R, int T, uint64_t seed, int mode) {
+  char where[96];
+  std::snprintf(where, sizeof where, "message soup G=%llu R=%u mode=%d", (unsigned long long)G, R, mode);
+  orc_engine *o = orc_create(G, R, 0, 5, 1, seed, 0);
+  HostEngine e(G, R);
+  OracleCols c(G, R);
+  c.load(o);
+  import_from_oracle(e, c);
+  std::vector<uint8_t> type(G * R);
+  std::vector<uint64_t> term(G * R), index(G * R), logterm(G * R), commit(G * R);
+  std::vector<uint32_t> prop(G);
+  static const uint8_t kTypes[] = {0, 0, 0, 3, 4, 4, 4, 5, 6, 6, 6, 6, 6, 8, 9, 4 | 0x80, 6 | 0x80, 3 | 0x80};
+  uint64_t x = seed * 77 + 5;
+  auto rnd = [&]() { return x = mrq_mix64(x + 0x9E3779B97F4A7C15ull); };
+  auto around = [](uint64_t v, int64_t d) -> uint64_t { return (d < 0 && v < (uint64_t)(-d)) ? 0 : v + (uint64_t)d; };
+  uint32_t seen_roles = 0;
+  for (int t = 0; t < T; ++t) {
+    for (uint64_t g = 0; g < G; ++g) {
+      for (uint32_t r = 0; r < R; ++r) {
+        const uint64_t w = (uint64_t)r * G + g;
+        const uint8_t ty = kTypes[rnd() % sizeof kTypes];
+        type[w] = ty;
+        if ((ty & 0x0F) == 0) {
+          term[w] = index[w] = logterm[w] = commit[w] = 0;
+          continue;
+        }
+        const uint64_t u = rnd() % 64;  // mostly the receiver's own term; now and then stale or ahead
+        term[w] = around(c.term[g], u == 0 ? -2 : u == 1 ? -1 : u == 2 ? 1 : u == 3 ? 2 : 0);
+        index[w] = around(c.last_index[g], (int64_t)(rnd() % 7) - 3);
+        logterm[w] = around(c.last_term[g], (int64_t)(rnd() % 3) - 1);
+        commit[w] = c.committed[g] + rnd() % 4;
+        if ((ty & 0x0F) == 3) {  // a host-resolved MsgApp reports the log AFTER the append (include/mrq.h):
+          if (commit[w] > index[w]) commit[w] = index[w];  // commit <= its new last index,
+          if (index[w] == 0) logterm[w] = 0;               // an empty log has no last term,
+          if (logterm[w] > term[w]) logterm[w] = term[w];  // and no entry is newer than the leader that sent it: with
+          // that raft invariant a new leader's own entries are the only ones of its term, which is what lets the
+          // engine keep `term_start` instead of per-entry terms (tests/test_golden.py, TestCommit)
+        }
+      }
+      static const uint32_t kProps[] = {0, 0, 1, 4};
+      prop[g] = kProps[rnd() % 4];
+    }
+    for (uint32_t r = 0; r < R; ++r) {
+      std::memcpy(&e.itype[(uint64_t)r * e.gs], &type[(uint64_t)r * G], G);
+      std::memcpy(&e.iterm[(uint64_t)r * e.gs], &term[(uint64_t)r * G], G * 8);
+      std::memcpy(&e.iindex[(uint64_t)r * e.gs], &index[(uint64_t)r * G], G * 8);
+      std::memcpy(&e.ilogterm[(uint64_t)r * e.gs], &logterm[(uint64_t)r * G], G * 8);
+      std::memcpy(&e.icommit[(uint64_t)r * e.gs], &commit[(uint64_t)r * G], G * 8);
+    }
+    std::memcpy(e.iprop.data(), prop.data(), G * 4);
+    orc_tick(o, type.data(), term.data(), index.data(), logterm.data(), commit.data(), prop.data(), 1);
+    const TickArgs a = e.args(0, seed, 5, 1, true);
+    dispatch_tick(e, a, mode);
+    c.load(o);
+    if (!compare(e, c, where, (uint64_t)t)) break;
+    for (uint64_t g = 0; g < G; ++g) seen_roles |= 1u << c.role[g];
+  }
+  std::printf("  %-34s %4d ticks  fast %9llu  general %9llu  oracle errors %llu\n", where, T, (unsigned long long)e.fast_groups,
+              (unsigned long long)e.slow_groups, (unsigned long long)orc_errors(o));
+  if ((seen_roles & 3u) != 3u || (R <= 5 && seen_roles != 7u)) {  // (with 6+ noisy peers nobody holds a term long enough to win)
+    std::printf("FAIL %s: the soup did not drive the groups through the roles (mask %u)\n", where, seen_roles);
+    ++failures;
+  }
+  orc_destroy(o);
+}
+
 // The fused all-gather of the tick (multi-GPU mode 1): every group's commit index is stored into every rank's gather
 // buffer as a low word every tick and a high word only when it changes (or when priming).  Steady-state leaders
 // whose commit indices sit just below a multiple of 2^32, so that they CROSS it during the run: after every tick the
@@ -506,6 +583,7 @@ int main(int argc, char **) {
   run_case(400 / k, 5, 3, 120, 0, 0, 0);  // steady-state preset of the bench (from a cold start)
   if (!quick) run_case(1000, 3, 2, 1024, 0, 0, 0);  // BASELINE configs[1] shape, all 1,024 ticks
   run_gather_case(600 / k, 5, 80);
+  for (uint32_t R : {2u, 3u, 4u, 5u, 7u, 8u}) run_soup(120 / k + 8, R, 220, 100 + R, (int)(R % 2));
   // the byte-form inbox through the device decode (unpack8_group), then the ticks
   for (uint32_t R : {1u, 2u, 3u, 5u, 7u, 8u}) run_case8(300 / k, R, 5, 200, 25);
   run_case8(400 / k, 5, 2, 300, 40);   // elections: votes and vote responses ride the bytes / the escapes
