@@ -367,9 +367,13 @@ void run_case8(uint64_t G, uint32_t R, uint32_t cfg, int T, int rebase_every, in
 // Nothing protocol-shaped about it (tests/test_oracle_vs_pymodel.py's message soup, here against the DEVICE source): any
 // type from any sender with terms around the receiver's, rejects, indices below / at / beyond the log, commits a
 // little beyond it (upstream would panic: both sides count an error and skip), bursts of proposals.
+// mode 0 / 1: wide inbox through fast + general / general only.  mode 8: the same soup as BYTE frames consumed by
+// fast_group_tick8 / general_group_tick8 (re-based every tick; whatever does not fit a byte rides the wide list).
 void run_soup(uint64_t G, uint32_t R, int T, uint64_t seed, int mode) {
   char where[96];
   std::snprintf(where, sizeof where, "message soup G=%llu R=%u mode=%d", (unsigned long long)G, R, mode);
+  std::vector<uint8_t> word(((G + 127) / 128) * 128 * (R > 1 ? R - 1 : 1)), prop8(((G + 127) / 128) * 128);
+  std::vector<uint64_t> base_index(((G + 127) / 128) * 128, 0), base_term(((G + 127) / 128) * 128, 0);
   orc_engine *o = orc_create(G, R, 0, 5, 1, seed, 0);
   HostEngine e(G, R);
   OracleCols c(G, R);
@@ -417,9 +421,30 @@ void run_soup(uint64_t G, uint32_t R, int T, uint64_t seed, int mode) {
       std::memcpy(&e.icommit[(uint64_t)r * e.gs], &commit[(uint64_t)r * G], G * 8);
     }
     std::memcpy(e.iprop.data(), prop.data(), G * 4);
-    orc_tick(o, type.data(), term.data(), index.data(), logterm.data(), commit.data(), prop.data(), 1);
     const TickArgs a = e.args(0, seed, 5, 1, true);
-    dispatch_tick(e, a, mode);
+    if (mode == 8) {  // re-encode as a byte frame: the wide inbox keeps only what escapes (as scatter_msgs_kernel leaves it)
+      for (uint64_t g = 0; g < G; ++g) {
+        base_index[g] = c.last_index[g] > 2 ? c.last_index[g] - 2 : 0;
+        base_term[g] = c.term[g];
+        for (uint32_t r = 0; r < R; ++r) {
+          const uint32_t row = mrq_p8_row(r, c.self_id[g], R);
+          const uint64_t w = (uint64_t)r * G + g, d = (uint64_t)r * e.gs + g;
+          if (row >= R - 1u) continue;
+          const uint8_t b = mrq_p8_encode(type[w], term[w], index[w], commit[w], base_index[g], base_term[g]);
+          word[(uint64_t)row * e.gs + g] = b;
+          if (b != MRQ_P8_ESCAPE) e.itype[d] = 0xEE, e.iterm[d] = e.iindex[d] = e.icommit[d] = ~0ull;  // poison: must come from the byte
+        }
+        prop8[g] = (uint8_t)prop[g];
+        e.iprop[g] = 0xEEEEEEEEu;
+      }
+    }
+    orc_tick(o, type.data(), term.data(), index.data(), logterm.data(), commit.data(), prop.data(), 1);
+    if (mode == 8) {
+      const Inbox8 b8{word.data(), prop8.data(), base_index.data(), base_term.data()};
+      dispatch_tick8(e, a, b8);
+    } else {
+      dispatch_tick(e, a, mode);
+    }
     c.load(o);
     if (!compare(e, c, where, (uint64_t)t)) break;
     for (uint64_t g = 0; g < G; ++g) seen_roles |= 1u << c.role[g];
@@ -584,6 +609,7 @@ int main(int argc, char **) {
   if (!quick) run_case(1000, 3, 2, 1024, 0, 0, 0);  // BASELINE configs[1] shape, all 1,024 ticks
   run_gather_case(600 / k, 5, 80);
   for (uint32_t R : {2u, 3u, 4u, 5u, 7u, 8u}) run_soup(120 / k + 8, R, 220, 100 + R, (int)(R % 2));
+  for (uint32_t R : {2u, 3u, 5u, 8u}) run_soup(120 / k + 8, R, 220, 200 + R, 8);
   // the byte-form inbox through the device decode (unpack8_group), then the ticks
   for (uint32_t R : {1u, 2u, 3u, 5u, 7u, 8u}) run_case8(300 / k, R, 5, 200, 25);
   run_case8(400 / k, 5, 2, 300, 40);   // elections: votes and vote responses ride the bytes / the escapes
