@@ -82,3 +82,10 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 echo "exit $?" | tee -a "$OUT/summary.txt"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_event_reasons.active --format=csv >> "$OUT/summary.txt" 2>&1
 cat "$OUT/summary.txt"
+
+echo "== 5. quorum-kernel shape explorer (tools/k3_explore.cu)" | tee -a "$OUT/summary.txt"
+PEAK=$(python -c "import json;print(json.load(open('MEASURED_PEAKS.json'))['hbm_gbs'])" 2>/dev/null || echo 6583.5)
+nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -o /tmp/k3_explore tools/k3_explore.cu > "$OUT/k3_explore_build.log" 2>&1 \
+  && timeout 300 /tmp/k3_explore "$PEAK" > "$OUT/k3_explore.txt" 2>&1
+echo "exit $?" | tee -a "$OUT/summary.txt"
+cat "$OUT/k3_explore.txt" 2>/dev/null | tee -a "$OUT/summary.txt"
