@@ -195,11 +195,13 @@ mrq_trace_params preset(uint32_t cfg) {
   return p;
 }
 
-void run_case(uint64_t G, uint32_t R, uint32_t cfg, int T, int mode, uint32_t self_id, uint64_t group_base) {
+void run_case(uint64_t G, uint32_t R, uint32_t cfg, int T, int mode, uint32_t self_id, uint64_t group_base, uint32_t et = 10,
+              uint32_t ht = 1) {
   char where[96];
-  std::snprintf(where, sizeof where, "G=%llu R=%u cfg=%u mode=%d", (unsigned long long)G, R, cfg, mode);
+  std::snprintf(where, sizeof where, "G=%llu R=%u cfg=%u mode=%d%s", (unsigned long long)G, R, cfg, mode,
+                (et != 10 || ht != 1) ? " timers" : "");
   const uint64_t seed = 0x5EED0000ull + cfg * 131 + R;
-  orc_engine *o = orc_create(G, R, group_base, 10, 1, seed, self_id);
+  orc_engine *o = orc_create(G, R, group_base, et, ht, seed, self_id);
   HostEngine e(G, R);
   OracleCols c(G, R);
   c.load(o);
@@ -224,7 +226,7 @@ void run_case(uint64_t G, uint32_t R, uint32_t cfg, int T, int mode, uint32_t se
     } else {
       orc_tick(o, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1);
     }
-    const TickArgs a = e.args(group_base, seed, 10, 1, !idle);
+    const TickArgs a = e.args(group_base, seed, et, ht, !idle);
     dispatch_tick(e, a, mode);
     c.load(o);
     if (!compare(e, c, where, (uint64_t)t)) break;
@@ -606,6 +608,9 @@ int main(int argc, char **) {
   run_case(513 / k, 5, 5, 300, 1, 0, 0);
   run_case(400 / k, 5, 2, 200, 0, 3, 0);  // a fixed self id (the G = 1 per node shape, many at once)
   run_case(400 / k, 5, 3, 120, 0, 0, 0);  // steady-state preset of the bench (from a cold start)
+  run_case(300 / k, 5, 5, 400, 0, 0, 0, 7, 3);     // other timer settings: ElectionTick 7, HeartbeatTick 3
+  run_case(300 / k, 3, 6, 400, 0, 0, 0, 23, 5);    // ... 23 / 5 (heartbeats every 5th tick: followers count between them)
+  run_case(200 / k, 4, 2, 300, 1, 0, 0, 3, 1);     // ... a 3-tick election timeout (campaigns all the time)
   if (!quick) run_case(1000, 3, 2, 1024, 0, 0, 0);  // BASELINE configs[1] shape, all 1,024 ticks
   run_gather_case(600 / k, 5, 80);
   for (uint32_t R : {2u, 3u, 4u, 5u, 7u, 8u}) run_soup(120 / k + 8, R, 220, 100 + R, (int)(R % 2));
