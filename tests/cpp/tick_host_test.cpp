@@ -611,6 +611,7 @@ int main(int argc, char **) {
   run_case(300 / k, 5, 5, 400, 0, 0, 0, 7, 3);     // other timer settings: ElectionTick 7, HeartbeatTick 3
   run_case(300 / k, 3, 6, 400, 0, 0, 0, 23, 5);    // ... 23 / 5 (heartbeats every 5th tick: followers count between them)
   run_case(200 / k, 4, 2, 300, 1, 0, 0, 3, 1);     // ... a 3-tick election timeout (campaigns all the time)
+  run_case(48, 3, 2, 9000 / (int)k, 0, 0, 0, 2047, 255);  // ... the largest the packed meta word holds (12-bit timers, 8-bit heartbeat)
   if (!quick) run_case(1000, 3, 2, 1024, 0, 0, 0);  // BASELINE configs[1] shape, all 1,024 ticks
   run_gather_case(600 / k, 5, 80);
   for (uint32_t R : {2u, 3u, 4u, 5u, 7u, 8u}) run_soup(120 / k + 8, R, 220, 100 + R, (int)(R % 2));
