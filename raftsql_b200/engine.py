@@ -161,10 +161,10 @@ class Engine:
         rows = self.R - 1 if word.dtype == np.uint8 else self.R
         assert word.shape == (rows, self.G), f"word must be [{rows}][{self.G}]"
         v = F.InboxPacked()
-        keep = word if word.size else np.zeros(1, np.uint8)  # R = 1 in the byte form: no sender rows at all
-        v.word, v.prop_count8 = keep.ctypes.data, _p(prop8, F.u8p)
+        buf = word if word.size else np.zeros(1, np.uint8)  # R = 1 in the byte form: no sender rows at all
+        v.word, v.prop_count8 = buf.ctypes.data, _p(prop8, F.u8p)
         v.word_bits = 8 * word.dtype.itemsize
-        v.reserved = 1 if keep else 0  # MRQ_PACKED_KEEP (tick mode 3: the frame stays in its slot after its tick)
+        v.reserved = 1 if bool(keep) else 0  # MRQ_PACKED_KEEP (tick mode 3: the frame stays in its slot after its tick)
         arr = (F.Msg * max(1, len(wide)))()
         for i, m in enumerate(wide):
             g, frm, ty, term, index, logterm, commit = m

@@ -62,7 +62,5 @@ def test_cpp_raftpipe_scenarios_gpu_engine(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="C++ multi-group seam over the GPU engine (EngineMultiCore): first hardware run pending; "
-                                        "the same scenario passes over the oracle core in the CPU suite")
 def test_cpp_multi_group_seam_gpu_engine(tmp_path):
     _run("engine", tmp_path, env={"MRQ_TEST_MULTI_GROUP": "1"})

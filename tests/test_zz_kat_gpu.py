@@ -1,11 +1,7 @@
 """Upstream's known-answer tables of tests/test_oracle_kat2.py (ack-commit, stepdown, candidate fallback, start of
 an election, preceding entries, proposals by role) replayed THROUGH THE GPU ENGINE, one message per tick: the same
 test bodies, with the engine behind the state-machine verbs instead of a CPU restatement.
-
-STATUS: written after round 1's GPU budget was spent.  Only engine entry points the GPU suite already validates
-are used (sparse posts, proposals, idle ticks, partial imports, state export), and the bodies are rehearsed on the
-CPU against tests/engine_double.py (tests/test_rehearsals_cpu.py) — but this file has not yet run on hardware, so
-it is non-strict xfail until it has.  Round 2 removes the marker."""
+The bodies are also rehearsed on the CPU against tests/engine_double.py (tests/test_rehearsals_cpu.py)."""
 import numpy as np
 import pytest
 
@@ -13,8 +9,7 @@ import test_oracle_kat2 as k
 from raftsql_b200 import Engine
 from raftsql_b200 import _ffi as F
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="upstream tables through the engine: first hardware run pending")]
+pytestmark = [pytest.mark.gpu]
 
 
 class EngineSM:

@@ -1,21 +1,9 @@
 """GPU side of the byte-form inbox (include/mrq_packed8.h, word_bits = 8): unpack8_inbox_kernel must produce exactly
 what the host decode `mrq_unpack8` produces (same inline codec; tests/test_packed8_cpu.py proves that one exact),
 slide the device's window in step with the frame builder's, and the ticks that consume it must stay bit-equal to
-the oracle.
-
-STATUS: this form was written after round 1's GPU budget was spent — the codec, the frame builder and the decode
-are verified on the CPU, including the kernel's own per-group body (`unpack8_group`, compiled for the host and run
-against the oracle in tests/cpp/tick_host_test.cpp); the kernel's launch wrapper and the `word_bits = 8` branch of
-`mrq_post_inbox_packed` have not yet run on hardware.  Until they have, this file is shielded twice:
-  * the tests run in a CHILD pytest process (`test_byte_form_suite_in_a_child_process` spawns it), so that neither a
-    poisoned CUDA context nor a crash in never-run host code can reach the process that holds the validated suite;
-  * that one wrapper test is non-strict xfail: a pass is reported as XPASS, a failure as xfail.
-Round 2 runs them directly (`MRQ_PACKED8_INPROC=1 pytest tests/test_zz_packed8_gpu.py -m gpu --runxfail`, see
-tools/round2_first_call.sh) and then removes both shields.
+the oracle.  These tests run in-process like every other GPU test: a failure here turns the suite red.
 """
 import os
-import subprocess
-import sys
 
 import numpy as np
 import pytest
@@ -27,19 +15,7 @@ from raftsql_b200 import _ffi as F
 from raftsql_b200.packed import Pack8, unpack8
 from util import assert_state_equal
 
-INPROC = os.environ.get("MRQ_PACKED8_INPROC") == "1"
 pytestmark = [pytest.mark.gpu]
-child_only = pytest.mark.skipif(not INPROC, reason="runs in a child process: test_byte_form_suite_in_a_child_process")
-
-
-@pytest.mark.skipif(INPROC, reason="this IS the child process")
-@pytest.mark.xfail(strict=False, reason="byte-form inbox and tick mode 3: first hardware run pending (arithmetic CPU-verified)")
-def test_byte_form_suite_in_a_child_process():
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"],
-                       capture_output=True, text=True, timeout=1700, env=dict(os.environ, MRQ_PACKED8_INPROC="1"),
-                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    tail = (r.stdout + r.stderr)[-3000:]
-    assert r.returncode == 0 and " passed" in tail and " failed" not in tail, tail
 
 
 def _orc_params(p):
@@ -60,7 +36,6 @@ def _warm(G, R, seed, ticks, cfg_no):
     return eng, orc, p
 
 
-@child_only
 @pytest.mark.parametrize("G,R,cfg", [(4000, 7, 5), (3001, 5, 3), (777, 2, 5), (64, 1, 2), (2500, 8, 5)])
 def test_byte_form_decodes_like_the_host_and_ticks_like_the_oracle(G, R, cfg):
     eng, orc, p = _warm(G, R, 31 + R, 60, cfg)
@@ -109,7 +84,6 @@ def test_byte_form_decodes_like_the_host_and_ticks_like_the_oracle(G, R, cfg):
     eng.close()
 
 
-@child_only
 @pytest.mark.parametrize("G,R,cfg", [(4000, 7, 5), (3001, 5, 3), (777, 2, 5), (2500, 8, 5), (3000, 3, 2)])
 def test_tick_mode_3_consumes_the_bytes_itself(G, R, cfg):
     """tick mode 3: no unpack pass — tick_fast8_kernel reads the frame in the staging buffer, tick_slow8_kernel
@@ -144,7 +118,6 @@ def test_tick_mode_3_consumes_the_bytes_itself(G, R, cfg):
     eng.close()
 
 
-@child_only
 def test_device_window_slides_by_itself_for_hundreds_of_ticks():
     """steady-state leaders (bench shape): one set_packed_base, then 300 frames with no host re-base, no escapes"""
     G, R = 8192, 5

@@ -3,8 +3,7 @@
 #
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'
 #
-# 1. the byte-form inbox on hardware for the first time (tests/test_zz_packed8_gpu.py WITHOUT the xfail shield),
-#    and under compute-sanitizer memcheck on a reduced run;
+# 1. the full -m gpu suite without -x (every shield removed), and the byte form under compute-sanitizer memcheck;
 # 2. the default bench (e2e.packed8 = the byte form's end-to-end number, from its child process);
 # 3. the persisting-L2 experiment of DESIGN.md §10 item 0: the same bench with the device limit raised;
 # 4. a launch list of the byte-form e2e leg (share of unpack8 / tick / drain kernels in its step).
@@ -13,22 +12,19 @@ set -u
 OUT=gpurun_out/r02_first
 mkdir -p "$OUT"
 
-echo "== 1. byte-form GPU tests (xfail shield off)" | tee "$OUT/summary.txt"
-MRQ_PACKED8_INPROC=1 timeout 900 python -m pytest tests/test_zz_packed8_gpu.py -m gpu --runxfail -q > "$OUT/packed8_tests.log" 2>&1
+echo "== 1. the FULL -m gpu suite, no -x, no shields" | tee "$OUT/summary.txt"
+timeout 1200 python -m pytest tests -m gpu -q -p no:cacheprovider > "$OUT/gpu_suite.log" 2>&1
 echo "exit $?" | tee -a "$OUT/summary.txt"
-tail -5 "$OUT/packed8_tests.log" | tee -a "$OUT/summary.txt"
+tail -15 "$OUT/gpu_suite.log" | tee -a "$OUT/summary.txt"
+grep -E "^(FAILED|ERROR)" "$OUT/gpu_suite.log" | tee -a "$OUT/summary.txt"
 
-echo "== 1b. memcheck on one byte-form case" | tee -a "$OUT/summary.txt"
-MRQ_PACKED8_INPROC=1 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 \
+echo "== 1b. memcheck on one byte-form case + one mode-3 case" | tee -a "$OUT/summary.txt"
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 \
   python -m pytest "tests/test_zz_packed8_gpu.py::test_byte_form_decodes_like_the_host_and_ticks_like_the_oracle[777-2-5]" \
-  -m gpu --runxfail -x -q > "$OUT/packed8_memcheck.log" 2>&1
+  "tests/test_zz_packed8_gpu.py::test_tick_mode_3_consumes_the_bytes_itself[777-2-5]" \
+  -m gpu -q -p no:cacheprovider > "$OUT/packed8_memcheck.log" 2>&1
 echo "exit $?" | tee -a "$OUT/summary.txt"
 grep -E "ERROR SUMMARY|passed|failed" "$OUT/packed8_memcheck.log" | tail -3 | tee -a "$OUT/summary.txt"
-
-echo "== 1c. multi-group seam over the engine (xfail shield off)" | tee -a "$OUT/summary.txt"
-timeout 900 python -m pytest tests/test_zz_multipipe_gpu.py tests/test_zz_kat_gpu.py tests/test_cpp_host.py -m gpu --runxfail -q > "$OUT/multipipe_tests.log" 2>&1
-echo "exit $?" | tee -a "$OUT/summary.txt"
-tail -3 "$OUT/multipipe_tests.log" | tee -a "$OUT/summary.txt"
 
 echo "== 2. default bench" | tee -a "$OUT/summary.txt"
 timeout 900 python bench.py > "$OUT/bench_default.json" 2> "$OUT/bench_default.err"
