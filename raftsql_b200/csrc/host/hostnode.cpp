@@ -48,6 +48,97 @@ bool Log::maybe_append(uint64_t index, uint64_t logterm, const std::vector<Entry
   return true;
 }
 
+// ---- WAL records ---------------------------------------------------------------------------------------------
+// One format for both logs:  [u8 kind][u32 group][u64 a][u64 b][u64 c][u32 len][u32 crc][len bytes]
+// crc = CRC-32 (IEEE) of everything before it plus the payload.  A scan stops at the first record that is cut
+// short or fails its CRC (a crash mid-append); open() truncates the file to that valid prefix BEFORE appending,
+// as etcd's wal repairs its tail — otherwise every record written after the first crash would sit behind the
+// garbage and be dropped by the next replay (a node could vote twice in a term or lose acknowledged entries).
+namespace {
+uint32_t crc32_update(uint32_t crc, const void *data, size_t n) {
+  static uint32_t table[256];
+  static bool init = false;
+  if (!init) {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+      table[i] = c;
+    }
+    init = true;
+  }
+  const unsigned char *p = (const unsigned char *)data;
+  crc = ~crc;
+  for (size_t i = 0; i < n; ++i) crc = table[(crc ^ p[i]) & 0xFFu] ^ (crc >> 8);
+  return ~crc;
+}
+constexpr size_t kWalHeader = 1 + 4 + 8 + 8 + 8 + 4;  // bytes before the crc field
+
+void wal_put(FILE *f, char kind, uint32_t g, uint64_t a, uint64_t b, uint64_t c, const std::string &payload) {
+  unsigned char h[kWalHeader + 4];
+  const uint32_t len = (uint32_t)payload.size();
+  h[0] = (unsigned char)kind;
+  std::memcpy(h + 1, &g, 4);
+  std::memcpy(h + 5, &a, 8);
+  std::memcpy(h + 13, &b, 8);
+  std::memcpy(h + 21, &c, 8);
+  std::memcpy(h + 29, &len, 4);
+  uint32_t crc = crc32_update(0, h, kWalHeader);
+  if (len) crc = crc32_update(crc, payload.data(), len);
+  std::memcpy(h + kWalHeader, &crc, 4);
+  std::fwrite(h, 1, sizeof h, f);
+  if (len) std::fwrite(payload.data(), 1, len, f);
+}
+
+// calls rec(kind, group, a, b, c, payload) for every valid record; returns the byte offset where the valid prefix ends
+template <class F>
+long wal_scan(const std::string &path, F rec) {
+  FILE *f = std::fopen(path.c_str(), "rb");
+  if (!f) return 0;
+  std::fseek(f, 0, SEEK_END);
+  const long file_size = std::ftell(f);
+  std::fseek(f, 0, SEEK_SET);
+  long good = 0;
+  for (;;) {
+    unsigned char h[kWalHeader + 4];
+    if (std::fread(h, 1, sizeof h, f) != sizeof h) break;  // half a header
+    uint32_t g, len, crc;
+    uint64_t a, b, c;
+    std::memcpy(&g, h + 1, 4);
+    std::memcpy(&a, h + 5, 8);
+    std::memcpy(&b, h + 13, 8);
+    std::memcpy(&c, h + 21, 8);
+    std::memcpy(&len, h + 29, 4);
+    std::memcpy(&crc, h + kWalHeader, 4);
+    if ((long)len > file_size - std::ftell(f)) break;  // its length field outruns the file
+    std::string payload(len, '\0');
+    if (len && std::fread(&payload[0], 1, len, f) != len) break;
+    uint32_t want = crc32_update(0, h, kWalHeader);
+    if (len) want = crc32_update(want, payload.data(), len);
+    if (want != crc) break;  // bytes that never all reached the disk
+    rec((char)h[0], g, a, b, c, payload);
+    good = std::ftell(f);
+  }
+  std::fclose(f);
+  return good;
+}
+
+// cut a torn tail off (and make the cut durable) so that appends land right behind the last valid record
+void wal_repair_tail(const std::string &path) {
+  struct stat st;
+  if (::stat(path.c_str(), &st) != 0) return;
+  const long good = wal_scan(path, [](char, uint32_t, uint64_t, uint64_t, uint64_t, const std::string &) {});
+  if (good < (long)st.st_size) {
+    if (::truncate(path.c_str(), good) == 0) {
+      FILE *f = std::fopen(path.c_str(), "rb+");
+      if (f) {
+        ::fsync(fileno(f));
+        std::fclose(f);
+      }
+    }
+  }
+}
+}  // namespace
+
 // ---- Wal -------------------------------------------------------------------------------------------------
 bool Wal::exist(const std::string &dir) {
   struct stat st;
@@ -56,6 +147,7 @@ bool Wal::exist(const std::string &dir) {
 
 bool Wal::open() {
   ::mkdir(dir_.c_str(), 0750);  // raft.go:101
+  wal_repair_tail(path_);
   f_ = std::fopen(path_.c_str(), "ab");
   return f_ != nullptr;
 }
@@ -67,15 +159,7 @@ void Wal::close() {
   }
 }
 
-void Wal::put(char kind, uint64_t a, uint64_t b, uint64_t c, const std::string &payload) {
-  const uint32_t len = (uint32_t)payload.size();
-  std::fwrite(&kind, 1, 1, f_);
-  std::fwrite(&a, 8, 1, f_);
-  std::fwrite(&b, 8, 1, f_);
-  std::fwrite(&c, 8, 1, f_);
-  std::fwrite(&len, 4, 1, f_);
-  if (len) std::fwrite(payload.data(), 1, len, f_);
-}
+void Wal::put(char kind, uint64_t a, uint64_t b, uint64_t c, const std::string &payload) { wal_put(f_, kind, 0, a, b, c, payload); }
 
 void Wal::save(const uint64_t *hs, const std::vector<Entry> &new_entries, uint64_t first_index, bool truncate, uint64_t truncate_after) {
   if (!f_) return;
@@ -89,21 +173,7 @@ void Wal::save(const uint64_t *hs, const std::vector<Entry> &new_entries, uint64
 void Wal::read_all(std::vector<Entry> *ents, bool *has_hs, uint64_t hs[3]) {
   ents->clear();
   *has_hs = false;
-  FILE *f = std::fopen(path_.c_str(), "rb");
-  if (!f) return;
-  std::fseek(f, 0, SEEK_END);
-  const long file_size = std::ftell(f);
-  std::fseek(f, 0, SEEK_SET);
-  for (;;) {
-    char kind;
-    uint64_t a, b, c;
-    uint32_t len;
-    if (std::fread(&kind, 1, 1, f) != 1 || std::fread(&a, 8, 1, f) != 1 || std::fread(&b, 8, 1, f) != 1 ||
-        std::fread(&c, 8, 1, f) != 1 || std::fread(&len, 4, 1, f) != 1)
-      break;
-    if ((long)len > file_size - std::ftell(f)) break;  // torn tail record: its length field outruns the file
-    std::string payload(len, '\0');
-    if (len && std::fread(&payload[0], 1, len, f) != len) break;  // torn tail record
+  wal_scan(path_, [&](char kind, uint32_t, uint64_t a, uint64_t b, uint64_t c, const std::string &payload) {
     if (kind == 'H') {
       *has_hs = true;
       hs[0] = a;
@@ -120,12 +190,10 @@ void Wal::read_all(std::vector<Entry> *ents, bool *has_hs, uint64_t hs[3]) {
     } else if (kind == 'T') {
       if (a < ents->size()) ents->resize(a);
     }
-  }
-  std::fclose(f);
+  });
 }
 
 // ---- MultiWal ------------------------------------------------------------------------------------------------
-// records: [u8 kind][u32 group][u64 a][u64 b][u64 c][u32 len][len bytes]
 bool MultiWal::existed() const {
   struct stat st;
   return ::stat(path_.c_str(), &st) == 0;
@@ -134,6 +202,8 @@ bool MultiWal::existed() const {
 bool MultiWal::open() {
   if (f_) return true;
   ::mkdir(dir_.c_str(), 0750);
+  parse();                   // replay first: the records of the valid prefix
+  wal_repair_tail(path_);    // then cut the torn tail off before anything is appended
   f_ = std::fopen(path_.c_str(), "ab");
   return f_ != nullptr;
 }
@@ -148,14 +218,7 @@ void MultiWal::close() {
 
 void MultiWal::put(uint32_t g, char kind, uint64_t a, uint64_t b, uint64_t c, const std::string &payload) {
   if (!f_) return;
-  const uint32_t len = (uint32_t)payload.size();
-  std::fwrite(&kind, 1, 1, f_);
-  std::fwrite(&g, 4, 1, f_);
-  std::fwrite(&a, 8, 1, f_);
-  std::fwrite(&b, 8, 1, f_);
-  std::fwrite(&c, 8, 1, f_);
-  std::fwrite(&len, 4, 1, f_);
-  if (len) std::fwrite(payload.data(), 1, len, f_);
+  wal_put(f_, kind, g, a, b, c, payload);
   dirty_ = true;
 }
 
@@ -167,45 +230,32 @@ void MultiWal::sync() {
   ++syncs_;
 }
 
-const MultiWal::Replayed &MultiWal::replayed(uint32_t g) {
-  if (!parsed_) {
-    parsed_ = true;
-    FILE *f = std::fopen(path_.c_str(), "rb");
-    if (f) {
-      std::fseek(f, 0, SEEK_END);
-      const long file_size = std::ftell(f);
-      std::fseek(f, 0, SEEK_SET);
-      for (;;) {
-        char kind;
-        uint32_t grp, len;
-        uint64_t a, b, c;
-        if (std::fread(&kind, 1, 1, f) != 1 || std::fread(&grp, 4, 1, f) != 1 || std::fread(&a, 8, 1, f) != 1 ||
-            std::fread(&b, 8, 1, f) != 1 || std::fread(&c, 8, 1, f) != 1 || std::fread(&len, 4, 1, f) != 1)
-          break;
-        if ((long)len > file_size - std::ftell(f)) break;  // torn tail record
-        std::string payload(len, '\0');
-        if (len && std::fread(&payload[0], 1, len, f) != len) break;
-        Replayed &r = groups_[grp];
-        if (kind == 'H') {
-          r.has_hs = true;
-          r.hs[0] = a;
-          r.hs[1] = b;
-          r.hs[2] = c;
-        } else if (kind == 'E') {
-          if (a >= 1 && a <= r.ents.size() + 1) {
-            r.ents.resize(a - 1);
-            Entry e;
-            e.term = b;
-            e.data = payload;
-            r.ents.push_back(e);
-          }
-        } else if (kind == 'T') {
-          if (a < r.ents.size()) r.ents.resize(a);
-        }
+void MultiWal::parse() {
+  if (parsed_) return;
+  parsed_ = true;
+  wal_scan(path_, [&](char kind, uint32_t grp, uint64_t a, uint64_t b, uint64_t c, const std::string &payload) {
+    Replayed &r = groups_[grp];
+    if (kind == 'H') {
+      r.has_hs = true;
+      r.hs[0] = a;
+      r.hs[1] = b;
+      r.hs[2] = c;
+    } else if (kind == 'E') {
+      if (a >= 1 && a <= r.ents.size() + 1) {
+        r.ents.resize(a - 1);
+        Entry e;
+        e.term = b;
+        e.data = payload;
+        r.ents.push_back(e);
       }
-      std::fclose(f);
+    } else if (kind == 'T') {
+      if (a < r.ents.size()) r.ents.resize(a);
     }
-  }
+  });
+}
+
+const MultiWal::Replayed &MultiWal::replayed(uint32_t g) {
+  parse();
   return groups_[g];
 }
 
@@ -325,12 +375,16 @@ void HostNode::hardstate(uint64_t *term, uint64_t *vote, uint64_t *commit, uint6
 
 void HostNode::propose(const std::string &data) { pending_.push_back(data); }
 
-bool HostNode::resolve_append(const Message &m, std::map<uint32_t, Message> *replies, CoreMsg *out) {
+// Resolved against the (term, role) the engine will have when it Steps this message: prepare_tick walks the tick's
+// messages in sender order, as the engine does, so an append the engine is going to drop on the term rule never
+// touches the host log or the WAL.
+bool HostNode::resolve_append(const Message &m, std::map<uint32_t, Message> *replies, CoreMsg *out, uint64_t eff_term,
+                              uint32_t eff_role) {
   out->from = m.from;
   out->type = MRQ_MSG_APP;
   out->term = m.term;
   out->index = out->logterm = out->commit = 0;
-  if (m.term < term_ || (role_ == MRQ_ROLE_LEADER && m.term == term_)) return true;  // the engine drops it on the term rule
+  if (m.term < eff_term || (eff_role == MRQ_ROLE_LEADER && m.term == eff_term)) return true;  // the engine drops it on the term rule
   Message rep;
   rep.type = kMsgAppResp;
   rep.to = m.from;
@@ -383,23 +437,46 @@ HostNode::Prepared HostNode::prepare_tick() {
   Prepared prep;
   std::vector<CoreMsg> &eng_msgs = prep.msgs;
   std::map<uint32_t, Message> &replies = prep.replies;
-  std::set<uint32_t> seen;
+  // One message per sender per tick (include/mrq.h), and at most ONE MsgApp per tick (a second one, from another
+  // sender, was matched against a log the first is about to change): the rest waits in the backlog, in order.
+  std::map<uint32_t, Message> chosen;
+  bool have_app = false;
   for (const Message &m : inbound) {
     if (m.type == kMsgProp) {  // a follower forwarded client proposals to us
       for (const Entry &e : m.entries) pending_.push_back(e.data);
       continue;
     }
-    if (seen.count(m.from)) {  // the engine inbox holds one message per sender per tick (include/mrq.h)
+    if (chosen.count(m.from) || (m.type == kMsgApp && have_app)) {
       backlog_.push_back(m);
       continue;
     }
-    seen.insert(m.from);
+    chosen[m.from] = m;
+    have_app = have_app || m.type == kMsgApp;
+  }
+  // The engine Steps the tick's messages in SENDER order: a higher-term message from a lower sender id
+  // moves it to that term before it sees a later sender's MsgApp.  Track that effective (term, role) here.
+  uint64_t eff_term = term_;
+  uint32_t eff_role = role_;
+  for (auto &kv : chosen) {  // std::map: ascending sender id
+    const Message &m = kv.second;
+    if (m.term > eff_term) {  // Step(): becomeFollower(m.Term, ...)
+      eff_term = m.term;
+      eff_role = MRQ_ROLE_FOLLOWER;
+    }
     CoreMsg cm;
     if (m.type == kMsgApp) {
-      resolve_append(m, &replies, &cm);
+      bool votes_before = false;
+      for (auto &kv2 : chosen) votes_before = votes_before || (kv2.first < kv.first && kv2.second.type == kMsgVoteResp);
+      if (eff_role == MRQ_ROLE_CANDIDATE && m.term == eff_term && votes_before) {
+        backlog_.insert(backlog_.begin(), m);  // the votes may make us leader within this tick: resolve it next tick
+        continue;
+      }
+      resolve_append(m, &replies, &cm, eff_term, eff_role);
       eng_msgs.push_back(cm);
+      if (eff_role == MRQ_ROLE_CANDIDATE && m.term == eff_term) eff_role = MRQ_ROLE_FOLLOWER;
       continue;
     }
+    if (m.type == kMsgHeartbeat && eff_role == MRQ_ROLE_CANDIDATE && m.term == eff_term) eff_role = MRQ_ROLE_FOLLOWER;
     if (m.type == kMsgAppResp && m.reject && role_ == MRQ_ROLE_LEADER && m.term == term_)
       next_[m.from] = std::max<uint64_t>(1, std::min(m.index, m.reject_hint + 1));  // Progress.maybeDecrTo
     if (m.type == kMsgHeartbeatResp && role_ == MRQ_ROLE_LEADER && m.term == term_) behind_.insert(m.from);
@@ -551,6 +628,12 @@ std::vector<std::string> HostNode::ready(const CoreState &s, std::map<uint32_t, 
     const std::string &d = log_.ents[applied_ - 1].data;
     if (!d.empty()) published.push_back(d);  // "ignore conf changes and empty messages" (raft.go:84-86)
   }
+  // the engine tracks (lastIndex, lastTerm) of the log the host keeps: after Ready they must agree (fatal otherwise,
+  // like the reference's log.Fatalf sites: every later vote / commit decision would be about a log that does not exist)
+  if (s.last_index != log_.last_index() || s.last_term != log_.last_term())
+    throw std::runtime_error("host log and engine diverged: log (" + std::to_string(log_.last_index()) + ", t" +
+                             std::to_string(log_.last_term()) + ") engine (" + std::to_string(s.last_index) + ", t" +
+                             std::to_string(s.last_term) + ")");
   return published;
 }
 

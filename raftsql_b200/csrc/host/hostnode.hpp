@@ -118,7 +118,8 @@ class MultiWal {
     uint64_t hs[3] = {0, 0, 0};
   };
   void put(uint32_t g, char kind, uint64_t a, uint64_t b, uint64_t c, const std::string &payload);
-  const Replayed &replayed(uint32_t g);  // parses the file once
+  void parse();                          // replays the file's valid prefix, once
+  const Replayed &replayed(uint32_t g);
   std::string dir_, path_;
   FILE *f_ = nullptr;
   bool dirty_ = false, parsed_ = false;
@@ -170,7 +171,7 @@ class HostNode {
   uint64_t commit() const { return commit_; }
 
  private:
-  bool resolve_append(const Message &m, std::map<uint32_t, Message> *replies, CoreMsg *out);
+  bool resolve_append(const Message &m, std::map<uint32_t, Message> *replies, CoreMsg *out, uint64_t eff_term, uint32_t eff_role);
   std::vector<std::string> ready(const CoreState &s, std::map<uint32_t, Message> &replies);
   std::vector<uint32_t> peers() const;
 

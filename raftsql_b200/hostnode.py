@@ -22,6 +22,7 @@ import json
 import os
 import struct
 import threading
+import zlib
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -94,6 +95,50 @@ class Log:
         return lastnewi, True, first_written, truncated
 
 
+def frame_record(rec: dict) -> bytes:
+    """one WAL record: u32 length, u32 CRC-32 of the payload, JSON payload"""
+    b = json.dumps(rec, separators=(",", ":")).encode()
+    return struct.pack("<II", len(b), zlib.crc32(b)) + b
+
+
+def scan_records(path: str):
+    """-> (records, valid_end): every record up to the first torn / garbled one, and the byte offset where the
+    valid prefix ends (a length that outruns the file, a CRC mismatch, or half a header all end the scan)."""
+    recs = []
+    if not os.path.exists(path):
+        return recs, 0
+    with open(path, "rb") as f:
+        buf = f.read()
+    off = 0
+    while off + 8 <= len(buf):
+        n, crc = struct.unpack_from("<II", buf, off)
+        if off + 8 + n > len(buf):
+            break  # torn tail record
+        body = buf[off + 8: off + 8 + n]
+        if zlib.crc32(body) != crc:
+            break  # a record whose bytes never all reached the disk: everything before it stands
+        try:
+            recs.append(json.loads(body))
+        except ValueError:
+            break
+        off += 8 + n
+    return recs, off
+
+
+def repair_tail(path: str) -> int:
+    """truncate the file to its valid prefix and make that durable; returns the number of bytes cut"""
+    if not os.path.exists(path):
+        return 0
+    _, end = scan_records(path)
+    size = os.path.getsize(path)
+    if end < size:
+        with open(path, "r+b") as f:
+            f.truncate(end)
+            f.flush()
+            os.fsync(f.fileno())
+    return size - end
+
+
 class Wal:
     """A minimal write-ahead log standing in for etcd `wal` (reference raft.go:100-124,228): a directory
     `raftsql-<id>` with one append-only file of length-prefixed JSON records
@@ -109,26 +154,16 @@ class Wal:
         return os.path.exists(os.path.join(dirname, "wal.log"))
 
     def open(self):
+        """Open for appending.  A torn or garbled tail (a crash mid-append) is CUT OFF first, as etcd's wal repairs
+        its tail before reuse: appending behind the garbage would hide every later record from the next replay."""
         os.makedirs(self.dir, mode=0o750, exist_ok=True)  # raft.go:101
+        repair_tail(self.path)
         self.f = open(self.path, "ab")
 
     def read_all(self):
         """-> (hardstate or None, entries [(term, data)])  (wal.ReadAll, raft.go:124)"""
         hs, ents = None, []
-        if not os.path.exists(self.path):
-            return hs, ents
-        with open(self.path, "rb") as f:
-            buf = f.read()
-        off = 0
-        while off + 4 <= len(buf):
-            (n,) = struct.unpack_from("<I", buf, off)
-            if off + 4 + n > len(buf):
-                break  # torn tail record
-            try:
-                rec = json.loads(buf[off + 4: off + 4 + n])
-            except ValueError:
-                break  # a record whose bytes never all reached the disk: everything before it stands
-            off += 4 + n
+        for rec in scan_records(self.path)[0]:
             if "hs" in rec:
                 hs = tuple(rec["hs"])
             elif "e" in rec:
@@ -140,8 +175,7 @@ class Wal:
         return hs, ents
 
     def _put(self, rec):
-        b = json.dumps(rec, separators=(",", ":")).encode()
-        self.f.write(struct.pack("<I", len(b)) + b)
+        self.f.write(frame_record(rec))
 
     def save(self, hardstate, new_entries, first_index, truncate_after=None):  # wal.Save (raft.go:228)
         if truncate_after is not None:
@@ -251,23 +285,45 @@ class HostNode:
         inbound = self.backlog + self.tr.drain(self.id)
         self.backlog = []
         eng_msgs, app_replies = [], {}
-        seen_from: set[int] = set()
+        # the engine inbox holds ONE message per sender per tick (include/mrq.h): a second message from the
+        # same peer (say MsgApp then MsgHeartbeat when two of its ticks land in one of ours) waits for the
+        # next tick, in order.  At most ONE MsgApp is resolved per tick: a second one (another sender) was
+        # matched against a log the first is about to change, so it waits too.
+        chosen: dict[int, Message] = {}
+        have_app = False
         for m in inbound:
             if m.type == MsgProp:  # a follower forwarded client proposals to us
                 self.pending.extend(d for (_, d) in m.entries)
                 continue
-            # the engine inbox holds ONE message per sender per tick (include/mrq.h): a second message
-            # from the same peer (say MsgApp then MsgHeartbeat when two of its ticks land in one of ours)
-            # waits for the next tick, in order
-            if m.frm in seen_from:
+            if m.frm in chosen or (m.type == F.MSG_APP and have_app):
                 self.backlog.append(m)
                 continue
-            seen_from.add(m.frm)
+            chosen[m.frm] = m
+            have_app = have_app or m.type == F.MSG_APP
+        # The engine Steps the tick's messages in SENDER order, so a higher-term message from a
+        # lower sender id moves the engine to that term before it sees a later sender's MsgApp.  The host must
+        # resolve the append against that same effective (term, role), or it would change its log and WAL for
+        # an append the engine then drops on the term rule (host log and engine would disagree: ADVICE r1).
+        eff_term, eff_role = self.term, self.role
+        for frm in sorted(chosen):
+            m = chosen[frm]
+            if m.term > eff_term:  # Step(): becomeFollower(m.Term, ...)
+                eff_term, eff_role = m.term, F.ROLE_FOLLOWER
             if m.type == F.MSG_APP:
-                rec = self._resolve_append(m, app_replies)
+                if eff_role == F.ROLE_CANDIDATE and m.term == eff_term and any(
+                        c.type == F.MSG_VOTE_RESP and f < frm for f, c in chosen.items()):
+                    # votes stepped before it may make us leader within this tick (the append would then be
+                    # ignored): let the votes land first, resolve the append next tick
+                    self.backlog.insert(0, m)
+                    continue
+                rec = self._resolve_append(m, app_replies, eff_term, eff_role)
                 if rec is not None:
                     eng_msgs.append(rec)
+                if eff_role == F.ROLE_CANDIDATE and m.term == eff_term:
+                    eff_role = F.ROLE_FOLLOWER  # stepCandidate MsgApp: becomeFollower(Term, From)
                 continue
+            if m.type == F.MSG_HEARTBEAT and eff_role == F.ROLE_CANDIDATE and m.term == eff_term:
+                eff_role = F.ROLE_FOLLOWER
             if m.type == F.MSG_APP_RESP and m.reject and self.role == F.ROLE_LEADER and m.term == self.term:
                 # Progress.maybeDecrTo: message-construction state, host side
                 self.next[m.frm] = max(1, min(m.index, m.reject_hint + 1))
@@ -291,9 +347,12 @@ class HostNode:
         """Everything of step_tick that follows the engine's tick (Ready handling)."""
         return self._ready(app_replies)
 
-    def _resolve_append(self, m: Message, replies: dict):
-        """The log-matching half of handleAppendEntries, host side (include/mrq.h MSG_APP contract)."""
-        if m.term < self.term or (self.role == F.ROLE_LEADER and m.term == self.term):
+    def _resolve_append(self, m: Message, replies: dict, eff_term: int | None = None, eff_role: int | None = None):
+        """The log-matching half of handleAppendEntries, host side (include/mrq.h MSG_APP contract), against the
+        (term, role) the engine will have when it Steps this message (prepare_tick computes them in sender order)."""
+        eff_term = self.term if eff_term is None else eff_term
+        eff_role = self.role if eff_role is None else eff_role
+        if m.term < eff_term or (eff_role == F.ROLE_LEADER and m.term == eff_term):
             return (0, m.frm, F.MSG_APP, m.term, 0, 0, 0)  # the engine will drop it on the term rule
         if m.index < self.commit:
             replies[m.frm] = Message(F.MSG_APP_RESP, m.frm, self.id, index=self.commit)
@@ -376,6 +435,11 @@ class HostNode:
             d = self.log.ents[self.applied - 1][1]
             if d:  # "ignore conf changes and empty messages" (raft.go:84-86)
                 published.append(d)
+        # the engine tracks (lastIndex, lastTerm) of the log the host keeps: after Ready they must agree, or every
+        # later vote / commit decision is made about a log that does not exist (fatal, like the reference's log.Fatalf)
+        if (last, int(s["last_term"][0])) != (self.log.last_index(), self.log.last_term()):
+            raise RuntimeError(f"node {self.id}: host log ({self.log.last_index()}, t{self.log.last_term()}) and engine "
+                               f"({last}, t{int(s['last_term'][0])}) diverged")
         return published
 
     def _peers(self):

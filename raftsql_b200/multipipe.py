@@ -25,6 +25,7 @@ import time
 
 import numpy as np
 
+from . import hostnode
 from .hostnode import HostNode
 from .raftpipe import Chan, ChanClosed, _send_or_stop
 
@@ -88,6 +89,8 @@ class MultiWal:
     def open(self):
         if self.f is None:
             os.makedirs(self.dir, mode=0o750, exist_ok=True)
+            self.parse()                      # replay BEFORE the tail is cut and new records land
+            hostnode.repair_tail(self.path)   # a torn tail is cut off, or every later record would hide behind it
             self.f = open(self.path, "ab")
 
     def parse(self) -> dict:
@@ -95,34 +98,21 @@ class MultiWal:
         if self._parsed is not None:
             return self._parsed
         out: dict = {}
-        if os.path.exists(self.path):
-            with open(self.path, "rb") as f:
-                buf = f.read()
-            off = 0
-            while off + 4 <= len(buf):
-                (n,) = struct.unpack_from("<I", buf, off)
-                if off + 4 + n > len(buf):
-                    break
-                try:
-                    rec = json.loads(buf[off + 4: off + 4 + n])
-                except ValueError:
-                    break
-                off += 4 + n
-                hs, ents = out.setdefault(rec["g"], [None, []])
-                if "hs" in rec:
-                    out[rec["g"]][0] = tuple(rec["hs"])
-                elif "e" in rec:
-                    i, t, d = rec["e"]
-                    del ents[i - 1:]
-                    ents.append((t, bytes.fromhex(d)))
-                elif "t" in rec:
-                    del ents[rec["t"]:]
+        for rec in hostnode.scan_records(self.path)[0]:
+            hs, ents = out.setdefault(rec["g"], [None, []])
+            if "hs" in rec:
+                out[rec["g"]][0] = tuple(rec["hs"])
+            elif "e" in rec:
+                i, t, d = rec["e"]
+                del ents[i - 1:]
+                ents.append((t, bytes.fromhex(d)))
+            elif "t" in rec:
+                del ents[rec["t"]:]
         self._parsed = {g: (v[0], v[1]) for g, v in out.items()}
         return self._parsed
 
     def put(self, rec: dict):
-        b = json.dumps(rec, separators=(",", ":")).encode()
-        self.f.write(struct.pack("<I", len(b)) + b)
+        self.f.write(hostnode.frame_record(rec))
         self.dirty = True
 
     def sync(self):

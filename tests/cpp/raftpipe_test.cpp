@@ -309,11 +309,14 @@ void test_wal_recovery(const std::string &dir) {
     const char kind = 'E';
     const uint64_t a = 4, b = 2, c = 0;
     const uint32_t len = 0xC0000000u;
+    const uint32_t grp = 0, crc = 0;
     std::fwrite(&kind, 1, 1, f);
+    std::fwrite(&grp, 4, 1, f);
     std::fwrite(&a, 8, 1, f);
     std::fwrite(&b, 8, 1, f);
     std::fwrite(&c, 8, 1, f);
     std::fwrite(&len, 4, 1, f);
+    std::fwrite(&crc, 4, 1, f);
     std::fwrite("xy", 1, 2, f);
     std::fclose(f);
   }
@@ -324,6 +327,34 @@ void test_wal_recovery(const std::string &dir) {
   w.read_all(&ents, &has_hs, hs);
   CHECK(ents.size() == 3 && ents[2].data == "payload-2" && ents[0].term == 2, "intact prefix must survive a torn tail (%zu entries)", ents.size());
   CHECK(has_hs && hs[0] == 2 && hs[1] == 1 && hs[2] == 2, "hardstate must survive a torn tail");
+  {  // restart #1 appends AFTER the tear: open() must cut the garbage off first, or restart #2 loses these records
+    Wal w1(wdir);
+    CHECK(w1.open(), "reopen the torn wal");
+    std::vector<Entry> more(1);
+    more[0].term = 3;
+    more[0].data = "after-the-crash";
+    const uint64_t hs3[3] = {3, 2, 2};
+    w1.save(hs3, more, 4, false, 0);
+    w1.close();
+    Wal w2(wdir);
+    w2.read_all(&ents, &has_hs, hs);
+    CHECK(ents.size() == 4 && ents[3].data == "after-the-crash" && ents[3].term == 3,
+          "records saved after a torn tail must be replayed by the next restart (%zu entries)", ents.size());
+    CHECK(has_hs && hs[0] == 3 && hs[1] == 2, "the vote saved after a torn tail must survive (term %llu)", (unsigned long long)hs[0]);
+  }
+  {  // a flipped payload bit: the CRC ends the valid prefix there
+    const std::string path = wdir + "/wal.bin";
+    FILE *f = std::fopen(path.c_str(), "rb+");
+    std::fseek(f, -3, SEEK_END);  // inside the last record (the H record has no payload: this hits its crc/len area)
+    int ch = std::fgetc(f);
+    std::fseek(f, -3, SEEK_END);
+    std::fputc(ch ^ 1, f);
+    std::fclose(f);
+    Wal w3(wdir);
+    w3.read_all(&ents, &has_hs, hs);
+    CHECK(has_hs && hs[0] == 2 && ents.size() == 4, "a damaged last record is dropped, the prefix stands (term %llu, %zu entries)",
+          (unsigned long long)hs[0], ents.size());
+  }
 
   // an unopenable wal directory (a regular file stands where the directory should be) fails start()
   const std::string blocker = dir + "/not-a-dir";
@@ -571,6 +602,66 @@ void test_handle_msgapp_table(const std::string &dir) {
   }
 }
 
+// node 3 (term 2, log [1:t1, 2:t2]) hears in ONE tick MsgVote(term 7) from node 1 and MsgApp(term 2) from
+// node 2.  The engine Steps in sender order: term 7 first, then it drops the append on the term rule — the host must
+// not have appended / truncated / saved anything for it, and nothing may be acknowledged to the old leader.
+void test_msgapp_behind_a_higher_term_message(const std::string &dir) {
+  const std::string wdir = dir + "/stale-app";
+  {
+    Wal w(wdir);
+    CHECK(w.open(), "open wal");
+    std::vector<Entry> es(2);
+    es[0].term = 1;
+    es[0].data = "a";
+    es[1].term = 2;
+    es[1].data = "b";
+    const uint64_t hs[3] = {2, 0, 0};
+    w.save(hs, es, 1, false, 0);
+  }
+  auto tr = std::make_shared<LocalTransport>();
+  tr->add(1);
+  tr->add(2);
+  HostNode node(std::unique_ptr<Core>(new OracleCore(3, 3)), 3, 3, tr, wdir);
+  node.start();
+  raftsql::Message app, vote;
+  app.type = kMsgApp;
+  app.to = 3;
+  app.from = 2;
+  app.term = 2;
+  app.index = 1;
+  app.logterm = 1;
+  Entry e;
+  e.term = 2;
+  e.data = "would-truncate";
+  app.entries.push_back(e);
+  e.data = "more";
+  app.entries.push_back(e);
+  e.term = 2;
+  vote.type = kMsgVote;
+  vote.to = 3;
+  vote.from = 1;
+  vote.term = 7;
+  vote.index = 9;
+  vote.logterm = 9;
+  tr->send({app, vote});
+  node.step_tick();
+  uint64_t term, v, commit, li, lt;
+  node.hardstate(&term, &v, &commit, &li, &lt);
+  CHECK(term == 7 && v == 1, "the vote is granted at the new term (term %llu vote %llu)", (unsigned long long)term, (unsigned long long)v);
+  CHECK(li == 2 && lt == 2, "the stale append changed nothing (last %llu t%llu)", (unsigned long long)li, (unsigned long long)lt);
+  bool acked = false;
+  for (const raftsql::Message &m : tr->drain(2)) acked = acked || m.type == kMsgAppResp;
+  CHECK(!acked, "nothing is acknowledged to the deposed leader");
+  node.stop();
+  Wal w(wdir);
+  std::vector<Entry> ents;
+  bool has_hs = false;
+  uint64_t hs[3];
+  w.read_all(&ents, &has_hs, hs);
+  CHECK(ents.size() == 2 && ents[1].data == "b", "the WAL still holds the old log (%zu entries)", ents.size());
+  CHECK(has_hs && hs[0] == 7 && hs[1] == 1, "and the hardstate of the new term");
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -586,11 +677,11 @@ int main(int argc, char **argv) {
     test_chan_semantics();
     test_wal_recovery(dir);
     test_handle_msgapp_table(dir);
+    test_msgapp_behind_a_higher_term_message(dir);
     test_group_commit_wal(dir);
     test_single_node(core, dir);
     test_cluster_and_restart(core, dir);
-    // over the GPU engine the multi-group scenario is opt-in until its first hardware run (tests/test_cpp_host.py)
-    if (core == "oracle" || std::getenv("MRQ_TEST_MULTI_GROUP")) test_multi_group_cluster(core, dir);
+    test_multi_group_cluster(core, dir);
   } catch (const std::exception &ex) {
     std::printf("FAIL exception: %s\n", ex.what());
     ++failures;

@@ -58,9 +58,5 @@ def test_cpp_host_under_sanitizers(tmp_path, san, env):
 
 @pytest.mark.gpu
 def test_cpp_raftpipe_scenarios_gpu_engine(tmp_path):
+    """every C++ scenario — single node, 3-node cluster + restart, and the multi-group seam — over the GPU engine"""
     _run("engine", tmp_path)
-
-
-@pytest.mark.gpu
-def test_cpp_multi_group_seam_gpu_engine(tmp_path):
-    _run("engine", tmp_path, env={"MRQ_TEST_MULTI_GROUP": "1"})

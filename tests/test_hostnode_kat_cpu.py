@@ -172,3 +172,44 @@ def test_TestLeaderAppResp():
     # a stale (lower-term) ack is ignored by the term rule
     match, committed, _ = step(Message(F.MSG_APP_RESP, 1, 2, term=T - 1, index=9))
     assert (match, committed) == (3, 3)
+
+
+def test_msgapp_behind_a_higher_term_message_of_the_same_tick_leaves_log_and_wal_alone(tmp_path):
+    """the engine Steps a tick's messages in sender order.  Node 3 (term 5) hears, in ONE tick,
+    MsgVote(term 7) from node 1 and MsgApp(term 5) from node 2: the engine moves to term 7 first and drops the append
+    on the term rule — so the host must not have appended / truncated / saved anything for it."""
+    tr = LocalTransport()
+    for p in (1, 2):
+        tr.register(p)
+    core = make_oracle_core(3, 3)
+    node = HostNode(core, 3, 3, tr, str(tmp_path / "raftsql-3"))
+    node.start()
+    node.log.ents = [(5, b"a"), (5, b"b")]
+    node.term, node.commit, node.lead = 5, 0, 2
+    core.import_state({"term": u64(5), "vote": u64(0), "committed": u64(0), "last_index": u64(2), "last_term": u64(5),
+                       "lead": np.array([2], np.uint8)})
+    wal_size = lambda: __import__("os").path.getsize(node.wal.path)
+    before = wal_size()
+    tr.send([Message(F.MSG_APP, 3, 2, term=5, logterm=5, index=1, commit=0, entries=[(5, b"conflict-free"), (5, b"more")]),
+             Message(F.MSG_VOTE, 3, 1, term=7, logterm=9, index=9)])
+    node.step_tick()
+    assert node.term == 7 and node.vote == 1                      # the vote was granted at the new term
+    assert [d for _, d in node.log.ents] == [b"a", b"b"]          # the stale append changed nothing
+    s = node.core.export_state()
+    assert (int(s["last_index"][0]), int(s["last_term"][0])) == (2, 5)
+    from raftsql_b200.hostnode import scan_records
+    recs = scan_records(node.wal.path)[0]
+    assert all("e" not in r and "t" not in r for r in recs), recs  # only the hardstate of the new term was saved
+    assert wal_size() > before and recs[-1]["hs"][:2] == [7, 1]
+    assert not [m for m in tr.drain(2) if m.type == F.MSG_APP_RESP]  # and nothing was acknowledged to the old leader
+    node.stop()
+
+
+def test_two_msgapps_in_one_tick_are_resolved_one_per_tick():
+    node, tr = follower_with_log([1, 2], term=2)
+    tr.send([Message(F.MSG_APP, 1, 2, term=2, logterm=2, index=2, commit=0, entries=[(2, b"x3")]),
+             Message(F.MSG_APP, 1, 3, term=2, logterm=2, index=2, commit=0, entries=[(2, b"other3")])])
+    node.step_tick()
+    assert node.log.last_index() == 3 and len(node.backlog) == 1   # the second append waits for the next tick
+    node.step_tick()
+    assert node.log.last_index() == 3 and not node.backlog

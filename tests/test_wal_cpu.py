@@ -40,13 +40,13 @@ def test_torn_tail_records_are_dropped_and_the_prefix_stands(tmp_path):
     good = os.path.getsize(w.path)
     # (a) a length prefix that outruns the file
     with open(w.path, "ab") as f:
-        f.write(struct.pack("<I", 1 << 30) + b'{"e":[4,1,')
+        f.write(struct.pack("<II", 1 << 30, 0) + b'{"e":[4,1,')
     assert Wal(w.dir).read_all() == ((1, 1, 2), [(1, b""), (1, b"CREATE"), (1, b"INSERT-0")])
     # (b) a complete length but bytes that are not a record (the sector never reached the disk)
     with open(w.path, "r+b") as f:
         f.truncate(good)
         f.seek(good)
-        f.write(struct.pack("<I", 6) + b"\0\0\0\0\0\0")
+        f.write(struct.pack("<II", 6, 0) + b"\0\0\0\0\0\0")
     assert Wal(w.dir).read_all() == ((1, 1, 2), [(1, b""), (1, b"CREATE"), (1, b"INSERT-0")])
     # (c) only half a length prefix
     with open(w.path, "r+b") as f:
@@ -54,6 +54,40 @@ def test_torn_tail_records_are_dropped_and_the_prefix_stands(tmp_path):
         f.seek(good)
         f.write(b"\x07\x00")
     assert Wal(w.dir).read_all() == ((1, 1, 2), [(1, b""), (1, b"CREATE"), (1, b"INSERT-0")])
+
+
+def test_a_torn_tail_is_cut_off_on_open_so_later_records_survive_the_next_restart(tmp_path):
+    """read_all stopped at a torn record but open() appended BEHIND it, hiding every later record (votes,
+    acknowledged entries) from the next replay.  Now open() truncates to the valid prefix first."""
+    w = _saved(tmp_path)
+    good = os.path.getsize(w.path)
+    for garbage in (struct.pack("<II", 1 << 30, 0) + b'{"e":[4,1,', struct.pack("<II", 6, 0) + b"\0\0\0\0\0\0", b"\x07\x00"):
+        with open(w.path, "r+b") as f:
+            f.truncate(good)
+            f.seek(good)
+            f.write(garbage)
+        w2 = Wal(w.dir)                      # crash, restart #1
+        assert w2.read_all()[0] == (1, 1, 2)
+        w2.open()
+        assert os.path.getsize(w.path) == good, "the torn tail must be cut off before anything is appended"
+        w2.save((3, 2, 2), [(3, b"after-the-crash")], 4)
+        w2.close()
+        hs, ents = Wal(w.dir).read_all()     # restart #2 finds what restart #1 saved
+        assert hs == (3, 2, 2) and ents[-1] == (3, b"after-the-crash") and len(ents) == 4
+        with open(w.path, "r+b") as f:
+            f.truncate(good)
+
+
+def test_a_flipped_bit_inside_a_record_ends_the_valid_prefix(tmp_path):
+    w = _saved(tmp_path)
+    size = os.path.getsize(w.path)
+    with open(w.path, "r+b") as f:  # corrupt one payload byte of the LAST record (the hardstate (1,1,2))
+        f.seek(size - 3)
+        b = f.read(1)
+        f.seek(size - 3)
+        f.write(bytes([b[0] ^ 0x01]))
+    hs, ents = Wal(w.dir).read_all()
+    assert hs == (1, 1, 0) and len(ents) == 3  # the CRC rejects the damaged record; the prefix stands
 
 
 def test_missing_wal_reads_as_empty(tmp_path):
