@@ -273,8 +273,19 @@ int mrq_tick_idle(mrq_engine *e, uint32_t n);
  * (differential testing); 3 = mode 0 on the BYTE FORM of the inbox: a slot posted with word_bits = 8 is not
  * unpacked — the fast kernel reads the frame's bytes where the copy left them and the general kernel
  * materialises only the groups the fast one declines (a slot posted in any other form ticks as in mode 0;
- * no graph replay in this mode).  All give identical results.                                    */
+ * no graph replay in this mode); 4 = the byte form on COMPACT STATE: every index-like column of a group
+ * (lastIndex, committed, Progress.Match, the frame window) is held as a 32-bit offset from one per-group
+ * 64-bit base, one thread owns four adjacent groups (128-bit column accesses), and the steady-state tick
+ * moves ~82 B per group instead of 217; a group whose values do not fit, or whose tick needs the role
+ * machinery, goes through the general path on the wide columns and is re-compacted; every call that
+ * reads or writes wide state (import / export / sync / gen_trace / quorum / a wide post) converts first.
+ * In mode 4 mrq_tick_many runs its whole slot sequence in ONE pair of launches (each thread carries its
+ * groups' state in registers from tick to tick; per-tick out words and commit advances go to per-slot
+ * buffers).  All modes give identical results.                                                   */
 int mrq_set_tick_mode(mrq_engine *e, int mode);
+/* mrq_tick_many in mode 4: 1 (default) = the state columns are written back after every tick of the
+ * sequence (device state is exact at tick granularity), 0 = after the last tick only.           */
+int mrq_set_write_through(mrq_engine *e, int on);
 
 /* The standalone quorum kernel (K3; SURVEY §8a rows a15–a16): for every leader group,
  * mci = q-th largest of match[0..R-1][g]; committed = mci iff mci > committed && mci >= term_start.
@@ -310,6 +321,14 @@ int mrq_sync_commit_deltas(mrq_engine *e, uint8_t *delta_out);
  * is idle, so an mrq_post_inbox_packed issued in between keeps copying underneath.             */
 int mrq_drain_commit_deltas(mrq_engine *e, uint8_t *delta_out_pinned);
 int mrq_drain_wait(mrq_engine *e);
+/* Mode 4 only: the tick kernels themselves write each group's commit advance of THAT tick (one byte,
+ * 255 = "read the index in full") next to its out word, so draining the last tick is a plain
+ * asynchronous copy (page-locked destination; mrq_drain_wait waits for it) — no extra kernel.
+ * MRQ_E_STATE when the last tick was not a mode-4 tick on a byte frame.                           */
+int mrq_drain_tick_deltas(mrq_engine *e, uint8_t *delta_out_pinned);
+/* Mode 4, after mrq_tick_many: the out words and commit advances of the tick that consumed inbox slot `slot`
+ * (every tick of the sequence writes to its slot's own buffers).  Blocking; a NULL pointer skips that column. */
+int mrq_sync_slot_outputs(mrq_engine *e, uint32_t slot, uint32_t *out_words, uint8_t *delta_out);
 int mrq_synchronize(mrq_engine *e);
 
 /* ---- synthetic vote/append traces, generated on the device (include/mrq_trace.h) -------- */

@@ -131,6 +131,9 @@ SIGNATURES = {
     "mrq_sync_commit_deltas": (C.c_int, [_EP, u8p]),
     "mrq_drain_commit_deltas": (C.c_int, [_EP, u8p]),
     "mrq_drain_wait": (C.c_int, [_EP]),
+    "mrq_drain_tick_deltas": (C.c_int, [_EP, u8p]),
+    "mrq_set_write_through": (C.c_int, [_EP, C.c_int]),
+    "mrq_sync_slot_outputs": (C.c_int, [_EP, C.c_uint32, u32p, u8p]),
     "mrq_synchronize": (C.c_int, [_EP]),
     "mrq_gen_trace": (C.c_int, [_EP, C.c_uint32, C.POINTER(TraceParams), C.c_uint64]),
     "mrq_read_inbox": (C.c_int, [_EP, C.c_uint32, C.POINTER(InboxOut)]),

@@ -10,9 +10,13 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <condition_variable>
+#include <functional>
 #include <map>
+#include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_set>
 #include <vector>
 
 #include "mrq_kernels.cuh"
@@ -123,6 +127,18 @@ struct mrq_engine {
   uint64_t *peer_gather[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool ipc_attached = false;
   int quorum_variant = 0;  // 0 = LDG.256 (4 groups/thread), 1 = TMA bulk, 2 = LDG.128
+  // tick mode 4: compact state (32-bit offsets from a per-group base) + the byte inbox, four groups per thread
+  CompactView c{};
+  bool compact_alloc = false;  // the compact columns exist
+  bool compact_live = false;   // some groups may be compact-authoritative (wide columns stale for them)
+  unsigned long long *slow_list64 = nullptr;
+  std::vector<uint32_t *> out_slot;   // per inbox slot: that tick's out words (mrq_tick_many in mode 4)
+  std::vector<uint8_t *> delta_slot;  // per inbox slot: that tick's commit advances
+  uint32_t *last_out = nullptr;       // where the most recent tick wrote its out words (mrq_sync_out)
+  uint8_t *last_delta = nullptr;      // ... and its commit advances (mrq_drain_tick_deltas)
+  int write_through = 1;              // multi-tick launches: state columns written after every tick (1) or the last (0)
+  uint64_t stage_gen = 0;             // bumps when a staging buffer moves: cached descriptor tables are keyed by it
+  std::map<std::string, TickDesc *> desc_tables;
   std::string err;
 };
 
@@ -222,14 +238,48 @@ int g_sm_count = 148;
 // (N=2: 51.5k vs 43.2k ticks/s; N=4: 72.3k vs 60.0k; N=8: 81.8k vs 63.8k) and loses at 1,048,576 (40.9 vs 37.5 us).
 constexpr uint64_t kGraphAutoMaxGroups = 600000;
 
-int launch_tick(mrq_engine *e, const InboxBuf *ib) {
-  if (e->G == 0) {
-    e->tick_no++;
-    return MRQ_OK;
-  }
-  TickArgs a{};
+
+// ---- tick mode 4 plumbing ------------------------------------------------------------------------------------------
+int ensure_compact_alloc(mrq_engine *e) {
+  if (e->compact_alloc) return MRQ_OK;
+  const size_t gs = e->gs;
+  int r;
+  if ((r = dalloc(e, &e->c.flag, gs))) return r;
+  if ((r = dalloc(e, &e->c.commit, gs))) return r;
+  if ((r = dalloc(e, &e->c.win, gs))) return r;
+  if ((r = dalloc(e, &e->c.gate, gs))) return r;
+  if ((r = dalloc(e, &e->c.iblo, gs))) return r;
+  if ((r = dalloc(e, &e->c.match, gs * e->R))) return r;
+  if ((r = dalloc(e, &e->c.ibase, gs))) return r;
+  if ((r = dalloc(e, &e->slow_list64, gs))) return r;
+  e->compact_alloc = true;
+  return MRQ_OK;
+}
+
+// Make the WIDE columns exact (compact -> wide for every compact group).  invalidate: the caller is about to change
+// wide state, so the compact copies die (every group is re-compacted by the next mode-4 tick).
+int ensure_wide(mrq_engine *e, bool invalidate) {
+  if (!e->compact_live || e->G == 0) return MRQ_OK;
+  materialise_all_kernel<<<nblocks(e->G), 256, 0, e->stream>>>(e->s, e->c, e->pk_base_index, e->gs, e->G, e->R, invalidate ? 1 : 0);
+  CK(e, cudaGetLastError());
+  e->launches++;
+  if (invalidate) e->compact_live = false;
+  return MRQ_OK;
+}
+
+int ensure_compact(mrq_engine *e) {
+  if (e->compact_live || e->G == 0) return MRQ_OK;
+  int r = ensure_compact_alloc(e);
+  if (r) return r;
+  compact_all_kernel<<<nblocks(e->G), 256, 0, e->stream>>>(e->s, e->c, e->pk_base_index, e->pk_base_term, e->gs, e->G, e->R);
+  CK(e, cudaGetLastError());
+  e->launches++;
+  e->compact_live = true;
+  return MRQ_OK;
+}
+
+void fill_tick_args(mrq_engine *e, TickArgs &a) {
   a.s = e->s;
-  if (ib) a.in = ib->view();
   a.ctr = e->ctr;
   a.G = e->G;
   a.gs = e->gs;
@@ -247,15 +297,121 @@ int launch_tick(mrq_engine *e, const InboxBuf *ib) {
     a.peer_lo[p] = reinterpret_cast<uint32_t *>(e->peer_gather[p]);
     a.peer_hi[p] = a.peer_lo[p] ? a.peer_lo[p] + (size_t)e->world * e->G : nullptr;
   }
-  if (a.world > 1) e->gather_prime = false;
-  e->tick_parity ^= 1u;
   a.slow_list = e->slow_list;
   a.slow_count = e->slow_count + (e->slow_parity & 1u);
   a.slow_count_next = e->slow_count + ((e->slow_parity + 1u) & 1u);
+}
+
+// n ticks of mode 4 in ONE pair of launches: every slot holds a byte frame (mrq_post_inbox_packed, word_bits 8).
+int launch_tick4(mrq_engine *e, const uint32_t *slots, uint32_t n) {
+  int r = ensure_compact(e);
+  if (r) return r;
+  Tick4Args A{};
+  fill_tick_args(e, A.t);
+  A.c = e->c;
+  A.base_index = e->pk_base_index;
+  A.base_term = e->pk_base_term;
+  A.nticks = n;
+  A.write_through = e->write_through ? 1u : 0u;
+  A.slow_list64 = e->slow_list64;
+  auto desc_of = [&](uint32_t slot, bool per_slot_outputs, TickDesc *d) -> int {
+    PackedStage &sg = e->pk_stage[slot];
+    d->word8 = sg.word8;
+    d->prop8 = sg.prop8;
+    d->in = e->inbox[slot].view();
+    if (per_slot_outputs) {
+      if (e->out_slot.size() < e->inbox.size()) e->out_slot.resize(e->inbox.size(), nullptr);
+      if (e->delta_slot.size() < e->inbox.size()) e->delta_slot.resize(e->inbox.size(), nullptr);
+      int rr;
+      if (!e->out_slot[slot] && (rr = dalloc(e, &e->out_slot[slot], e->gs))) return rr;
+      if (!e->delta_slot[slot] && (rr = dalloc(e, &e->delta_slot[slot], e->gs))) return rr;
+      d->out = e->out_slot[slot];
+      d->delta = e->delta_slot[slot];
+    } else {
+      d->out = e->s.out;
+      d->delta = e->delta;
+    }
+    return MRQ_OK;
+  };
+  if (n == 1) {
+    if ((r = desc_of(slots[0], false, &A.d0))) return r;
+    A.descs = nullptr;
+    e->last_out = A.d0.out;
+    e->last_delta = A.d0.delta;
+  } else {
+    std::string key((const char *)slots, (size_t)n * sizeof(uint32_t));
+    key.append((const char *)&e->stage_gen, sizeof e->stage_gen);
+    auto it = e->desc_tables.find(key);
+    if (it == e->desc_tables.end()) {  // first use of this slot sequence: build and upload its descriptor table
+      std::vector<TickDesc> host(n);
+      for (uint32_t k = 0; k < n; ++k)
+        if ((r = desc_of(slots[k], true, &host[k]))) return r;
+      TickDesc *dev = nullptr;
+      CK(e, cudaMalloc((void **)&dev, n * sizeof(TickDesc)));
+      CK(e, cudaMemcpyAsync(dev, host.data(), n * sizeof(TickDesc), cudaMemcpyHostToDevice, e->stream));
+      CK(e, cudaStreamSynchronize(e->stream));  // `host` dies with this scope
+      it = e->desc_tables.emplace(key, dev).first;
+    }
+    A.descs = it->second;
+    A.d0 = TickDesc{};
+    e->last_out = e->out_slot[slots[n - 1]];
+    e->last_delta = e->delta_slot[slots[n - 1]];
+  }
+  const unsigned nb = nblocks(e->gs / 4, kQuadThreads);
+  cudaError_t lst = cudaErrorInvalidValue;
+  MRQ_DISPATCH_R(e->R, lst = launch_pdl(tick_fast4_kernel<kR>, nb, kQuadThreads, 0, e->stream, A));
+  CK(e, lst);
+  unsigned nslow = (unsigned)g_sm_count * 6u;
+  const unsigned nb1 = nblocks(e->G, kTickThreads);
+  if (nslow > nb1) nslow = nb1;
+  MRQ_DISPATCH_R(e->R, lst = launch_pdl(tick_slow4_kernel<kR>, nslow, kTickThreads, 0, e->stream, A));
+  CK(e, lst);
+  // host-side bookkeeping only once both launches are in the stream
+  e->launches += 2;
+  e->tick_parity ^= 1u;
+  e->slow_parity ^= 1u;
+  if (A.t.world > 1) e->gather_prime = false;
+  e->tick_no += n;
+  for (uint32_t k = 0; k < n; ++k) {
+    PackedStage &sg = e->pk_stage[slots[k]];
+    if (!sg.keep8) sg.frame8 = false;
+    CK(e, cudaEventRecord(sg.consumed, e->stream));  // only now may the next frame overwrite the staging buffer
+  }
+  return MRQ_OK;
+}
+
+bool slot_has_frame8(mrq_engine *e, uint32_t slot) { return slot < e->pk_stage.size() && e->pk_stage[slot].frame8; }
+
+int launch_tick(mrq_engine *e, const InboxBuf *ib) {
+  if (e->G == 0) {
+    e->tick_no++;
+    return MRQ_OK;
+  }
+  const size_t slot = ib ? (size_t)(ib - e->inbox.data()) : 0;
+  if (e->tick_mode == 4) {
+    if (ib && slot_has_frame8(e, (uint32_t)slot)) {
+      const uint32_t s1 = (uint32_t)slot;
+      int r = launch_tick4(e, &s1, 1);
+      if (r) return r;
+      if (e->world > 1 && e->comm_mode == 0 && e->comm) {  // per-tick ncclAllGather reads the wide committed column
+        if ((r = ensure_wide(e, false))) return r;
+        int st = g_nccl.AllGather(e->s.committed, e->gathered, (size_t)e->G, kNcclUint64, e->comm, e->stream);
+        if (st != 0) return fail(e, MRQ_E_NCCL, "ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(st) : "?");
+      }
+      return MRQ_OK;
+    }
+    // a wide inbox (or an idle tick) in mode 4: the general kernels work on the wide columns
+    int r = ensure_wide(e, true);
+    if (r) return r;
+  }
+  TickArgs a{};
+  fill_tick_args(e, a);
+  if (ib) a.in = ib->view();
   const unsigned nb = nblocks(e->G, kTickThreads);
   cudaError_t lst = cudaErrorInvalidValue;
-  const size_t slot = ib ? (size_t)(ib - e->inbox.data()) : 0;
-  if (e->tick_mode == 3 && ib && slot < e->pk_stage.size() && e->pk_stage[slot].frame8) {
+  unsigned nlaunch = 0;
+  bool flip_slow = false;
+  if (e->tick_mode == 3 && ib && slot_has_frame8(e, (uint32_t)slot)) {
     // the tick on the byte form: the kernels read the frame where the copy left it (no unpack pass)
     PackedStage &sg = e->pk_stage[slot];
     Tick8Args a8{a, Inbox8{sg.word8, sg.prop8, e->pk_base_index, e->pk_base_term}};
@@ -265,18 +421,18 @@ int launch_tick(mrq_engine *e, const InboxBuf *ib) {
     if (nslow > nb) nslow = nb;
     MRQ_DISPATCH_R(e->R, lst = launch_pdl(tick_slow8_kernel<kR>, nslow, kTickThreads, 0, e->stream, a8));
     CK(e, lst);
-    e->launches += 2;
-    e->slow_parity ^= 1u;
+    nlaunch = 2;
+    flip_slow = true;
     if (!sg.keep8) sg.frame8 = false;
     CK(e, cudaEventRecord(sg.consumed, e->stream));  // only now may the next frame overwrite the staging buffer
   } else if (e->tick_mode == 1) {  // single launch, every group through the general path (differential testing)
     MRQ_DISPATCH_R(e->R, lst = launch_pdl(tick_general_kernel<kR>, nb, kTickThreads, 0, e->stream, a));
     CK(e, lst);
-    e->launches++;
+    nlaunch = 1;
   } else if (e->tick_mode == 2) {  // single launch: fast tick + in-CTA general path for the stragglers
     MRQ_DISPATCH_R(e->R, lst = launch_pdl(tick_fused_kernel<kR>, nb, kTickThreads, 0, e->stream, a));
     CK(e, lst);
-    e->launches++;
+    nlaunch = 1;
   } else {
     MRQ_DISPATCH_R(e->R, lst = launch_pdl(tick_fast_kernel<kR>, nb, kTickThreads, 0, e->stream, a));
     CK(e, lst);
@@ -284,9 +440,17 @@ int launch_tick(mrq_engine *e, const InboxBuf *ib) {
     if (nslow > nb) nslow = nb;
     MRQ_DISPATCH_R(e->R, lst = launch_pdl(tick_slow_kernel<kR>, nslow, kTickThreads, 0, e->stream, a));
     CK(e, lst);
-    e->launches += 2;
-    e->slow_parity ^= 1u;
+    nlaunch = 2;
+    flip_slow = true;
   }
+  // the double-buffer parities move only once the launches are in the stream: a failed launch leaves the host's
+  // bookkeeping in step with the device
+  e->launches += nlaunch;
+  e->tick_parity ^= 1u;
+  if (flip_slow) e->slow_parity ^= 1u;
+  if (a.world > 1) e->gather_prime = false;
+  e->last_out = e->s.out;
+  e->last_delta = nullptr;
   e->tick_no++;
   if (e->world > 1 && e->comm_mode == 0 && e->comm) {
     int st = g_nccl.AllGather(e->s.committed, e->gathered, (size_t)e->G, kNcclUint64, e->comm, e->stream);
@@ -499,6 +663,16 @@ void mrq_destroy(mrq_engine *e) {
   void *ptrs[] = {e->s.term, e->s.meta, e->s.last_index, e->s.last_term, e->s.committed, e->s.term_start, e->s.match,
                   e->s.out, e->ctr, e->commit_prev, e->delta, e->gathered, e->scratch, e->pk_base_index, e->pk_base_term, e->slow_list, e->slow_count, e->tickbuf};
   for (auto &kv : e->graphs) cudaGraphExecDestroy(kv.second);
+  for (auto &kv : e->desc_tables) cudaFree(kv.second);
+  {
+    void *cp[] = {e->c.flag, e->c.commit, e->c.win, e->c.gate, e->c.iblo, e->c.match, e->c.ibase, e->slow_list64};
+    for (void *p : cp)
+      if (p) cudaFree(p);
+    for (void *p : e->out_slot)
+      if (p) cudaFree(p);
+    for (void *p : e->delta_slot)
+      if (p) cudaFree(p);
+  }
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (auto &ib : e->inbox) {
@@ -562,6 +736,10 @@ int mrq_export_state(mrq_engine *e, mrq_state *o) {
   CK(e, cudaSetDevice(e->device));
   const size_t gs = e->gs, G = e->G;
   if (G == 0) return MRQ_OK;
+  {
+    int rw = ensure_wide(e, false);
+    if (rw) return rw;
+  }
   // unpack meta into scratch columns: role, lead, self (u8), vote (u64), el, hb, rto (u16), votes (u8 [R][gs])
   const size_t need = gs * (3 + 8 + 6) + gs * e->R + 64;
   int r = ensure_scratch(e, need);
@@ -597,6 +775,7 @@ int mrq_import_state(mrq_engine *e, const mrq_state *in) {
   const size_t gs = e->gs, G = e->G;
   if (G == 0) return MRQ_OK;
   int r;
+  if ((r = ensure_wide(e, true))) return r;  // partial imports overwrite some wide columns: the rest must be exact first
   auto put = [&](void *dev, const void *host, size_t elem, size_t rows) -> int {
     if (!host) return MRQ_OK;
     return copy_in(e, dev, host, elem, rows);
@@ -642,8 +821,9 @@ int mrq_export_next(mrq_engine *e, uint64_t *next_out) {
   if (!e || !next_out) return MRQ_E_INVAL;
   CK(e, cudaSetDevice(e->device));
   if (e->G == 0) return MRQ_OK;
-  int r = ensure_scratch(e, e->G * e->R * 8);
+  int r = ensure_wide(e, false);
   if (r) return r;
+  if ((r = ensure_scratch(e, e->G * e->R * 8))) return r;
   export_next_kernel<<<nblocks(e->G), 256, 0, e->stream>>>(e->s.match, e->s.term_start, (uint64_t *)e->scratch, e->G, e->gs, e->R);
   CK(e, cudaGetLastError());
   e->launches++;
@@ -689,6 +869,27 @@ int mrq_post_inbox_delta(mrq_engine *e, uint32_t slot, const mrq_msg *msgs, size
   if (!accumulate && (r = mrq_clear_inbox(e, slot))) return r;
   if (n == 0) return MRQ_OK;
   if (!msgs) return fail(e, MRQ_E_INVAL, "null message list");
+  // Several messages for one (from, group) slot: the LAST one in the list wins (include/mrq.h).  The scatter kernel
+  // runs one unordered thread per message, so earlier duplicates are dropped here, on the host.
+  std::vector<mrq_msg> uniq;
+  {
+    std::unordered_set<uint64_t> seen;
+    seen.reserve(n * 2);
+    bool dup = false;
+    for (size_t k = n; k-- > 0;)
+      if (!seen.insert(msgs[k].group * 16u + msgs[k].from).second) {
+        dup = true;
+        break;
+      }
+    if (dup) {
+      seen.clear();
+      uniq.reserve(n);
+      for (size_t k = n; k-- > 0;)
+        if (seen.insert(msgs[k].group * 16u + msgs[k].from).second) uniq.push_back(msgs[k]);
+      msgs = uniq.data();
+      n = uniq.size();
+    }
+  }
   if ((r = ensure_scratch(e, n * sizeof(mrq_msg)))) return r;
   CK(e, cudaMemcpyAsync(e->scratch, msgs, n * sizeof(mrq_msg), cudaMemcpyHostToDevice, e->stream));
   scatter_msgs_kernel<<<nblocks(n), 256, 0, e->stream>>>(e->inbox[slot].view(), e->gs, e->G, e->R, (const MsgRec *)e->scratch, n);
@@ -732,6 +933,7 @@ int mrq_post_inbox_packed(mrq_engine *e, uint32_t slot, const mrq_inbox_packed *
     CK(e, cudaMalloc(&sg.buf, need + (1u << 16)));
     sg.bytes = need + (1u << 16);
     sg.used = false;
+    e->stage_gen++;  // descriptor tables cached by mrq_tick_many hold the old address
   }
   uint8_t *d_word = (uint8_t *)sg.buf;
   uint8_t *d_prop = d_word + wbytes;
@@ -745,7 +947,7 @@ int mrq_post_inbox_packed(mrq_engine *e, uint32_t slot, const mrq_inbox_packed *
   if (bits == 32u) {
     unpack_inbox_kernel<<<nblocks(e->G), 256, 0, e->stream>>>(e->inbox[slot].view(), e->pk_base_index, e->pk_base_term, e->gs,
                                                             e->G, e->R, (const uint32_t *)d_word, in->prop_count8 ? d_prop : nullptr);
-  } else if (bits == 8u && e->tick_mode == 3) {
+  } else if (bits == 8u && e->tick_mode >= 3) {
     // tick mode 3: no unpack pass — the tick kernels read the frame in the staging buffer (launch_tick records
     // `consumed` after them); only the escapes are scattered into the slot's wide columns, below
     sg.word8 = d_word;
@@ -782,6 +984,10 @@ int mrq_set_packed_base(mrq_engine *e, const uint64_t *base_index, const uint64_
   if (!e) return MRQ_E_INVAL;
   CK(e, cudaSetDevice(e->device));
   if (e->G == 0) return MRQ_OK;
+  {
+    int rw = ensure_wide(e, true);  // the window base is part of the compact representation (mode 4)
+    if (rw) return rw;
+  }
   if (base_index) CK(e, cudaMemcpyAsync(e->pk_base_index, base_index, e->G * 8, cudaMemcpyHostToDevice, e->stream));
   if (base_term) CK(e, cudaMemcpyAsync(e->pk_base_term, base_term, e->G * 8, cudaMemcpyHostToDevice, e->stream));
   CK(e, cudaStreamSynchronize(e->stream));
@@ -792,26 +998,94 @@ int mrq_set_packed_base(mrq_engine *e, const uint64_t *base_index, const uint64_
 }  // extern "C"
 
 namespace {
-// Contiguous group ranges on host threads: frames of a million groups are memory-bound host work (33 B of wide
-// columns read per cell), so the builder scales with the cores the host gives it.  MRQ_HOST_THREADS overrides.
+// Contiguous group ranges on a PERSISTENT pool of host threads: frames of a million groups are memory-bound host work
+// (17 B of wide columns read per cell), so the builder scales with the cores the host gives it, and a live host builds
+// one frame per tick — spawning threads per call would cost more than the frame.  MRQ_HOST_THREADS overrides the size.
+class HostPool {
+ public:
+  ~HostPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto &t : th_) t.join();
+  }
+  // f(chunk) for chunk = 0..n-1, on up to n threads (the caller's included); returns when all are done
+  template <class F>
+  void run(unsigned n, F f) {
+    if (n <= 1) {
+      if (n) f(0u);
+      return;
+    }
+    std::lock_guard<std::mutex> serial(run_mu_);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      while (th_.size() + 1 < n) th_.emplace_back([this] { worker(); });
+      job_ = [&f](unsigned c) { f(c); };
+      njobs_ = n;
+      next_ = 0;
+      left_ = n;
+      ++gen_;
+    }
+    cv_.notify_all();
+    drain();
+    std::unique_lock<std::mutex> lk(mu_);
+    done_cv_.wait(lk, [this] { return left_ == 0; });
+    job_ = nullptr;
+  }
+  std::vector<uint64_t> scratch;  // owned by whoever holds the pool inside run()'s caller (mrq_pack8 serialises itself)
+
+ private:
+  void drain() {
+    for (;;) {
+      unsigned c;
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (next_ >= njobs_) return;
+        c = next_++;
+      }
+      job_(c);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--left_ == 0) done_cv_.notify_all();
+      }
+    }
+  }
+  void worker() {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
+        if (stop_) return;
+        seen = gen_;
+      }
+      drain();
+    }
+  }
+  std::mutex mu_, run_mu_;
+  std::condition_variable cv_, done_cv_;
+  std::vector<std::thread> th_;
+  std::function<void(unsigned)> job_;
+  unsigned njobs_ = 0, next_ = 0, left_ = 0;
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+};
+HostPool &host_pool() {
+  static HostPool *p = new HostPool();  // leaked on purpose: worker threads must not be joined from a static destructor
+  return *p;
+}
+std::mutex g_pack_mu;
+
 unsigned host_threads(uint64_t G) {
   unsigned hw = std::thread::hardware_concurrency();
-  if (const char *s = getenv("MRQ_HOST_THREADS")) hw = (unsigned)strtoul(s, nullptr, 10);
+  unsigned cap = 32;  // memory-bound work: past a few threads per memory channel more buys nothing
+  if (const char *s = getenv("MRQ_HOST_THREADS")) hw = cap = (unsigned)strtoul(s, nullptr, 10);
   if (hw < 1) hw = 1;
-  const uint64_t by_size = G / 32768;  // below ~32k groups per thread the spawn costs more than it saves
+  const uint64_t by_size = G / 16384;  // below ~16k groups per thread the hand-off costs more than it saves
   if (by_size < hw) hw = (unsigned)(by_size < 1 ? 1 : by_size);
-  return hw > 16 ? 16 : hw;  // memory-bound work: more threads than memory channels buys nothing
-}
-template <class F>
-void for_group_chunks(uint64_t G, unsigned nt, F f) {  // f(chunk, g0, g1)
-  if (nt <= 1) {
-    f(0u, (uint64_t)0, G);
-    return;
-  }
-  std::vector<std::thread> th;
-  th.reserve(nt);
-  for (unsigned c = 0; c < nt; ++c) th.emplace_back(f, c, G * c / nt, G * (c + 1) / nt);
-  for (auto &t : th) t.join();
+  return hw > cap ? cap : hw;
 }
 }  // namespace
 
@@ -824,24 +1098,32 @@ int mrq_pack8(const mrq_inbox *in, const uint8_t *self_id, uint64_t G, uint32_t 
   if (R < 1 || R > MRQ_MAX_REPLICAS) return fail(nullptr, MRQ_E_INVAL, "mrq_pack8: n_replicas %u outside 1..%u", R, MRQ_MAX_REPLICAS);
   if (R > 1 && !word_out) return fail(nullptr, MRQ_E_INVAL, "mrq_pack8: null word_out");
   const unsigned nt = host_threads(G);
-  // One pass over the wide columns (they are the cost: 33 B per cell): bytes and proposal counts go straight to
-  // the output buffers, escapes and the slid bases are staged per chunk and published only if everything fits,
-  // so a refused call leaves base_index — the state that must stay in step with the device — untouched.
+  std::lock_guard<std::mutex> one_at_a_time(g_pack_mu);  // (the staging buffer below is shared)
+  // One pass over the wide columns (they are the cost): bytes and proposal counts go straight to the output buffers;
+  // escapes and the slid bases are staged and published only if everything fits, so a refused call leaves base_index —
+  // the state that must stay in step with the device — untouched.  Only the columns a message's type needs are read.
   constexpr uint64_t kNone = ~0ull;
   std::vector<std::vector<mrq_msg>> esc(nt);
-  std::vector<std::vector<uint64_t>> slid(nt);
+  std::vector<uint64_t> &slid = host_pool().scratch;
+  if (slid.size() < G) slid.resize(G);
   std::vector<uint64_t> bad(nt, kNone);
-  for_group_chunks(G, nt, [&](unsigned c, uint64_t g0, uint64_t g1) {
-    std::vector<uint64_t> &nb = slid[c];
-    nb.resize(g1 - g0);
+  host_pool().run(nt, [&](unsigned c) {
+    const uint64_t g0 = G * c / nt, g1 = G * (c + 1) / nt;
     for (uint64_t g = g0; g < g1; ++g) {
       uint32_t min_ack = MRQ_P8_NO_ACK;
       const uint64_t bi = base_index[g], bt = base_term[g];
+      const uint32_t self = self_id[g];
       for (uint32_t r = 0; r < R; ++r) {
-        const uint32_t row = mrq_p8_row(r, self_id[g], R);
+        const uint32_t row = mrq_p8_row(r, self, R);
         if (row >= R - 1u) continue;  // the group's own slot: nothing is ever stepped from there
         const uint64_t o = (uint64_t)r * G + g;
-        const uint8_t b = mrq_p8_encode(in->type[o], in->term[o], in->index[o], in->commit[o], bi, bt);
+        const uint32_t ty = in->type[o];
+        if ((ty & 0x0Fu) == 0u) {
+          word_out[(uint64_t)row * G + g] = 0;
+          continue;
+        }
+        const uint32_t kind = ty & 0x0Fu;
+        const uint8_t b = mrq_p8_encode(ty, in->term[o], kind == 4u ? in->index[o] : 0, kind == 8u ? in->commit[o] : 0, bi, bt);
         word_out[(uint64_t)row * G + g] = b;
         if (b == MRQ_P8_ESCAPE) {
           mrq_msg m;
@@ -859,7 +1141,7 @@ int mrq_pack8(const mrq_inbox *in, const uint8_t *self_id, uint64_t G, uint32_t 
           min_ack = p < min_ack ? p : min_ack;
         }
       }
-      nb[g - g0] = mrq_p8_next_base(bi, min_ack);
+      slid[g] = mrq_p8_next_base(bi, min_ack);
       if (prop8_out) {
         const uint32_t n = in->prop_count ? in->prop_count[g] : 0u;
         if (n > 255u && bad[c] == kNone) bad[c] = g;
@@ -879,9 +1161,11 @@ int mrq_pack8(const mrq_inbox *in, const uint8_t *self_id, uint64_t G, uint32_t 
   for (unsigned c = 0; c < nt; ++c) {  // chunks are contiguous group ranges: the list stays in group order
     if (!esc[c].empty()) memcpy(wide_out + at, esc[c].data(), esc[c].size() * sizeof(mrq_msg));
     at += esc[c].size();
-    const uint64_t g0 = G * c / nt;
-    if (!slid[c].empty()) memcpy(base_index + g0, slid[c].data(), slid[c].size() * sizeof(uint64_t));
   }
+  host_pool().run(nt, [&](unsigned c) {  // publish the slid window
+    const uint64_t g0 = G * c / nt, g1 = G * (c + 1) / nt;
+    if (g1 > g0) memcpy(base_index + g0, slid.data() + g0, (g1 - g0) * sizeof(uint64_t));
+  });
   return MRQ_OK;
 }
 
@@ -960,6 +1244,7 @@ int mrq_gen_trace(mrq_engine *e, uint32_t slot, const struct mrq_trace_params *p
   if (!p) return MRQ_E_INVAL;
   CK(e, cudaSetDevice(e->device));
   if (e->G == 0) return MRQ_OK;
+  if ((r = ensure_wide(e, false))) return r;
   gen_trace_kernel<<<nblocks(e->G), 256, 0, e->stream>>>(e->inbox[slot].view(), e->s, e->gs, e->G, e->R, e->cfg.group_base, *p, tick);
   CK(e, cudaGetLastError());
   e->launches++;
@@ -988,11 +1273,25 @@ int mrq_tick_many(mrq_engine *e, const uint32_t *slots, uint32_t n) {
   }
   CK(e, cudaSetDevice(e->device));
   const bool nccl_gather = e->world > 1 && e->comm_mode == 0 && e->comm;
+  if (e->tick_mode == 4 && e->G > 0 && !nccl_gather && e->graph_mode != 0) {
+    // mode 4: the whole sequence in ONE pair of launches — every thread walks its four groups through the n frames
+    // (state in registers from tick to tick), the general kernel finishes the groups that left the fast path
+    bool all8 = true;
+    for (uint32_t k = 0; k < n; ++k) all8 = all8 && slot_has_frame8(e, slots[k]);
+    if (all8) {
+      constexpr uint32_t kMaxBatch = 4096;
+      for (uint32_t k = 0; k < n; k += kMaxBatch) {
+        int r = launch_tick4(e, slots + k, n - k < kMaxBatch ? n - k : kMaxBatch);
+        if (r) return r;
+      }
+      return MRQ_OK;
+    }
+  }
   // graph_mode: 0 never, 1 always, 2 (default) only for small shards, where the host's launch rate rather than
   // the kernels bounds the tick rate (measured on B200: at 1M groups per GPU PDL stream launches are faster)
   const bool want_graph = e->graph_mode == 1 || (e->graph_mode == 2 && e->G <= kGraphAutoMaxGroups);
   const bool can_graph = want_graph && n >= 2 && !e->graphs_disabled && !nccl_gather && !e->gather_prime && e->G > 0 &&
-                         e->tick_mode != 3;  // mode 3 ticks read per-post staging buffers: not replayable
+                         e->tick_mode < 3;  // mode 3/4 ticks read per-post staging buffers: not replayable
   if (!can_graph) {
     for (uint32_t k = 0; k < n; ++k) {
       int r = launch_tick(e, &e->inbox[slots[k]]);
@@ -1058,6 +1357,10 @@ int mrq_quorum_commit(mrq_engine *e) {
   if (!e) return MRQ_E_INVAL;
   CK(e, cudaSetDevice(e->device));
   if (e->G == 0) return MRQ_OK;
+  {
+    int rw = ensure_wide(e, true);
+    if (rw) return rw;
+  }
   QuorumArgs a{e->s.match, e->s.committed, e->s.term_start, e->ctr, e->G, e->gs};
   return launch_quorum(e, a, e->quorum_variant);
 }
@@ -1075,7 +1378,16 @@ int mrq_set_graph_mode(mrq_engine *e, int mode) {
 }
 
 int mrq_set_tick_mode(mrq_engine *e, int mode) {
-  if (!e || mode < 0 || mode > 3) return MRQ_E_INVAL;
+  if (!e || mode < 0 || mode > 4) return MRQ_E_INVAL;
+  CK(e, cudaSetDevice(e->device));
+  if (e->tick_mode == 4 && mode != 4) {  // leaving compact state: the wide columns become the only truth again
+    int r = ensure_wide(e, true);
+    if (r) return r;
+  }
+  if (mode == 4) {
+    int r = ensure_compact_alloc(e);
+    if (r) return r;
+  }
   e->tick_mode = mode;
   return MRQ_OK;
 }
@@ -1104,8 +1416,9 @@ int mrq_match_update(mrq_engine *e, const uint64_t *groups, const uint8_t *from,
   if (n == 0) return MRQ_OK;
   if (!groups || !from || !index) return fail(e, MRQ_E_INVAL, "null ack list");
   CK(e, cudaSetDevice(e->device));
-  int r = ensure_scratch(e, n * 17 + 64);
+  int r = ensure_wide(e, true);
   if (r) return r;
+  if ((r = ensure_scratch(e, n * 17 + 64))) return r;
   uint64_t *d_g = (uint64_t *)e->scratch, *d_i = d_g + n;
   uint8_t *d_f = (uint8_t *)(d_i + n);
   CK(e, cudaMemcpyAsync(d_g, groups, n * 8, cudaMemcpyHostToDevice, e->stream));
@@ -1130,6 +1443,10 @@ int mrq_sync_commits(mrq_engine *e, uint64_t *committed_out, uint8_t *role_out, 
   if (!e) return MRQ_E_INVAL;
   CK(e, cudaSetDevice(e->device));
   if (e->G == 0) return MRQ_OK;
+  {
+    int rw = ensure_wide(e, false);
+    if (rw) return rw;
+  }
   if (committed_out) {
     CK(e, cudaMemcpyAsync(committed_out, e->s.committed, e->G * 8, cudaMemcpyDeviceToHost, e->stream));
     // a full read rebases the compact drain: the next mrq_sync_commit_deltas counts from these values
@@ -1149,19 +1466,25 @@ int mrq_sync_commits(mrq_engine *e, uint64_t *committed_out, uint8_t *role_out, 
 int mrq_sync_out(mrq_engine *e, uint32_t *out_words) {
   if (!e || !out_words) return MRQ_E_INVAL;
   CK(e, cudaSetDevice(e->device));
-  if (e->G) CK(e, cudaMemcpyAsync(out_words, e->s.out, e->G * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (e->G) CK(e, cudaMemcpyAsync(out_words, e->last_out ? e->last_out : e->s.out, e->G * 4, cudaMemcpyDeviceToHost, e->stream));
   CK(e, cudaStreamSynchronize(e->stream));
   return MRQ_OK;
 }
 
 int mrq_sync_commit_deltas(mrq_engine *e, uint8_t *delta_out) {
   if (!e || !delta_out) return MRQ_E_INVAL;
+  int r0 = MRQ_OK;
   CK(e, cudaSetDevice(e->device));
   if (e->G == 0) return MRQ_OK;
-  commit_delta_kernel<<<nblocks(e->G), 256, 0, e->stream>>>(e->s.committed, e->commit_prev, e->delta, e->G);
+  {
+    int rw = ensure_wide(e, false);
+    if (rw) return rw;
+  }
+  if ((r0 = ensure_scratch(e, e->gs))) return r0;  // (e->delta holds the last mode-4 tick's own advances)
+  commit_delta_kernel<<<nblocks(e->G), 256, 0, e->stream>>>(e->s.committed, e->commit_prev, (uint8_t *)e->scratch, e->G);
   CK(e, cudaGetLastError());
   e->launches++;
-  CK(e, cudaMemcpyAsync(delta_out, e->delta, e->G, cudaMemcpyDeviceToHost, e->stream));
+  CK(e, cudaMemcpyAsync(delta_out, e->scratch, e->G, cudaMemcpyDeviceToHost, e->stream));
   CK(e, cudaStreamSynchronize(e->stream));
   return MRQ_OK;
 }
@@ -1171,12 +1494,47 @@ int mrq_drain_commit_deltas(mrq_engine *e, uint8_t *delta_out_pinned) {
   CK(e, cudaSetDevice(e->device));
   if (!e->drain_done) CK(e, cudaEventCreateWithFlags(&e->drain_done, cudaEventDisableTiming));
   if (e->G) {
-    commit_delta_kernel<<<nblocks(e->G), 256, 0, e->stream>>>(e->s.committed, e->commit_prev, e->delta, e->G);
+    int rw = ensure_wide(e, false);
+    if (rw) return rw;
+    if ((rw = ensure_scratch(e, e->gs))) return rw;
+    commit_delta_kernel<<<nblocks(e->G), 256, 0, e->stream>>>(e->s.committed, e->commit_prev, (uint8_t *)e->scratch, e->G);
     CK(e, cudaGetLastError());
     e->launches++;
-    CK(e, cudaMemcpyAsync(delta_out_pinned, e->delta, e->G, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaMemcpyAsync(delta_out_pinned, e->scratch, e->G, cudaMemcpyDeviceToHost, e->stream));
   }
   CK(e, cudaEventRecord(e->drain_done, e->stream));
+  return MRQ_OK;
+}
+
+// Mode 4: the tick kernels write every group's commit advance of THAT tick (1 B, 255 = "read the index in full") next to
+// the out word, so the per-tick drain is a plain copy of the last tick's bytes — no extra kernel, no extra pass.
+int mrq_drain_tick_deltas(mrq_engine *e, uint8_t *delta_out_pinned) {
+  if (!e || !delta_out_pinned) return MRQ_E_INVAL;
+  if (!e->last_delta) return fail(e, MRQ_E_STATE, "mrq_drain_tick_deltas: the last tick was not a mode-4 tick on a byte frame");
+  CK(e, cudaSetDevice(e->device));
+  if (!e->drain_done) CK(e, cudaEventCreateWithFlags(&e->drain_done, cudaEventDisableTiming));
+  if (e->G) CK(e, cudaMemcpyAsync(delta_out_pinned, e->last_delta, e->G, cudaMemcpyDeviceToHost, e->stream));
+  CK(e, cudaEventRecord(e->drain_done, e->stream));
+  return MRQ_OK;
+}
+
+// The outputs of the tick that consumed inbox slot `slot` in the last mrq_tick_many of mode 4 (each tick of such a
+// sequence writes its out words and commit advances to its slot's own buffers).  Blocking; NULL skips a column.
+int mrq_sync_slot_outputs(mrq_engine *e, uint32_t slot, uint32_t *out_words, uint8_t *delta_out) {
+  int r = check_slot(e, slot);
+  if (r) return r;
+  if (slot >= e->out_slot.size() || !e->out_slot[slot] || !e->delta_slot[slot])
+    return fail(e, MRQ_E_STATE, "slot %u was not part of a mode-4 mrq_tick_many sequence", slot);
+  CK(e, cudaSetDevice(e->device));
+  if (e->G && out_words) CK(e, cudaMemcpyAsync(out_words, e->out_slot[slot], e->G * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (e->G && delta_out) CK(e, cudaMemcpyAsync(delta_out, e->delta_slot[slot], e->G, cudaMemcpyDeviceToHost, e->stream));
+  CK(e, cudaStreamSynchronize(e->stream));
+  return MRQ_OK;
+}
+
+int mrq_set_write_through(mrq_engine *e, int on) {
+  if (!e || on < 0 || on > 1) return MRQ_E_INVAL;
+  e->write_through = on;
   return MRQ_OK;
 }
 

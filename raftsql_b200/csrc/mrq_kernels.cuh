@@ -586,7 +586,7 @@ __device__ __forceinline__ void count_events(Counters *c, uint32_t ev) {
 // ---- the general per-group tick: every message through the full state machine (a3–a16) ------------------
 static constexpr int kTickThreads = 128;
 template <int R>
-__device__ __forceinline__ uint32_t general_group_tick(const TickArgs &a, const uint64_t i) {
+__device__ __forceinline__ uint32_t general_group_tick(const TickArgs &a, const uint64_t i, const uint64_t tick_no) {
   uint32_t ev = 0;
   {
     const bool has_inbox = a.in.type != nullptr;
@@ -610,7 +610,7 @@ __device__ __forceinline__ uint32_t general_group_tick(const TickArgs &a, const 
     g.elapsed = m.elapsed; g.rto = m.rto; g.hb = m.hb; g.votes = m.votes; g.strict = m.strict; g.ltok = m.ltok;
     g.out = 0; g.dirty = 0; g.ev = 0; g.lt_valid = false; g.last_term = 0; g.pending = false;
     g.lt_ptr = a.s.last_term + i;
-    g.seed = a.seed; g.gg = a.group_base + i; g.tick_no = *a.tick_cur;
+    g.seed = a.seed; g.gg = a.group_base + i; g.tick_no = tick_no;
     const uint64_t committed0 = g.committed;
     g.et = a.election_tick; g.ht = a.heartbeat_tick;
     // phase 2: the present messages' term / index
@@ -659,6 +659,11 @@ __device__ __forceinline__ uint32_t general_group_tick(const TickArgs &a, const 
     ev = g.ev;
   }
   return ev;
+}
+
+template <int R>
+__device__ __forceinline__ uint32_t general_group_tick(const TickArgs &a, const uint64_t i) {
+  return general_group_tick<R>(a, i, *a.tick_cur);
 }
 
 // ---- the tick, as two launches ------------------------------------------------------------------------------
@@ -981,7 +986,7 @@ __device__ __forceinline__ void fast_group_tick8(const TickArgs &a, const Inbox8
 // The general path on the byte form: write this group's decoded messages into its wide inbox slot (an escaped
 // sender keeps what the host's wide list scattered there), slide the window, then the unchanged general tick.
 template <int R>
-__device__ __forceinline__ uint32_t general_group_tick8(const TickArgs &a, const Inbox8 &b, const uint64_t i) {
+__device__ __forceinline__ uint32_t general_group_tick8(const TickArgs &a, const Inbox8 &b, const uint64_t i, const uint64_t tick_no) {
   const uint32_t self = meta_unpack(ld_state(a.s.meta + i)).self;
   const uint64_t bi = ld_state(b.base_index + i), bt = ld_state(b.base_term + i);
   uint32_t min_ack = MRQ_P8_NO_ACK;
@@ -1011,7 +1016,11 @@ __device__ __forceinline__ uint32_t general_group_tick8(const TickArgs &a, const
   if (a.in.prop) a.in.prop[i] = b.prop8 ? ld_stream_u8(b.prop8 + i) : 0u;
   const uint64_t nb = mrq_p8_next_base(bi, min_ack);
   if (nb != bi) st_state(b.base_index + i, nb);
-  return general_group_tick<R>(a, i);
+  return general_group_tick<R>(a, i, tick_no);
+}
+template <int R>
+__device__ __forceinline__ uint32_t general_group_tick8(const TickArgs &a, const Inbox8 &b, const uint64_t i) {
+  return general_group_tick8<R>(a, b, i, *a.tick_cur);
 }
 
 template <int R>
@@ -1141,6 +1150,498 @@ __global__ void __launch_bounds__(kTickThreads, (R <= 5 ? 6 : 5)) tick_general_k
   if (i < a.G) ev = general_group_tick<R>(a, i);
   if (__any_sync(0xFFFFFFFFu, ev != 0)) count_events(a.ctr, ev);
 }
+
+// ==== tick mode 4: the tick on COMPACT state + the byte inbox =====================================================
+// The wide layout moves 217 B per group-tick at R = 5, most of it 64-bit indices whose upper halves
+// never change.  In mode 4 every index-like column of a group is a 32-bit OFFSET from one per-group u64 base
+// `ibase[g]` that only the general path ever reads:
+//     c.commit[g]        committed  - ibase
+//     c.match[r][g]      Progress.Match[r] - ibase   (0 = "at or below ibase": the exact value stays in the wide column,
+//                         and since ibase <= committed such a match can neither win a quorum nor be told apart by one)
+//     c.match[self-1][g] lastIndex - ibase            (a leader's own Match IS lastIndex; followers keep theirs here too)
+//     c.win[g]           byte-inbox window base - ibase
+//     c.gate[g]          term_start - ibase, read only while the gate is still closed (flag bit CF_GATE_OPEN clear)
+//     c.flag[g]          CF_COMPACT (these columns, not the wide ones, are the truth for last_index / committed / match /
+//                         window base), CF_TERM_OK (base_term == term: window messages carry the group's term),
+//                         CF_GATE_OPEN (leader, term_start <= committed: the commit gate can no longer block)
+// term, term_start, last_term never change on the fast path: they stay wide and are never read by it.  With the byte
+// inbox (R-1 sender bytes + 1 proposal byte) the steady-state tick reads 8 (meta) + 1 + 4 + 4 + 4R + R = 42 B and
+// writes 8 + 4 (out) + 1 (commit advance) + 4 + 4 + 4(R-1) + 3 = 40 B per group at R = 5: 82 B instead of 217.
+// One thread owns FOUR adjacent groups: every column access is one 128-bit (u32 x 4) or 256-bit (u64 x 4) load or
+// store, which also cuts the instruction count per group-tick to a quarter of the scalar kernels'.
+// Exactness: a group whose values do not fit (2^31 entries from its base), whose tick needs the role machinery, or
+// whose frame holds anything but in-window acks / its leader's heartbeat is handed to the general path, which
+// materialises the wide columns, runs the unchanged general tick on them, and re-compacts.
+enum : uint32_t { CF_COMPACT = 1u, CF_TERM_OK = 2u, CF_GATE_OPEN = 4u };
+enum : uint32_t { CD_META = 1u, CD_COMMIT = 2u, CD_WIN = 4u, CD_MATCH0 = 1u << 8 };
+#ifndef MRQ_HOST_EMULATION
+static constexpr uint32_t kCompactSpan = 0x7FFFFFFFu;  // offsets stay below 2^31: sums of two never wrap
+#else
+static uint32_t kCompactSpan = 0x7FFFFFFFu;  // (the host test lowers it to drive groups through the re-base path)
+#endif
+
+struct CompactView {
+  uint8_t *flag;     // [gs]
+  uint32_t *commit;  // [gs]
+  uint32_t *win;     // [gs]
+  uint32_t *gate;    // [gs]
+  uint32_t *iblo;    // [gs] low word of ibase (fused gather only)
+  uint32_t *match;   // [R][gs]
+  uint64_t *ibase;   // [gs]
+};
+
+template <int R>
+struct CGroup {  // one group's compact state, in registers
+  uint64_t meta;
+  uint32_t commit, win;
+  uint32_t m[R];
+};
+
+// One tick of one group on compact state.  Returns true (and leaves `g` untouched) when the group needs the general
+// path.  `wb[j]`: the frame's byte of compact row j (R-1 rows), `nprop`: the proposal byte.  Mirrors fast_group_tick8
+// line for line, in offset space.
+template <int R>
+__device__ __forceinline__ bool compact_step(CGroup<R> &g, const uint32_t flag, const uint32_t (&wb)[R > 1 ? R - 1 : 1],
+                                             const uint32_t nprop, const uint32_t *gate_ptr, const uint32_t et, const uint32_t ht,
+                                             uint32_t &out, uint32_t &adv, uint32_t &dirty) {
+  out = 0;
+  adv = 0;
+  dirty = 0;
+  if (!(flag & CF_COMPACT)) return true;
+  Meta m = meta_unpack(g.meta);
+  // the frame's bytes by sender slot
+  uint32_t kind[R], pay[R];
+  bool any_ack = false, any_hb = false, other = false;
+  uint32_t min_ack = MRQ_P8_NO_ACK;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    kind[r] = 0;
+    pay[r] = 0;
+    const uint32_t row = mrq_p8_row((uint32_t)r, m.self, (uint32_t)R);
+    if (row >= (uint32_t)R - 1u) continue;  // the group's own slot
+    uint32_t w = 0;
+#pragma unroll
+    for (int j = 0; j < R - 1; ++j)
+      if ((uint32_t)j == row) w = wb[j];
+    kind[r] = w & 3u;
+    pay[r] = (w >> 2) & 63u;
+    if (kind[r] == 1u) {
+      any_ack = true;
+      min_ack = pay[r] < min_ack ? pay[r] : min_ack;
+    } else if (kind[r] == 3u) {
+      any_hb = true;
+    } else if (kind[r] == 2u && (pay[r] <= 2u || pay[r] == 63u)) {
+      other = true;  // heartbeat-resp, vote-resp, or escaped to the wide list: the general path's business
+    } else {
+      kind[r] = 0;  // no message
+    }
+  }
+  if (other) return true;
+  uint32_t li = 0;  // lastIndex offset: the group's own match slot
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    if ((uint32_t)(r + 1) == m.self) li = g.m[r];
+  CGroup<R> n = g;
+  if (m.role == MRQ_ROLE_LEADER) {
+    if (m.strict || !m.ltok || any_hb) return true;
+    if (any_ack && !(flag & CF_TERM_OK)) return true;
+    if (li + nprop > kCompactSpan) return true;  // time to re-base
+    bool changed = false;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (kind[r] == 1u) {
+        const uint32_t mx = g.win + pay[r];
+        if (mx > li) return true;  // ack beyond lastIndex: upstream's strict path
+        if (n.m[r] < mx) {         // Progress.maybeUpdate
+          n.m[r] = mx;
+          dirty |= CD_MATCH0 << r;
+          changed = true;
+        }
+      }
+    if (nprop) {  // appendEntry: lastTerm already equals Term (ltok), self Match = lastIndex
+      li += nprop;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if ((uint32_t)(r + 1) == m.self) {
+          n.m[r] = li;
+          dirty |= CD_MATCH0 << r;
+        }
+      out |= MRQ_OUT_BCAST_APPEND;
+      changed = true;
+    }
+    if (changed) {  // maybeCommit, once (see Group::flushCommit for why once is exact)
+      uint32_t d[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) d[r] = max(n.m[r], n.commit) - n.commit;
+      const uint32_t q = quorum_index32<R>(d);
+      const uint32_t mci = n.commit + q;
+      if (q != 0u && mci <= li) {
+        bool open = (flag & CF_GATE_OPEN) != 0u;
+        if (!open) open = mci >= ld_stream_u32(gate_ptr);
+        if (open) {
+          adv = q;
+          n.commit = mci;
+          dirty |= CD_COMMIT;
+          out |= MRQ_OUT_COMMIT_ADVANCED | MRQ_OUT_BCAST_APPEND;
+        }
+      }
+    }
+    ++m.hb;  // tickHeartbeat
+    ++m.elapsed;
+    if (m.elapsed >= et) m.elapsed = 0;
+    if (m.hb >= ht) {
+      m.hb = 0;
+      out |= MRQ_OUT_BCAST_HEARTBEAT;
+    }
+  } else if (m.role == MRQ_ROLE_FOLLOWER) {
+    if (nprop != 0u || any_ack) return true;
+    if (any_hb && !(flag & CF_TERM_OK)) return true;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (kind[r] == 3u && ((uint32_t)(r + 1) != m.lead || g.win + pay[r] > li)) return true;
+    if ((any_hb ? 1u : m.elapsed + 1u) >= m.rto) return true;  // the election timer would fire: campaign() is general
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (kind[r] == 3u) {  // stepFollower MsgHeartbeat: electionElapsed = 0, lead = From, commitTo, reply
+        const uint32_t mx = g.win + pay[r];
+        if (n.commit < mx) {
+          adv += mx - n.commit;
+          n.commit = mx;
+          dirty |= CD_COMMIT;
+          out |= MRQ_OUT_COMMIT_ADVANCED;
+        }
+        out |= 1u << (MRQ_OUT_ACK_REPLY_SHIFT + r);
+      }
+    m.elapsed = any_hb ? 1u : m.elapsed + 1u;
+  } else {
+    return true;
+  }
+  // the window slides for whoever decodes the frame
+  if (min_ack < MRQ_P8_NO_ACK && min_ack > MRQ_P8_SLACK) {
+    n.win = g.win + (min_ack - MRQ_P8_SLACK);
+    dirty |= CD_WIN;
+  }
+  n.meta = meta_pack(m);
+  if (n.meta != g.meta) dirty |= CD_META;
+  g = n;
+  return false;
+}
+
+// compact -> wide for one group: the wide columns become exact copies (flag untouched)
+__device__ __forceinline__ void materialise_group(const StateView &s, const CompactView &c, uint64_t *base_index, uint64_t gs, uint32_t R,
+                                                  const uint64_t i) {
+  if (!(c.flag[i] & CF_COMPACT)) return;
+  const Meta m = meta_unpack(s.meta[i]);
+  const uint64_t ib = c.ibase[i];
+  s.committed[i] = ib + c.commit[i];
+  base_index[i] = ib + c.win[i];
+  if (m.self >= 1 && m.self <= R) s.last_index[i] = ib + c.match[(uint64_t)(m.self - 1u) * gs + i];
+  if (m.role == MRQ_ROLE_LEADER) {
+    for (uint32_t r = 0; r < R; ++r) {
+      const uint32_t v = c.match[(uint64_t)r * gs + i];
+      if (v != 0u) s.match[(uint64_t)r * gs + i] = ib + v;
+    }
+  }
+}
+
+// wide -> compact for one group (after the general path, an import, or a new window base): picks a fresh ibase just
+// below min(committed, window base) and writes the offsets; a group that does not fit stays wide (flag 0)
+__device__ __forceinline__ void compact_group(const StateView &s, const CompactView &c, const uint64_t *base_index,
+                                              const uint64_t *base_term, uint64_t gs, uint32_t R, const uint64_t i) {
+  const Meta m = meta_unpack(s.meta[i]);
+  const uint64_t li = s.last_index[i], cm = s.committed[i], wb = base_index[i], gate = s.term_start[i];
+  const uint64_t lo = cm < wb ? cm : wb;
+  const uint64_t ib = lo ? lo - 1u : 0u;
+  bool fits = m.self >= 1 && m.self <= R && !m.strict && cm <= li && li - ib <= (uint64_t)kCompactSpan &&
+              wb - ib <= (uint64_t)kCompactSpan;
+  const bool leader = m.role == MRQ_ROLE_LEADER;
+  if (fits && leader) fits = s.match[(uint64_t)(m.self - 1u) * gs + i] == li;  // a leader's own Match is lastIndex
+  if (!fits) {
+    c.flag[i] = 0;
+    return;
+  }
+  c.ibase[i] = ib;
+  c.iblo[i] = (uint32_t)ib;
+  c.commit[i] = (uint32_t)(cm - ib);
+  c.win[i] = (uint32_t)(wb - ib);
+  for (uint32_t r = 0; r < R; ++r) {
+    uint32_t v = 0;
+    if ((uint32_t)(r + 1) == m.self) {
+      v = (uint32_t)(li - ib);
+    } else if (leader) {
+      const uint64_t mv = s.match[(uint64_t)r * gs + i];
+      v = mv > ib ? (uint32_t)(mv - ib) : 0u;  // mv <= lastIndex (not strict), so the offset fits
+    }
+    c.match[(uint64_t)r * gs + i] = v;
+  }
+  uint32_t go = 0xFFFFFFFFu;  // closed for good (not a leader)
+  if (leader) go = gate > ib ? (gate - ib > 0xFFFFFFFEull ? 0xFFFFFFFFu : (uint32_t)(gate - ib)) : 0u;
+  c.gate[i] = go;
+  c.flag[i] = (uint8_t)(CF_COMPACT | (base_term[i] == s.term[i] ? CF_TERM_OK : 0u) | ((leader && gate <= cm) ? CF_GATE_OPEN : 0u));
+}
+
+// One tick of a mode-4 launch: where its frame is, and where its per-tick outputs go.
+struct TickDesc {
+  const uint8_t *word8;  // [R-1][gs] the byte frame (in the slot's staging buffer)
+  const uint8_t *prop8;  // [gs] proposal bytes, or nullptr
+  InboxView in;          // the slot's wide inbox: escaped messages were scattered there; the general path decodes into it
+  uint32_t *out;         // [gs] this tick's out words
+  uint8_t *delta;        // [gs] this tick's commit advances, saturating at 255 ("read the index in full")
+};
+struct Tick4Args {
+  TickArgs t;  // t.in and t.s.out are per tick (TickDesc)
+  CompactView c;
+  uint64_t *base_index;  // the wide window base (general path only)
+  const uint64_t *base_term;
+  TickDesc d0;            // nticks == 1: the descriptor rides in the kernel arguments
+  const TickDesc *descs;  // nticks > 1: a table in device memory
+  uint32_t nticks;
+  uint32_t write_through;  // nticks > 1: 1 = the state columns are written after every tick, 0 = after the last one
+  unsigned long long *slow_list64;  // (first general tick << 32) | group
+};
+
+// The general path of mode 4 for one group, from tick t0 of the launch to its last tick.
+template <int R>
+__device__ __forceinline__ uint32_t slow_group_ticks_c(const Tick4Args &A, const uint64_t i, const uint32_t t0) {
+  const TickArgs &a0 = A.t;
+  materialise_group(a0.s, A.c, A.base_index, a0.gs, (uint32_t)R, i);
+  uint32_t ev = 0;
+  const uint64_t tick0 = *a0.tick_cur;
+  for (uint32_t t = t0; t < A.nticks; ++t) {
+    const TickDesc d = A.descs ? A.descs[t] : A.d0;
+    TickArgs a = a0;
+    a.in = d.in;
+    a.s.out = d.out;
+    const uint64_t c0 = a.s.committed[i];
+    const Inbox8 b{d.word8, d.prop8, A.base_index, A.base_term};
+    ev |= general_group_tick8<R>(a, b, i, tick0 + t);
+    const uint64_t adv = a.s.committed[i] - c0;
+    d.delta[i] = (uint8_t)(adv > 255u ? 255u : adv);
+  }
+  compact_group(a0.s, A.c, A.base_index, A.base_term, a0.gs, (uint32_t)R, i);
+  return ev;
+}
+
+#ifndef MRQ_HOST_EMULATION
+// 128-bit / 256-bit column accesses with the L2 residency policy of the scalar kernels
+struct u32x4 {
+  uint32_t v[4];
+};
+__device__ __forceinline__ u32x4 ld_v4u32_p(const uint32_t *p, uint64_t pol) {
+  u32x4 r;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3])
+               : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ void st_v4u32_p(uint32_t *p, const u32x4 &r, uint64_t pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(r.v[0]), "r"(r.v[1]),
+               "r"(r.v[2]), "r"(r.v[3]), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void ld_v2u64_p(const uint64_t *p, uint64_t pol, uint64_t &a, uint64_t &b) {
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(a), "=l"(b) : "l"(p), "l"(pol));
+}
+__device__ __forceinline__ void st_v2u64_p(uint64_t *p, uint64_t a, uint64_t b, uint64_t pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.u64 [%0], {%1, %2}, %3;" ::"l"(p), "l"(a), "l"(b), "l"(pol) : "memory");
+}
+
+static constexpr int kQuadThreads = 128;  // x 4 groups per thread = 512 groups per CTA
+
+template <int R>
+__global__ void __launch_bounds__(kQuadThreads, (R <= 5 ? 4 : 3)) tick_fast4_kernel(const Tick4Args A) {
+  const TickArgs &a = A.t;
+  pdl_launch_dependents();
+  const uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+  const bool active = i0 < a.gs;       // the whole quad lies inside the padded row (gs is a multiple of 128)
+  const uint64_t i = active ? i0 : 0;  // inactive lanes shadow quad 0: they load, never store
+  const uint64_t pol_stream = l2_policy(a.l2_policy ? 1u : 0u);
+  const uint64_t pol_keep = l2_policy(a.l2_policy ? 2u : 0u);
+  pdl_wait();
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.tick_next = *a.tick_cur + A.nticks;
+  // ---- the quad's state: one wave of independent 128-bit loads ---------------------------------------------------
+  CGroup<R> g[4];
+  uint32_t flag[4];
+  {
+    const uint32_t fw = ld_stream_u32_p(reinterpret_cast<const uint32_t *>(A.c.flag + i), pol_keep);
+    ld_v2u64_p(a.s.meta + i, pol_keep, g[0].meta, g[1].meta);
+    ld_v2u64_p(a.s.meta + i + 2, pol_keep, g[2].meta, g[3].meta);
+    const u32x4 cm = ld_v4u32_p(A.c.commit + i, pol_keep);
+    const u32x4 wn = ld_v4u32_p(A.c.win + i, pol_keep);
+    u32x4 mv[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) mv[r] = ld_v4u32_p(A.c.match + (uint64_t)r * a.gs + i, pol_keep);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      flag[k] = (fw >> (8 * k)) & 0xFFu;
+      g[k].commit = cm.v[k];
+      g[k].win = wn.v[k];
+#pragma unroll
+      for (int r = 0; r < R; ++r) g[k].m[r] = mv[r].v[k];
+    }
+  }
+  uint32_t stopped = 0;  // bit k: group k is not this kernel's (padding, or handed to the general path at an earlier tick)
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (!active || i0 + k >= a.G) stopped |= 1u << k;
+  const bool gather = a.world > 1;
+  u32x4 iblo{};
+  if (gather) iblo = ld_v4u32_p(A.c.iblo + i, pol_keep);
+  uint32_t acc_dirty = 0, ncommit = 0;
+  // the first tick's frame; every later frame is loaded one tick ahead of its use
+  TickDesc d = A.descs ? A.descs[0] : A.d0;
+  uint32_t wb[R > 1 ? R - 1 : 1], pb;
+#pragma unroll
+  for (int j = 0; j < R - 1; ++j) wb[j] = ld_stream_u32_p(reinterpret_cast<const uint32_t *>(d.word8 + (uint64_t)j * a.gs + i), pol_stream);
+  if (R == 1) wb[0] = 0;
+  pb = d.prop8 ? ld_stream_u32_p(reinterpret_cast<const uint32_t *>(d.prop8 + i), pol_stream) : 0u;
+  for (uint32_t t = 0; t < A.nticks; ++t) {
+    uint32_t nwb[R > 1 ? R - 1 : 1], npb = 0;
+    TickDesc dn = d;
+    if (t + 1 < A.nticks) {  // prefetch the next tick's frame while this one is computed
+      dn = A.descs[t + 1];
+#pragma unroll
+      for (int j = 0; j < R - 1; ++j)
+        nwb[j] = ld_stream_u32_p(reinterpret_cast<const uint32_t *>(dn.word8 + (uint64_t)j * a.gs + i), pol_stream);
+      npb = dn.prop8 ? ld_stream_u32_p(reinterpret_cast<const uint32_t *>(dn.prop8 + i), pol_stream) : 0u;
+    }
+    if (R == 1) nwb[0] = 0;
+    u32x4 outw{};
+    uint32_t dw = 0, newly = 0, tdirty = 0;
+    u32x4 lo_old{};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      lo_old.v[k] = iblo.v[k] + g[k].commit;
+      if (stopped & (1u << k)) continue;
+      uint32_t wk[R > 1 ? R - 1 : 1];
+#pragma unroll
+      for (int j = 0; j < (R > 1 ? R - 1 : 1); ++j) wk[j] = (wb[j] >> (8 * k)) & 0xFFu;
+      uint32_t o, adv, dirty;
+      const bool slow = compact_step<R>(g[k], flag[k], wk, (pb >> (8 * k)) & 0xFFu, A.c.gate + i + k, a.election_tick,
+                                        a.heartbeat_tick, o, adv, dirty);
+      if (slow) {
+        newly |= 1u << k;
+      } else {
+        outw.v[k] = o;
+        dw |= (adv > 255u ? 255u : adv) << (8 * k);
+        tdirty |= dirty;
+        ncommit += adv != 0u;
+      }
+    }
+    if (__any_sync(0xFFFFFFFFu, newly != 0u)) {  // hand those groups (from this tick on) to the general kernel
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool s = (newly >> k) & 1u;
+        const unsigned smask = __ballot_sync(0xFFFFFFFFu, s);
+        if (smask != 0) {
+          const unsigned lane = threadIdx.x & 31u;
+          unsigned base = 0;
+          if (lane == 0) base = atomicAdd(a.slow_count, (unsigned)__popc(smask));
+          base = __shfl_sync(0xFFFFFFFFu, base, 0);
+          if (s) A.slow_list64[base + __popc(smask & ((1u << lane) - 1u))] = ((unsigned long long)t << 32) | (unsigned long long)(i0 + k);
+        }
+      }
+      stopped |= newly;
+    }
+    acc_dirty |= tdirty;
+    // ---- this tick's outputs (a stopped group's words are rewritten by the general kernel, which runs afterwards) --
+    if (active) {
+      st_v4u32_p(d.out + i, outw, pol_stream);
+      st_state_u32_p(reinterpret_cast<uint32_t *>(d.delta + i), dw, pol_stream);
+      if (gather) {  // fused all-gather: low words of the quad's commit indices, one 16-byte store per peer
+        u32x4 lo;
+        bool wrap = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          lo.v[k] = iblo.v[k] + g[k].commit;
+          wrap = wrap || lo.v[k] < lo_old.v[k];
+        }
+        const uint64_t at = (uint64_t)a.rank * a.G + i;
+        const bool whole = i0 + 3 < a.G && (at & 3u) == 0u && stopped == 0u;
+#pragma unroll 1
+        for (uint32_t p = 0; p < a.world; ++p) {
+          if (whole) {
+            st_v4u32_p(a.peer_lo[p] + at, lo, pol_stream);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (!(stopped & (1u << k))) a.peer_lo[p][at + k] = lo.v[k];
+          }
+        }
+        if (a.gather_prime || wrap) {  // high words: only when they change (or when priming)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (!(stopped & (1u << k)) && (a.gather_prime || lo.v[k] < lo_old.v[k])) {
+              const uint32_t hi = (uint32_t)((A.c.ibase[i + k] + g[k].commit) >> 32);
+#pragma unroll 1
+              for (uint32_t p = 0; p < a.world; ++p) a.peer_hi[p][at + k] = hi;
+            }
+        }
+      }
+    }
+    // ---- state write-back: per warp, whole 16-byte quads (see fast_group_tick for why per warp) ---------------------
+    const bool last = t + 1 == A.nticks;
+    if (A.write_through || last) {
+      uint32_t wd = __reduce_or_sync(0xFFFFFFFFu, A.write_through ? tdirty : acc_dirty);
+      if (active && stopped != 0xFu) {
+        if (wd & CD_META) {
+          st_v2u64_p(a.s.meta + i, g[0].meta, g[1].meta, pol_keep);
+          st_v2u64_p(a.s.meta + i + 2, g[2].meta, g[3].meta, pol_keep);
+        }
+        if (wd & CD_COMMIT) st_v4u32_p(A.c.commit + i, u32x4{{g[0].commit, g[1].commit, g[2].commit, g[3].commit}}, pol_keep);
+        if (wd & CD_WIN) st_v4u32_p(A.c.win + i, u32x4{{g[0].win, g[1].win, g[2].win, g[3].win}}, pol_keep);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (wd & (CD_MATCH0 << r))
+            st_v4u32_p(A.c.match + (uint64_t)r * a.gs + i, u32x4{{g[0].m[r], g[1].m[r], g[2].m[r], g[3].m[r]}}, pol_keep);
+      }
+    }
+    d = dn;
+#pragma unroll
+    for (int j = 0; j < (R > 1 ? R - 1 : 1); ++j) wb[j] = nwb[j];
+    pb = npb;
+  }
+  // "commit advanced" events: one warp-reduced atomic
+  const unsigned tot = __reduce_add_sync(0xFFFFFFFFu, ncommit);
+  if (tot != 0 && (threadIdx.x & 31u) == 0)
+    atomicAdd(&a.ctr[blockIdx.x & (kCtrShards - 1)].commits_advanced, (unsigned long long)tot);
+}
+
+template <int R>
+__global__ void __launch_bounds__(kTickThreads, (R <= 5 ? 6 : 5)) tick_slow4_kernel(const Tick4Args A) {
+  const TickArgs &a = A.t;
+  pdl_launch_dependents();
+  pdl_wait();
+  const unsigned n = *a.slow_count;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.slow_count_next = 0;
+  const unsigned stride = gridDim.x * blockDim.x;
+  const unsigned rounds = (n + stride - 1) / stride;
+  unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  for (unsigned it = 0; it < rounds; ++it, k += stride) {
+    uint32_t ev = 0;
+    if (k < n) {
+      const unsigned long long e = A.slow_list64[k];
+      ev = slow_group_ticks_c<R>(A, (uint64_t)(e & 0xFFFFFFFFull), (uint32_t)(e >> 32));
+    }
+    if (__any_sync(0xFFFFFFFFu, ev != 0)) count_events(a.ctr, ev);
+  }
+}
+
+// whole-engine passes between the two representations (import / export / a new window base / a mode switch)
+__global__ void __launch_bounds__(256) materialise_all_kernel(StateView s, CompactView c, uint64_t *base_index, uint64_t gs, uint64_t G,
+                                                               uint32_t R, int clear_flags) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G) return;
+  materialise_group(s, c, base_index, gs, R, i);
+  if (clear_flags) c.flag[i] = 0;
+}
+__global__ void __launch_bounds__(256) compact_all_kernel(StateView s, CompactView c, const uint64_t *base_index,
+                                                           const uint64_t *base_term, uint64_t gs, uint64_t G, uint32_t R) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G) return;
+  compact_group(s, c, base_index, base_term, gs, R, i);
+}
+#endif  // !MRQ_HOST_EMULATION
 
 // ---- K3: the standalone quorum kernel (a15–a16) ------------------------------------------------------------
 // Reads 8R+16 bytes per group (match[R], committed, term_start); writes committed where it moves.

@@ -216,6 +216,9 @@ class Engine:
     def set_tick_mode(self, mode: int):
         self._ck(self.L.mrq_set_tick_mode(self.h, mode))
 
+    def set_write_through(self, on: int):
+        self._ck(self.L.mrq_set_write_through(self.h, on))
+
     def quorum_commit(self):
         self._ck(self.L.mrq_quorum_commit(self.h))
 
@@ -252,6 +255,20 @@ class Engine:
         d = np.zeros(self.G, np.uint8)
         self._ck(self.L.mrq_sync_commit_deltas(self.h, _p(d, F.u8p)))
         return d
+
+    def sync_tick_deltas(self) -> np.ndarray:
+        """mode 4: the commit advances of the last tick, as the tick kernels wrote them (1 B per group)"""
+        d = np.zeros(self.G, np.uint8)
+        self._ck(self.L.mrq_drain_tick_deltas(self.h, _p(d, F.u8p)))
+        self._ck(self.L.mrq_drain_wait(self.h))
+        self.synchronize()
+        return d
+
+    def sync_slot_outputs(self, slot: int):
+        """mode 4, after tick_many: (out words, commit advances) of the tick that consumed `slot`"""
+        o, d = np.zeros(self.G, np.uint32), np.zeros(self.G, np.uint8)
+        self._ck(self.L.mrq_sync_slot_outputs(self.h, slot, _p(o, F.u32p), _p(d, F.u8p)))
+        return o, d
 
     def counters(self) -> dict:
         c = F.Counters()

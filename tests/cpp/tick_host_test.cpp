@@ -460,6 +460,260 @@ void run_soup(uint64_t G, uint32_t R, int T, uint64_t seed, int mode) {
   orc_destroy(o);
 }
 
+// ---- tick mode 4 on the host: compact state (32-bit offsets from a per-group base) + the byte inbox ------------------
+// What tick_fast4_kernel does per group — compact_step on registers loaded from the compact columns, the group handed
+// to slow_group_ticks_c (materialise -> general tick on the wide columns -> re-compact) from the first tick that needs
+// the general path — over K-tick batches (K = 1: the per-tick launch; K > 1: mrq_tick_many's single launch).  After
+// every batch the wide view (materialise_group over a scratch copy is not needed: it is idempotent) must equal the
+// oracle, every tick's out word and commit advance must equal the oracle's, and the window must match the frame builder's.
+struct CompactHost {
+  uint64_t gs;
+  uint32_t R;
+  std::vector<uint8_t> flag;
+  std::vector<uint32_t> commit, win, gate, iblo, match;
+  std::vector<uint64_t> ibase;
+  uint64_t fast_ticks = 0, slow_entries = 0;
+  CompactHost(uint64_t gs_, uint32_t R_) : gs(gs_), R(R_), flag(gs_, 0), commit(gs_, 0), win(gs_, 0), gate(gs_, 0), iblo(gs_, 0),
+                                            match(gs_ * R_, 0), ibase(gs_, 0) {}
+  CompactView view() { return CompactView{flag.data(), commit.data(), win.data(), gate.data(), iblo.data(), match.data(), ibase.data()}; }
+  void invalidate() { std::fill(flag.begin(), flag.end(), 0); }
+};
+
+struct HostSlot {  // one tick's frame, wide inbox slot (escapes + the general path's decode target) and outputs
+  std::vector<uint8_t> word, prop8, itype, delta;
+  std::vector<uint64_t> iterm, iindex, ilogterm, icommit;
+  std::vector<uint32_t> iprop, out;
+  HostSlot(uint64_t gs, uint32_t R)
+      : word(gs * (R > 1 ? R - 1 : 1), 0), prop8(gs, 0), itype(gs * R, 0xEE), delta(gs, 0xEE), iterm(gs * R, ~0ull), iindex(gs * R, ~0ull),
+        ilogterm(gs * R, ~0ull), icommit(gs * R, ~0ull), iprop(gs, 0xEEEEEEEEu), out(gs, 0xEEEEEEEEu) {}
+  TickDesc desc() {
+    return TickDesc{word.data(), prop8.data(), InboxView{itype.data(), iterm.data(), iindex.data(), ilogterm.data(), icommit.data(), iprop.data()},
+                    out.data(), delta.data()};
+  }
+};
+
+template <int R>
+void host_ticks_c(HostEngine &e, CompactHost &ch, const TickArgs &a, std::vector<TickDesc> &descs, uint64_t *base_index,
+                  const uint64_t *base_term) {
+  Tick4Args A{};
+  A.t = a;
+  A.c = ch.view();
+  A.base_index = base_index;
+  A.base_term = base_term;
+  A.nticks = (uint32_t)descs.size();
+  A.d0 = descs[0];
+  A.descs = descs.size() > 1 ? descs.data() : nullptr;
+  A.write_through = 1;
+  for (uint64_t i = 0; i < e.G; ++i) {
+    CGroup<R> g;
+    g.meta = e.meta[i];
+    g.commit = ch.commit[i];
+    g.win = ch.win[i];
+    for (int r = 0; r < R; ++r) g.m[r] = ch.match[(uint64_t)r * e.gs + i];
+    const uint32_t flag = ch.flag[i];
+    uint32_t t = 0;
+    bool slow = false;
+    for (; t < A.nticks; ++t) {
+      const TickDesc &d = descs[t];
+      uint32_t wb[R > 1 ? R - 1 : 1] = {0};
+      for (int j = 0; j < R - 1; ++j) wb[j] = d.word8[(uint64_t)j * e.gs + i];
+      uint32_t o, adv, dirty;
+      slow = compact_step<R>(g, flag, wb, d.prop8 ? d.prop8[i] : 0u, ch.gate.data() + i, a.election_tick, a.heartbeat_tick, o, adv, dirty);
+      if (slow) break;
+      d.out[i] = o;
+      d.delta[i] = (uint8_t)(adv > 255u ? 255u : adv);
+      ++ch.fast_ticks;
+    }
+    e.meta[i] = g.meta;  // the state as of the last tick the fast path handled
+    ch.commit[i] = g.commit;
+    ch.win[i] = g.win;
+    for (int r = 0; r < R; ++r) ch.match[(uint64_t)r * e.gs + i] = g.m[r];
+    if (slow) {
+      slow_group_ticks_c<R>(A, i, t);
+      ++ch.slow_entries;
+    }
+  }
+  e.tick_no[0] += A.nticks;
+}
+
+void dispatch_ticks_c(HostEngine &e, CompactHost &ch, const TickArgs &a, std::vector<TickDesc> &descs, uint64_t *bi, const uint64_t *bt) {
+  switch (e.R) {
+    case 1: host_ticks_c<1>(e, ch, a, descs, bi, bt); break;
+    case 2: host_ticks_c<2>(e, ch, a, descs, bi, bt); break;
+    case 3: host_ticks_c<3>(e, ch, a, descs, bi, bt); break;
+    case 4: host_ticks_c<4>(e, ch, a, descs, bi, bt); break;
+    case 5: host_ticks_c<5>(e, ch, a, descs, bi, bt); break;
+    case 6: host_ticks_c<6>(e, ch, a, descs, bi, bt); break;
+    case 7: host_ticks_c<7>(e, ch, a, descs, bi, bt); break;
+    case 8: host_ticks_c<8>(e, ch, a, descs, bi, bt); break;
+  }
+}
+
+// soup = false: the synthetic trace `cfg` (as run_case8);  soup = true: the adversarial message soup (as run_soup),
+// re-based every `rebase_every` ticks with the window sliding in between.
+void run_case_c(uint64_t G, uint32_t R, uint32_t cfg, int T, int rebase_every, uint32_t K, bool soup = false, uint64_t big = 0,
+                int also_rebase_at = -1) {
+  char where[112];
+  std::snprintf(where, sizeof where, "compact%s K=%u G=%llu R=%u %s=%u%s", soup ? " soup" : "", K, (unsigned long long)G, R, soup ? "seed" : "cfg", cfg,
+                big ? " near 2^31" : "");
+  const uint64_t seed = 0x5EEDC000ull + cfg * 131 + R;
+  const uint32_t et = soup ? 5 : 10;
+  orc_engine *o = orc_create(G, R, 0, et, 1, seed, 0);
+  HostEngine e(G, R);
+  CompactHost ch(e.gs, R);
+  OracleCols c(G, R);
+  c.load(o);
+  if (big) {  // steady-state leaders whose indices sit `big` above a multiple of 2^32: offsets run towards the re-base limit
+    uint64_t x = 7;
+    auto rnd = [&]() { return x = mrq_mix64(x + 0x9E3779B97F4A7C15ull); };
+    for (uint64_t g = 0; g < G; ++g) {
+      const uint32_t self = (uint32_t)(g % R) + 1;
+      c.self_id[g] = (uint8_t)self;
+      c.role[g] = MRQ_ROLE_LEADER;
+      c.lead[g] = (uint8_t)self;
+      c.term[g] = 1 + rnd() % 8;
+      c.vote[g] = self;
+      c.last_index[g] = big + rnd() % 40;
+      c.last_term[g] = c.term[g];
+      for (uint32_t r = 0; r < R; ++r) c.match[(uint64_t)r * G + g] = (g % 7 == 3 && r == (self % R)) ? 5 : c.last_index[g] - 1 - rnd() % 6;  // some far-behind followers
+      c.match[(uint64_t)(self - 1) * G + g] = c.last_index[g];
+      c.committed[g] = c.last_index[g] - 8;
+      c.term_start[g] = (g % 5 == 0) ? c.last_index[g] - 2 : c.committed[g] - 5;  // some gates still closed
+      c.rto[g] = 10;
+    }
+    orc_import(o, c.term.data(), c.vote.data(), c.committed.data(), c.last_index.data(), c.last_term.data(), c.term_start.data(),
+               c.match.data(), c.role.data(), c.lead.data(), c.self_id.data(), nullptr, nullptr, nullptr, c.rto.data());
+    c.load(o);
+  }
+  import_from_oracle(e, c);
+  const mrq_trace_params p = preset(soup ? 3 : cfg);
+  std::vector<uint8_t> type(G * R);
+  std::vector<uint64_t> term(G * R), index(G * R), logterm(G * R), commit(G * R);
+  std::vector<uint32_t> prop(G);
+  std::vector<uint64_t> dev_base(e.gs, 0), enc_base(G, 0), base_term(e.gs, 0);
+  std::vector<HostSlot> slots;
+  for (uint32_t k = 0; k < K; ++k) slots.emplace_back(e.gs, R);
+  std::vector<std::vector<uint32_t>> want_out(K, std::vector<uint32_t>(G));
+  std::vector<std::vector<uint64_t>> want_commit(K + 1, std::vector<uint64_t>(G));
+  static const uint8_t kTypes[] = {0, 0, 0, 3, 4, 4, 4, 4, 4, 5, 6, 6, 6, 8, 8, 9, 4 | 0x80, 6 | 0x80, 3 | 0x80};
+  uint64_t x = seed * 77 + 5;
+  auto rnd = [&]() { return x = mrq_mix64(x + 0x9E3779B97F4A7C15ull); };
+  auto around = [](uint64_t v, int64_t d) -> uint64_t { return (d < 0 && v < (uint64_t)(-d)) ? 0 : v + (uint64_t)d; };
+  uint64_t n_bytes = 0, n_escapes = 0;
+  bool bad = false;
+  for (int t0 = 0; t0 < T && !bad; t0 += (int)K) {
+    if (t0 % rebase_every == 0 || t0 == also_rebase_at) {  // mrq_set_packed_base: the wide columns are made exact, the compact copies die
+      const TickArgs a0 = e.args(0, seed, et, 1, true);
+      for (uint64_t g = 0; g < G; ++g) materialise_group(a0.s, ch.view(), dev_base.data(), e.gs, R, g);
+      ch.invalidate();
+      c.load(o);
+      for (uint64_t g = 0; g < G; ++g) {
+        const uint64_t back = soup ? 6 : 30;
+        enc_base[g] = dev_base[g] = c.last_index[g] > back ? c.last_index[g] - back : 0;
+        base_term[g] = c.term[g];
+      }
+    }
+    c.load(o);
+    want_commit[0] = c.committed;
+    for (uint32_t k = 0; k < K; ++k) {  // K ticks of the trace: frames built as the oracle advances
+      HostSlot &s = slots[k];
+      if (!soup) {
+        orc_gen_trace(o, &p, (uint64_t)(t0 + k), type.data(), term.data(), index.data(), logterm.data(), commit.data(), prop.data(), 1);
+      } else {
+        for (uint64_t g = 0; g < G; ++g) {
+          for (uint32_t r = 0; r < R; ++r) {
+            const uint64_t w = (uint64_t)r * G + g;
+            const uint8_t ty = kTypes[rnd() % sizeof kTypes];
+            type[w] = ty;
+            if ((ty & 0x0F) == 0) {
+              term[w] = index[w] = logterm[w] = commit[w] = 0;
+              continue;
+            }
+            const uint64_t u = rnd() % 64;
+            term[w] = around(c.term[g], u == 0 ? -2 : u == 1 ? -1 : u == 2 ? 1 : u == 3 ? 2 : 0);
+            index[w] = around(c.last_index[g], (int64_t)(rnd() % 7) - 4);
+            logterm[w] = around(c.last_term[g], (int64_t)(rnd() % 3) - 1);
+            commit[w] = c.committed[g] + rnd() % 4;
+            if ((ty & 0x0F) == 3) {
+              if (commit[w] > index[w]) commit[w] = index[w];
+              if (index[w] == 0) logterm[w] = 0;
+              if (logterm[w] > term[w]) logterm[w] = term[w];
+            }
+          }
+          static const uint32_t kProps[] = {0, 0, 1, 4};
+          prop[g] = kProps[rnd() % 4];
+        }
+      }
+      std::fill(s.itype.begin(), s.itype.end(), 0xEE);  // poison: whatever the tick reads must come from the bytes / the escapes
+      for (uint64_t g = 0; g < G; ++g) {
+        const uint32_t self = c.self_id[g];
+        uint32_t min_ack = MRQ_P8_NO_ACK;
+        for (uint32_t r = 0; r < R; ++r) {
+          const uint32_t row = mrq_p8_row(r, self, R);
+          if (row >= R - 1u) continue;
+          const uint64_t w = (uint64_t)r * G + g, d = (uint64_t)r * e.gs + g;
+          const uint8_t b = mrq_p8_encode(type[w], term[w], index[w], commit[w], enc_base[g], base_term[g]);
+          s.word[(uint64_t)row * e.gs + g] = b;
+          if (b == MRQ_P8_ESCAPE) {  // scatter_msgs_kernel: the wide message rides in the slot
+            s.itype[d] = type[w];
+            s.iterm[d] = term[w];
+            s.iindex[d] = index[w];
+            s.ilogterm[d] = logterm[w];
+            s.icommit[d] = commit[w];
+            ++n_escapes;
+          } else if (b != 0) {
+            ++n_bytes;
+            if ((b & 3u) == 1u && (uint32_t)(b >> 2) < min_ack) min_ack = b >> 2;
+          }
+        }
+        enc_base[g] = mrq_p8_next_base(enc_base[g], min_ack);
+        s.prop8[g] = (uint8_t)prop[g];
+      }
+      orc_tick(o, type.data(), term.data(), index.data(), logterm.data(), commit.data(), prop.data(), 1);
+      c.load(o);
+      want_out[k] = c.out;
+      want_commit[k + 1] = c.committed;
+    }
+    const TickArgs a = e.args(0, seed, et, 1, true);
+    std::vector<TickDesc> descs;
+    for (uint32_t k = 0; k < K; ++k) descs.push_back(slots[k].desc());
+    dispatch_ticks_c(e, ch, a, descs, dev_base.data(), base_term.data());
+    // the wide view of the result (what every reading entry point of the library does first)
+    for (uint64_t g = 0; g < G; ++g) materialise_group(a.s, ch.view(), dev_base.data(), e.gs, R, g);
+    for (uint32_t k = 0; k < K && !bad; ++k)
+      for (uint64_t g = 0; g < G; ++g) {
+        const uint64_t adv = want_commit[k + 1][g] - want_commit[k][g];
+        if (slots[k].out[g] != want_out[k][g] || slots[k].delta[g] != (adv > 255 ? 255 : adv)) {
+          std::printf("FAIL %s tick %d group %llu: out %08x want %08x, commit advance %u want %llu\n", where, t0 + (int)k, (unsigned long long)g,
+                      slots[k].out[g], want_out[k][g], slots[k].delta[g], (unsigned long long)adv);
+          ++failures;
+          bad = true;
+          break;
+        }
+      }
+    for (uint64_t g = 0; g < G && !bad; ++g)
+      if (dev_base[g] != enc_base[g]) {
+        std::printf("FAIL %s tick %d group %llu: device window %llu, frame builder's %llu\n", where, t0, (unsigned long long)g,
+                    (unsigned long long)dev_base[g], (unsigned long long)enc_base[g]);
+        ++failures;
+        bad = true;
+      }
+    std::memcpy(e.out.data(), slots[K - 1].out.data(), e.gs * 4);  // compare() reads the last tick's out words from e.out
+    if (!bad && !compare(e, c, where, (uint64_t)(t0 + K - 1))) bad = true;
+  }
+  uint64_t n_compact = 0;
+  for (uint64_t g = 0; g < G; ++g) n_compact += ch.flag[g] & CF_COMPACT;
+  std::printf("  %-44s %4d ticks  bytes %8llu  escapes %7llu  fast group-ticks %8llu  general entries %7llu  compact now %llu/%llu\n", where, T,
+              (unsigned long long)n_bytes, (unsigned long long)n_escapes, (unsigned long long)ch.fast_ticks, (unsigned long long)ch.slow_entries,
+              (unsigned long long)n_compact, (unsigned long long)G);
+  if (!bad && !soup && R > 1 && ch.fast_ticks < (uint64_t)T * G / 4) {
+    std::printf("FAIL %s: the compact fast path handled too little (%llu of %llu group-ticks)\n", where, (unsigned long long)ch.fast_ticks,
+                (unsigned long long)((uint64_t)T * G));
+    ++failures;
+  }
+  orc_destroy(o);
+}
+
 // The fused all-gather of the tick (multi-GPU mode 1): every group's commit index is stored into every rank's gather
 // buffer as a low word every tick and a high word only when it changes (or when priming).  Steady-state leaders
 // whose commit indices sit just below a multiple of 2^32, so that they CROSS it during the run: after every tick the
@@ -593,8 +847,10 @@ int main(int argc, char **) {
   if (const char *soak = std::getenv("MRQ_SOAK")) {  // MRQ_SOAK=<n>: n more seeds of every soup, every R, every mode
     const int n = std::atoi(soak);
     for (int s = 0; s < n && failures == 0; ++s)
-      for (uint32_t R = 1; R <= 8; ++R)
+      for (uint32_t R = 1; R <= 8; ++R) {
         for (int mode : {0, 1, 8}) run_soup(96, R, 300, 1000 + 37 * (uint64_t)s + R, mode);
+        run_case_c(96, R, 1000 + 37 * (uint32_t)s + R, 300, 8, 1 + (uint32_t)s % 4, true);
+      }
     std::printf(failures ? "tick_host_test soak: %d failure(s)\n" : "tick_host_test soak: ok\n", failures);
     return failures ? 1 : 0;
   }
@@ -633,6 +889,19 @@ int main(int argc, char **) {
   run_case8(400 / k, 5, 2, 300, 40, -1, true);
   run_case8(400 / k, 3, 6, 300, 30, -1, true);    // follower / heartbeat heavy: the follower fast path on bytes
   run_case8(400 / k, 5, 3, 400, 1000, 60, true);  // steady state: nearly everything stays on the byte fast path
+  // tick mode 4: compact state + the byte inbox; K = 1 (per-tick launch) and K > 1 (mrq_tick_many's single launch)
+  for (uint32_t R : {1u, 2u, 3u, 4u, 5u, 6u, 7u, 8u}) run_case_c(300 / k, R, 5, 224, 32, R % 2 ? 1 : 4);
+  run_case_c(400 / k, 5, 2, 300, 60, 1);           // elections from a cold start
+  run_case_c(400 / k, 5, 2, 300, 60, 5);
+  run_case_c(400 / k, 3, 6, 300, 30, 3);           // follower / heartbeat heavy: the follower fast path
+  run_case_c(400 / k, 5, 3, 400, 1000, 1, false, 0, 60);  // steady state: one base once the leaders stand, then the window slides by itself
+  run_case_c(400 / k, 5, 3, 400, 1000, 8, false, 0, 64);
+  run_case_c(300 / k, 5, 3, 300, 1000, 4, false, (1ull << 33) + 100);          // 64-bit bases, far-behind followers, closed gates
+  kCompactSpan = 120;  // a tiny offset span: every group outgrows it every few dozen ticks and is re-based by the general path
+  run_case_c(200 / k, 5, 3, 240, 1000, 4, false, (1ull << 31) - 300);
+  run_case_c(200 / k, 3, 5, 240, 40, 1);
+  kCompactSpan = 0x7FFFFFFFu;
+  for (uint32_t R : {2u, 3u, 5u, 8u}) run_case_c(120 / k + 8, R, 300 + R, 240, 8, R == 5 ? 4 : 1, true);  // message soups
   std::printf(failures ? "tick_host_test: %d failure(s)\n" : "tick_host_test: ok\n", failures);
   return failures ? 1 : 0;
 }

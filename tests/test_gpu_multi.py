@@ -26,7 +26,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, G_total, R, cfg, T, seed, mode, q):
+def _worker(rank, world, port, G_total, R, cfg, T, seed, mode, q, tick_mode=0):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -42,9 +42,26 @@ def _worker(rank, world, port, G_total, R, cfg, T, seed, mode, q):
         eng = Engine(G, R, seed=seed, group_base=base, device=rank)
         multi.attach(eng, dist, mode)
         p = preset_trace(cfg)
-        for t in range(T):
-            eng.gen_trace(p, t)
-            eng.tick()
+        if tick_mode == 4:  # compact state + byte frames: the fused gather rides the quad kernel's 16-byte peer stores
+            from raftsql_b200.packed import Pack8
+
+            eng.set_tick_mode(4)
+            pk = None
+            for t in range(T):
+                eng.gen_trace(p, t)
+                ib = eng.read_inbox()
+                if t % 25 == 0:
+                    s = eng.export_state()
+                    base = np.where(s["last_index"] > 30, s["last_index"] - np.uint64(30), 0).astype(np.uint64)
+                    pk = Pack8(s["self_id"], base, s["term"], R)
+                    eng.set_packed_base(pk.base_index, pk.base_term)
+                word, prop8, wide = pk.frame(ib)
+                eng.post_inbox_packed(word, prop8, wide, slot=1)
+                eng.tick(1)
+        else:
+            for t in range(T):
+                eng.gen_trace(p, t)
+                eng.tick()
         eng.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
@@ -61,8 +78,8 @@ def _worker(rank, world, port, G_total, R, cfg, T, seed, mode, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["nccl", "fused"])
-def test_sharded_engines_gather_equals_single_engine(mode):
+@pytest.mark.parametrize("mode,tick_mode", [("nccl", 0), ("fused", 0), ("fused", 4), ("nccl", 4)])
+def test_sharded_engines_gather_equals_single_engine(mode, tick_mode):
     if _ngpu() < 2:
         pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
     import torch.multiprocessing as mp
@@ -75,7 +92,7 @@ def test_sharded_engines_gather_equals_single_engine(mode):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, G_total, R, cfg, T, seed, mode, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, G_total, R, cfg, T, seed, mode, q, tick_mode)) for r in range(world)]
     for p in procs:
         p.start()
     gathered, oks = q.get(timeout=600)
