@@ -66,18 +66,30 @@ def steady_state(G: int, Rr: int, group_base: int, seed: int) -> dict:
     return st
 
 
-def tick_bytes_per_group(Rr: int, inbox: str = "wide") -> dict:
-    """Algorithmic HBM bytes of one fused tick per group on the steady-state trace: every
-    follower acks, proposals arrive on 3 of 4 ticks.  inbox = "bytes": the tick on the byte form (tick mode 3) reads
-    R-1 sender bytes + 1 proposal byte + the two base words instead of the wide inbox columns, and slides the base."""
-    state = 8 * 5 + 8 * Rr  # meta,term,last_index,committed,term_start + match
+def tick_bytes_per_group(Rr: int, inbox: str = "compact", ticks_per_launch: int = 1, write_through: bool = True) -> dict:
+    """Algorithmic HBM bytes of one tick per group on the steady-state trace: every follower acks,
+    proposals arrive on 3 of 4 ticks.
+      "wide":    tick mode 0 — 64-bit state columns + the wide inbox columns;
+      "bytes":   tick mode 3 — the byte inbox (R-1 sender bytes + 1 proposal byte + two base words) on 64-bit state;
+      "compact": tick mode 4 — the byte inbox on compact state (32-bit offsets).  With ticks_per_launch = K > 1 the state
+                 is read once per K ticks (registers carry it from tick to tick) and, unless write_through, also written
+                 once per K ticks; every tick still reads its frame and writes its out word + commit-advance byte."""
+    if inbox == "wide":
+        read = 8 * 5 + 8 * Rr + Rr + 4 + 16 * (Rr - 1)  # meta,term,last_index,committed,term_start + match + types + prop + ack term/index
+        write = 8 + 4 + 8 * (Rr - 1) + 8 + 12           # meta, out, acked match, committed, (last_index + self match) x 3/4
+        return {"read": read, "write": write, "total": read + write}
     if inbox == "bytes":
-        read = state + (Rr - 1) + 1 + 16
-        write = 8 + 4 + 8 * (Rr - 1) + 8 + 12 + 8  # ... + the slid window base
-    else:
-        read = state + Rr + 4 + 16 * (Rr - 1)      # + types + prop + ack term/index
-        write = 8 + 4 + 8 * (Rr - 1) + 8 + 12      # meta, out, acked match, committed, (last_index + self match) x 3/4
-    return {"read": read, "write": write, "total": read + write}
+        read = 8 * 5 + 8 * Rr + (Rr - 1) + 1 + 16
+        write = 8 + 4 + 8 * (Rr - 1) + 8 + 12 + 8
+        return {"read": read, "write": write, "total": read + write}
+    K = max(1, ticks_per_launch)
+    state_read = 1 + 8 + 4 + 4 + 4 * Rr            # flag, meta, commit, window, match[R] (last row = lastIndex)
+    state_write = 8 + 4 + 4 + 4 * (Rr - 1) + 3     # meta, commit, window, acked match rows, lastIndex row x 3/4
+    frame = (Rr - 1) + 1                           # sender bytes + proposal byte
+    outputs = 4 + 1                                # out word + commit-advance byte
+    read = frame + state_read / K
+    write = outputs + (state_write if (write_through or K == 1) else state_write / K)
+    return {"read": round(read, 2), "write": round(write, 2), "total": round(read + write, 2)}
 
 
 def quorum_bytes_per_group(Rr: int) -> int:
@@ -121,11 +133,31 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
-def ncu_traffic(kernel: str):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu summary (bench.py never
-    runs under a profiler itself)."""
+def sass_instruction_count(kernel_substr: str):
+    """Static SASS instruction count of a kernel in the loaded libmrq.so (None if cuobjdump is unavailable)."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[kernel]
+        lib = os.path.join(ROOT, "raftsql_b200", "libmrq.so")
+        txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, timeout=120).stdout
+        for part in txt.split("Function : ")[1:]:
+            name = part.split("\n", 1)[0].strip()
+            if kernel_substr in name:
+                return sum(1 for ln in part.splitlines() if ln.lstrip().startswith("/*") and ln.rstrip().endswith(";") and "*/" in ln[:14])
+    except Exception:
+        pass
+    return None
+
+
+def ncu_traffic(kernel: str, mangled_substr: str | None = None):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu summary (bench.py never runs
+    under a profiler itself).  The figure is REFUSED (None) when the summary was captured from a binary whose SASS
+    instruction count for this kernel differs from the library loaded now: a capture of another kernel version is
+    not a measurement of this one."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))[kernel]
+        if mangled_substr and t.get("sass_instructions") is not None:
+            now = sass_instruction_count(mangled_substr)
+            if now is not None and int(t["sass_instructions"]) != now:
+                return None
         return int(t["dram_read_bytes"]) + int(t["dram_write_bytes"])
     except Exception:
         return None
@@ -218,6 +250,7 @@ def run_ours(args):
     import torch
 
     from raftsql_b200 import Engine, _ffi, preset_trace
+    from raftsql_b200.packed import Pack8
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -238,11 +271,12 @@ def run_ours(args):
     base = rank * G
     K, W = args.steps, max(3, args.warmup)
     nslots = min(K + W, MAX_SLOTS)
+    reps = max(1, int(os.environ.get("MRQ_BENCH_REPS", "5")))
+    inbox = args.inbox
+    mode = {"compact": 4, "bytes": 3, "wide": 0}[inbox]
+    fast = os.environ.get("MRQ_BENCH_FAST") == "1"  # profiling runs (ncu): kernels only, no CPU legs
 
     eng = Engine(G, R, seed=SEED, group_base=base, device=dev, inbox_slots=nslots)
-    eng.set_graph_mode({"off": 0, "on": 1, "auto": 2}[args.graph])
-    if args.tick_mode is not None:
-        eng.set_tick_mode(args.tick_mode)
     if args.l2 is not None:
         eng.set_l2_policy(args.l2)
     st0 = steady_state(G, R, base, SEED)
@@ -254,36 +288,43 @@ def run_ours(args):
 
         multi.attach(eng, dist, args.gather)
 
-    # dry run: generate the trace tick by tick on the device (each tick's acks depend on that tick's state),
-    # one inbox slot per tick; then rewind the state so the timed run replays exactly these inputs.
+    # dry run (tick mode 0): generate the trace tick by tick on the device (each tick's acks depend on that tick's
+    # state), one inbox slot per tick; then rewind the state so the timed runs replay exactly these inputs.
+    e2e_steps = min(K, nslots)
+    commits_after = None
     for t in range(nslots):
         eng.gen_trace(p, t, slot=t)
         eng.tick(t)
+        if t == e2e_steps - 1:
+            commits_after = eng.sync_commits().copy()  # what the first e2e_steps ticks commit (checks the e2e leg)
     eng.synchronize()
-    e2e_slots = min(4, nslots)
-    host_ib = [eng.read_inbox(s) for s in range(e2e_slots)]  # every rank runs the e2e leg on its own shard
+    want_e2e = not fast
+    host_ib = [eng.read_inbox(s) for s in range(e2e_steps if want_e2e else 0)]  # every rank runs the e2e leg on its own shard
 
-    # --inbox bytes (experiment, tick mode 3): the same trace re-encoded as byte frames (include/mrq_packed8.h), one
-    # per slot, resident in HBM; the tick kernels read the bytes themselves (no wide inbox, no unpack pass)
-    bytes_mode = getattr(args, "inbox", "wide") == "bytes"
+    # byte frames (include/mrq_packed8.h) of the same trace, one per slot, resident in HBM: tick modes 3 / 4 read the
+    # bytes themselves (no wide inbox, no unpack pass)
     base0 = (st0["last_index"] - np.uint64(40)).astype(np.uint64)
-    if bytes_mode:
-        from raftsql_b200.packed import Pack8
-
+    n_escapes = 0
+    if mode >= 3:
         pk = Pack8(st0["self_id"], base0, st0["term"], R)
-        frames = [pk.frame(eng.read_inbox(t)) for t in range(nslots)]  # in tick order: the window only moves forward
-        eng.set_tick_mode(3)
-        for t, (w8, p8, wide8) in enumerate(frames):
+        eng.set_tick_mode(mode)
+        for t in range(nslots):  # in tick order: the window only moves forward
+            ib = host_ib[t] if t < len(host_ib) else eng.read_inbox(t)
+            w8, p8, wide8 = pk.frame(ib)
+            n_escapes += len(wide8)
             eng.post_inbox_packed(w8, p8, wide8, slot=t, keep=True)
-        n_escapes = sum(len(f[2]) for f in frames)
 
-    def rewind():
+    def rewind(tick_mode, graph, write_through=1):
+        eng.set_tick_mode(0)
         eng.import_state(st0)
         eng.tick_count = 0
-        if bytes_mode:
+        eng.set_tick_mode(tick_mode)
+        eng.set_graph_mode(graph)
+        eng.set_write_through(write_through)
+        if tick_mode >= 3:
             eng.set_packed_base(base0, st0["term"])
-
-    rewind()
+        if world > 1 and args.gather == "fused":
+            eng.comm_set_mode(1)  # the rewind changed committed[] behind the peers' backs: republish the high words
 
     def barrier():
         if dist is not None:
@@ -291,62 +332,68 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def run_ticks(n, first_slot):
-        if os.environ.get("MRQ_BENCH_PYLOOP") == "1":  # development switch: one mrq_tick call per tick
-            for k in range(n):
-                eng.tick((first_slot + k) % nslots)
-            return
-        # n ticks in one C call; the launch sequence for a slot list is a CUDA graph after its first use
+        # n ticks in one C call: mode 4 runs them in one launch pair; modes 0-3 replay a CUDA graph (small shards) or
+        # issue the per-tick launches
         eng.tick_many([(first_slot + k) % nslots for k in range(n)])
 
-    # rehearsal (untimed): the exact warm-up and timed sequences once, so that the timed region below
-    # replays captured graphs; then rewind the state again
-    run_ticks(W, 0)
-    run_ticks(K, W)
-    eng.synchronize()
-    barrier()
-    rewind()
-    if world > 1 and args.gather == "fused":
-        # the rewind changed committed[] behind the peers' backs: have the next tick republish the high words
-        eng.comm_set_mode(1)
-        barrier()
-    # warm-up, then the timed region
-    run_ticks(W, 0)
-    eng.synchronize()
-    c0 = eng.counters()
-    sampler = ClockSampler(dev)
-    sampler.start()
-    barrier()
-    eng.timer_start()
-    run_ticks(K, W)
-    ms = eng.timer_stop()
-    barrier()
-    c1 = eng.counters()
-    launches = c1["kernel_launches"] - c0["kernel_launches"]  # our kernels launched inside the timed region
-    if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
-        dist.all_reduce(lt)
-        launches_all = int(lt.item())
-    else:
-        launches_all = launches
-    # keep the GPU busy ~2 s more so the clock sampler sees it under this load even for short K.  The
-    # repeat count is derived from the max-over-ranks time, so EVERY rank issues the same number of ticks
-    # (a per-tick collective would deadlock on a time-based loop).
-    reps = max(4, min(40000, int(2.0 / max(1e-6, 8 * ms / K * 1e-3))))  # ~2 s: several nvidia-smi samples
-    for _ in range(reps):
-        run_ticks(8, 0)
-    eng.synchronize()
-    clocks = sampler.finish()
-    launches_timed = launches_all
+    def timed_leg(tick_mode, graph, write_through=1, nreps=reps, sample_clocks=False):
+        """`nreps` repetitions of: rewind, W warm-up ticks, then EXACTLY K ticks between barrier + synchronize, CUDA
+        events on the engine's stream, max over ranks.  Returns (median ms for K ticks, all reps, launches, clocks)."""
+        out_ms, launches, clocks = [], 0, None
+        rewind(tick_mode, graph, write_through)  # rehearsal (untimed): graphs captured, descriptor tables built
+        run_ticks(W, 0)
+        run_ticks(K, W)
+        eng.synchronize()
+        sampler = None
+        if sample_clocks:
+            sampler = ClockSampler(dev)
+            sampler.start()
+        for _ in range(nreps):
+            rewind(tick_mode, graph, write_through)
+            barrier()
+            run_ticks(W, 0)
+            eng.synchronize()
+            c0 = eng.counters()
+            barrier()
+            eng.timer_start()
+            run_ticks(K, W)
+            ms = eng.timer_stop()
+            barrier()
+            launches = eng.counters()["kernel_launches"] - c0["kernel_launches"]
+            if dist is not None:
+                t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            out_ms.append(ms)
+        med = float(np.median(out_ms))
+        if sampler is not None:
+            # keep the GPU under this load ~2 s more so the sampler sees it (same count on every rank)
+            n_more = max(4, min(40000, int(2.0 / max(1e-6, 8 * med / K * 1e-3))))
+            for _ in range(n_more):
+                run_ticks(8, 0)
+            eng.synchronize()
+            clocks = sampler.finish()
+        if dist is not None:
+            lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
+            dist.all_reduce(lt)
+            launches = int(lt.item())
+        return med, out_ms, launches, clocks
+
+    graph = {"off": 0, "on": 1, "auto": 2}[args.graph]
+    wt = 0 if args.write_back == "end" else 1
+    ms, ms_reps, launches_timed, clocks = timed_leg(mode, graph, wt, sample_clocks=True)
     ticks_per_s = K / (ms / 1e3)
     peak, peak_src = measured_peak_gbs()
+    batched = mode == 4 and graph != 0
 
-    # ---- roofline of the dominant kernel (the fused tick) -------------------------------------------
-    tb = tick_bytes_per_group(R, "bytes" if bytes_mode else "wide")
-    tick_kernel_ms = ms / K  # back-to-back launches on one stream: event time / K is the per-launch duration
+    # ---- roofline of the dominant kernel ---------------------------------------------------------------
+    tb = tick_bytes_per_group(R, inbox, K if batched else 1, bool(wt))
+    tick_kernel_ms = ms / K  # back-to-back on one stream: event time / K is the per-tick share of the launch
     tick_gbs = tb["total"] * G / (tick_kernel_ms * 1e-3) / 1e9
+    kernel_name = {4: "tick_fast4_kernel<5> (+ tick_slow4_kernel<5> over the groups that left the fast path)",
+                   3: "tick_fast8_kernel<5> (+ tick_slow8_kernel<5>)",
+                   0: "tick_fast_kernel<5> (+ tick_slow_kernel<5> over the slow list, empty on this trace)"}[mode]
+    frames_mb = nslots * G * R / 1e6
     line = {
         "metric": "raft_ticks_per_sec_1Mx5", "value": ticks_per_s, "unit": "ticks/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None,
@@ -357,39 +404,60 @@ def run_ours(args):
                                   "all-gather of committed[] per tick, fused into the tick kernel as peer stores over NVLink"
                                   if args.gather == "fused" else "ncclAllGather(committed) per tick" if args.gather == "nccl"
                                   else "none in the timed region (--gather none: shards tick independently; SURVEY 8d config 4)"),
-                   "inbox": (f"byte form resident in HBM, one frame per slot, {n_escapes} escaped messages (tick mode 3)" if bytes_mode
-                             else "wide columns resident in HBM, one inbox slot per tick"),
-                   "l2": (f"{nslots} rotating byte frames ({nslots * G * R / 1e6:.0f} MB in all); the engine state "
-                          f"({(8 * 5 + 8 * R) * G / 1e6:.0f} MB) is re-used every tick by design and is L2-resident" if bytes_mode else
-                          f"inputs larger than L2: {nslots} rotating inbox slots, per-step footprint "
-                          f"{(tb['total'] * G) / 1e6:.0f} MB vs 126 MB L2")},
+                   "tick_mode": mode,
+                   "inbox": ({4: f"byte frames resident in HBM, one per slot, {n_escapes} escaped messages; compact state (tick mode 4)",
+                              3: f"byte frames resident in HBM, one per slot, {n_escapes} escaped messages; wide state (tick mode 3)",
+                              0: "wide columns resident in HBM, one inbox slot per tick (tick mode 0)"}[mode]),
+                   "launches": (f"one launch pair per {K} ticks (mrq_tick_many; state carried in registers, "
+                                f"{'written through every tick' if wt else 'written back after the last tick'})" if batched
+                                else "one launch pair per tick"),
+                   "timing": f"median of {reps} repetitions of [rewind, {W} warm-up ticks, {K} timed ticks]",
+                   "l2": ((f"inputs larger than L2: {nslots} rotating byte frames + per-slot out/advance buffers "
+                           f"({frames_mb + nslots * G * 5 / 1e6:.0f} MB) vs 126 MB L2; ") if mode >= 3 else
+                          (f"inputs larger than L2: {nslots} rotating inbox slots, per-step footprint "
+                           f"{(tb['total'] * G) / 1e6:.0f} MB vs 126 MB L2; ")) +
+                         "the engine state is re-used every tick by design and may stay L2-resident"},
+        "ms_per_step_reps": [round(x / K, 6) for x in ms_reps],
         "group_ticks_per_sec": ticks_per_s * groups_job,
-        "roofline": {"bound": "hbm",
-                     "kernel": ("tick_fast8_kernel<5> (+ tick_slow8_kernel<5>): the tick on the byte form, tick mode 3" if bytes_mode else
-                                "tick_fast_kernel<5> (+ tick_slow_kernel<5> over the slow list, empty on this trace)"),
+        "roofline": {"bound": "hbm", "kernel": kernel_name,
                      "achieved": tick_gbs, "peak": peak, "unit": "GB/s",
                      "frac": tick_gbs / peak,
-                     "traffic": ncu_traffic("tick_fast_kernel<5>") if world == 1 and not bytes_mode else None,
-                     "traffic_source": "profiles/r01_traffic.json (ncu --set full, cold cache, isolated launch)",
+                     "traffic": (ncu_traffic("tick_fast4_kernel<5>", "tick_fast4_kernelILi5") if world == 1 and mode == 4 and not batched
+                                 else None),
+                     "traffic_source": "profiles/r02_traffic.json (ncu --set full, cold cache, isolated per-tick launch)",
                      "peak_source": peak_src, "algorithmic_bytes_per_group": tb,
-                     "algorithmic_bytes_per_launch": tb["total"] * G},
+                     "algorithmic_bytes_per_launch": tb["total"] * G * (K if batched else 1)},
         "gpu_launches": launches_timed,
         "clocks": clocks,
     }
 
-    fast = os.environ.get("MRQ_BENCH_FAST") == "1"  # profiling runs (ncu): kernels only, no CPU legs
+    if rank == 0 and world == 1:
+        # the other ways to run the same K ticks, each [rewind, W, K] x 3 (median): what the batching and the layout buy
+        legs = {}
+        if mode == 4:
+            for name, (tm, gr, w_) in {"compact_per_tick_launches": (4, 0, 1), "compact_batched_write_through": (4, 2, 1),
+                                        "compact_batched_write_back_at_end": (4, 2, 0), "bytes_on_wide_state_mode3": (3, 0, 1),
+                                        "wide_inbox_mode0": (0, graph, 1)}.items():
+                m_, r_, l_, _ = timed_leg(tm, gr, w_, nreps=3)
+                ib_name = {4: "compact", 3: "bytes", 0: "wide"}[tm]
+                tbl = tick_bytes_per_group(R, ib_name, K if (tm == 4 and gr != 0) else 1, bool(w_))
+                gbs = tbl["total"] * G / (m_ / K * 1e-3) / 1e9
+                legs[name] = {"ticks_per_s": K / (m_ / 1e3), "us_per_tick": m_ / K * 1e3, "launches": l_,
+                              "bytes_per_group_tick": tbl["total"], "achieved_GBps": gbs, "frac": gbs / peak,
+                              "us_per_tick_reps": [round(x / K * 1e3, 2) for x in r_]}
+            rewind(mode, graph, wt)
+        line["variants"] = legs
+        line["roofline_quorum_kernel"] = bench_quorum_kernel(torch, eng, peak, K, W)
     if rank == 0 and world == 1 and fast:
-        line["roofline_quorum_kernel"] = bench_quorum_kernel(torch, eng, peak, K, W)
         line["e2e"] = None
-    elif rank == 0 and world == 1:
-        line["roofline_quorum_kernel"] = bench_quorum_kernel(torch, eng, peak, K, W)
-        line["e2e"] = bench_e2e(eng, st0, host_ib, K, W)
+    elif world == 1:
+        line["e2e"] = bench_e2e(eng, st0, base0, host_ib, commits_after, e2e_steps)
         # CPU baseline: the oracle port on this box's host cores, bounded sample
         try:
-            tps, nt, n, el, _ = cpu_reference_ticks(G_TOTAL, R, st0, host_ib, budget_s=12.0)
+            tps, nt, n, el, _ = cpu_reference_ticks(G_TOTAL, R, st0, host_ib[:4], budget_s=12.0)
             line["cpu_baseline"] = {"value": tps, "unit": "ticks/s", "cores": nt, "kind": "port",
                                     "sample": f"{n} full ticks over all {G_TOTAL} groups x {R} replicas in {el:.1f} s on {nt} threads"}
-            tps1, _, n1, el1, _ = cpu_reference_ticks(G_TOTAL, R, st0, host_ib, budget_s=3.0, nthreads=1)
+            tps1, _, n1, el1, _ = cpu_reference_ticks(G_TOTAL, R, st0, host_ib[:4], budget_s=3.0, nthreads=1)
             line["cpu_baseline"]["single_thread"] = {"value": tps1, "cores": 1, "sample": f"{n1} full ticks in {el1:.1f} s"}
         except Exception as ex:  # the baseline must never take the GPU numbers down with it
             line["cpu_baseline"] = {"value": None, "unit": "ticks/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
@@ -405,15 +473,11 @@ def run_ours(args):
             line["gather_check"] = bool(ok.item())
         else:
             line["gather_check"] = None
-        # end to end at N GPUs: every rank ships its shard's packed inbox over its own PCIe link each tick
-        e2e = bench_e2e(eng, st0, host_ib, K, W, dist=dist, torch=torch)
+        # end to end at N GPUs: every rank encodes and ships its shard's byte frames over its own PCIe link each tick
+        e2e = bench_e2e(eng, st0, base0, host_ib, commits_after, e2e_steps, dist=dist, torch=torch)
         if rank == 0:
             line["e2e"] = e2e
     eng.close()
-    if rank == 0 and world == 1 and not fast and isinstance(line.get("e2e"), dict) and os.environ.get("MRQ_BENCH_NO_E2E8") != "1":
-        # the byte form of the packed inbox, measured in a process of its own once everything above is final;
-        # it becomes the e2e figure only if it verified itself against the wide form and is faster
-        merge_packed8(line["e2e"], e2e8_from_child(K))
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:
@@ -464,18 +528,24 @@ def bench_quorum_kernel(torch, eng, peak, K, W):
             "cold": f"{len(sets)} distinct column sets ({quorum_bytes_per_group(R) * G / 1e6:.1f} MB each), L2 flushed before timing"}
 
 
-def bench_e2e(eng, st0, host_ib, K, W, dist=None, torch=None):
-    """The same tick through the C-ABI with HOST buffers: per step H2D of that tick's inbox, the tick, and a
-    D2H drain of the commit indices — all inside the timed region.  With `dist`, every rank runs its shard and
-    the elapsed time is the max over ranks (barrier on both sides)."""
+def bench_e2e(eng, st0, base0, host_ib, commits_ref, steps, dist=None, torch=None):
+    """The same ticks through the C-ABI with HOST buffers, everything on the clock: per step the host ENCODES that tick's
+    inbox into a byte frame (mrq_pack8, on the library's host thread pool — frame k+1 is built while tick k runs), the
+    frame goes H2D from pinned memory (copy stream), mrq_tick (tick mode 4), and the tick's commit advances come back
+    D2H (1 B per group) and are waited for before the step counts.  Every step ships a DIFFERENT tick of the trace.
+    With `dist`, every rank runs its shard and the elapsed time is the max over ranks (barrier on both sides).
+    The result is accepted only if the commit indices rebuilt from the drained advances equal `commits_ref` — what the
+    same ticks commit from the device-generated wide inbox in tick mode 0."""
     import ctypes as C
+    import queue
 
     from raftsql_b200 import _ffi as F
-    from raftsql_b200.packed import PinnedArray, pack_inbox
+    from raftsql_b200.packed import Pack8, PinnedArray
 
-    n = len(host_ib)
     G, Rr = eng.G, eng.R
-    steps = K
+    S = min(steps, len(host_ib))
+    L, h = eng.L, eng.h
+    NB = 4  # pinned frame buffers in flight: built / copying / ticking / draining
 
     def sync_all():
         if dist is not None:
@@ -488,203 +558,141 @@ def bench_e2e(eng, st0, host_ib, K, W, dist=None, torch=None):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # -- wide form (33 B per slot, pageable numpy arrays): the straightforward host path ----------------
-    def run_wide(nsteps, timed):
+    def rewind(tick_mode):
+        eng.set_tick_mode(0)
         eng.import_state(st0)
         eng.tick_count = 0
-        sync_all()
-        t0 = time.perf_counter()
-        for k in range(nsteps):
-            eng.post_inbox_dense(host_ib[k % n], slot=k % 2)
-            eng.tick(k % 2)
-            c = eng.sync_commits()
-        return max_over_ranks(time.perf_counter() - t0), c
+        eng.set_tick_mode(tick_mode)
+        if tick_mode >= 3:
+            eng.set_packed_base(base0, st0["term"])
+        return eng.sync_commits().copy()
 
-    run_wide(2, False)
-    el_w, commits_wide = run_wide(min(steps, n), True)
-    wide = {"value": min(steps, n) / el_w, "h2d_bytes_per_step": sum(a.nbytes for a in host_ib[0].values()),
+    # -- wide form (33 B per slot, pageable numpy arrays): the straightforward host path, for scale -------------
+    rewind(0)
+    sync_all()
+    nw = min(4, S)
+    t0 = time.perf_counter()
+    for k in range(nw):
+        eng.post_inbox_dense(host_ib[k], slot=k % 2)
+        eng.tick(k % 2)
+        eng.sync_commits()
+    el_w = max_over_ranks(time.perf_counter() - t0)
+    wide = {"value": nw / el_w, "h2d_bytes_per_step": sum(a.nbytes for a in host_ib[0].values()),
             "d2h_bytes_per_step": G * 8, "api": "mrq_post_inbox_dense + mrq_tick + mrq_sync_commits"}
 
-    # -- packed forms from pinned host memory, 1 B per group commit-advance drain ---------------------
-    # Per step: H2D of that tick's packed inbox (on the engine's copy stream), the tick, D2H of the
-    # commit advances, host waits for THAT step's result.  The post of tick k+1 is issued while tick k
-    # runs, so the PCIe copy — the bound of this path — overlaps the kernels and the drain.
-    from raftsql_b200.packed import pack_inbox16
-
-    L, h = eng.L, eng.h
+    bufs = [(PinnedArray((max(Rr - 1, 1), G), np.uint8), PinnedArray((G,), np.uint8)) for _ in range(NB)]
     delta = PinnedArray((G,), np.uint8)
     dptr = C.cast(delta.ptr, F.u8p)
-    results, pinned = {}, [delta]
-    for bits, packer, back in ((32, pack_inbox, 8192), (16, pack_inbox16, 1024)):
-        base_index = (st0["last_index"] - np.uint64(back)).astype(np.uint64)
-        base_term = st0["term"].copy()
-        views, h2d = [], 0
-        for ib in host_ib:  # the host's message builder would emit this form directly; encoding is not timed
-            w, p8, esc = packer(ib, base_index, base_term)
-            assert not esc, "steady-state trace should need no escapes"
-            pw, pp = PinnedArray(w.shape, w.dtype), PinnedArray((G,), np.uint8)
-            pw.array[:] = w
-            pp.array[:] = p8
-            pinned += [pw, pp]
-            v = F.InboxPacked()
-            v.word, v.prop_count8 = pw.ptr, C.cast(pp.ptr, F.u8p)
-            v.wide, v.n_wide, v.word_bits = None, 0, bits
-            views.append(v)
-            h2d = int(pw.nbytes + pp.nbytes)
 
-        def run_packed(nsteps, accumulate):
-            eng.import_state(st0)
-            eng.tick_count = 0
-            eng.set_packed_base(base_index, base_term)
-            base = eng.sync_commits().copy()  # a full read also rebases the delta drain
-            acc = np.zeros(G, np.uint64)
-            sync_all()
-            t0 = time.perf_counter()
-            rc = L.mrq_post_inbox_packed(h, 0, C.byref(views[0]))
-            for k in range(nsteps):
-                rc |= L.mrq_tick(h, k % 2)
-                rc |= L.mrq_drain_commit_deltas(h, dptr)
-                if k + 1 < nsteps:  # next tick's inbox starts copying underneath this tick
-                    rc |= L.mrq_post_inbox_packed(h, (k + 1) % 2, C.byref(views[(k + 1) % n]))
-                rc |= L.mrq_drain_wait(h)  # this step's result is on the host
-                assert rc == 0
-                if accumulate:  # reconstruct commit indices from the per-tick advances (checking run only)
-                    assert delta.array.max() < 255
-                    acc += delta.array
-            el = max_over_ranks(time.perf_counter() - t0)
-            eng.synchronize()
-            return el, base + acc
-
-        run_packed(3, False)
-        _, commits_check = run_packed(min(steps, n), True)
-        same = bool(np.array_equal(commits_check, commits_wide)) and bool(np.array_equal(commits_check, eng.sync_commits()))
-        el_p, _ = run_packed(steps, False)
-        ws = 1 if dist is None else dist.get_world_size()  # bytes are whole-job figures (all ranks)
-        results[bits] = {"value": steps / el_p, "h2d_bytes_per_step": h2d * ws, "d2h_bytes_per_step": int(delta.nbytes) * ws,
-                         "equals_wide_form": same, "h2d_GBps_per_gpu": h2d * steps / el_p / 1e9,
-                         "inputs": f"{n} distinct ticks of the trace, cycled over the {steps} steps (same bytes per step)"}
-    best = max(results, key=lambda b: results[b]["value"])
-    res = {"value": results[best]["value"], "unit": "ticks/s", "h2d_bytes_per_step": results[best]["h2d_bytes_per_step"],
-           "d2h_bytes_per_step": results[best]["d2h_bytes_per_step"], "steps": steps,
-           "api": f"mrq_post_inbox_packed (pinned, {best}-bit words, copy stream) + mrq_tick + "
-                  "mrq_drain_commit_deltas/mrq_drain_wait (1 B/group)",
-           "packed_equals_wide": all(r["equals_wide_form"] for r in results.values()),
-           "packed32": results[32], "packed16": results[16], "wide_form": wide}
-    for a in pinned:
-        a.free()
-    return res
-
-
-def run_e2e8_child(args):
-    """The end-to-end leg on the BYTE form of the packed inbox (include/mrq_packed8.h: R-1 sender bytes + 1
-    proposal byte per group, window sliding on the device), N = 1.  It runs in a process of its own, launched by
-    run_ours after the main numbers are final: this form's device kernel is the newest code in the library, and
-    a fault in it must not be able to touch them.  Prints one JSON object.
-
-    Every step ships a DIFFERENT tick of the trace (S distinct frames built in order, as a live host would: the
-    sliding window only ever moves forward), and the result is accepted only if the commit indices it produces
-    equal the ones the same S ticks produce from the device-generated wide inbox."""
-    import ctypes as C
-
-    from raftsql_b200 import Engine, preset_trace
-    from raftsql_b200 import _ffi as F
-    from raftsql_b200.packed import Pack8, PinnedArray
-
-    G, Rr = G_TOTAL, R
-    S = max(4, min(args.steps, 64))
-    eng = Engine(G, Rr, seed=SEED, group_base=0, device=int(os.environ.get("LOCAL_RANK", "0")), inbox_slots=2)
-    st0 = steady_state(G, Rr, 0, SEED)
-    eng.import_state(st0)
-    tick_mode = os.environ.get("MRQ_E2E8_TICK_MODE")  # "3": the tick reads the bytes itself, no unpack pass (experiment)
-    if tick_mode:
-        eng.set_tick_mode(int(tick_mode))
-    p = preset_trace(3)
-    base0 = (st0["last_index"] - np.uint64(40)).astype(np.uint64)
-    pk = Pack8(st0["self_id"], base0, st0["term"], Rr)
-    views, keep, h2d, escapes = [], [], 0, 0
-    for t in range(S):  # the trace, tick by tick (each tick's acks depend on that tick's state), framed as it goes
-        eng.gen_trace(p, t, slot=0)
-        ib = eng.read_inbox(0)
-        pw, pp = PinnedArray((Rr - 1, G), np.uint8), PinnedArray((G,), np.uint8)
-        _, _, wide = pk.frame(ib, word_out=pw.array, prop8_out=pp.array)
-        arr = (F.Msg * max(1, len(wide)))()
-        for i, (g, frm, ty, term, index, logterm, commit) in enumerate(wide):
+    def view_of(b, wide_msgs):
+        arr = (F.Msg * max(1, len(wide_msgs)))()
+        for i, (g, frm, ty, term, index, logterm, commit) in enumerate(wide_msgs):
             arr[i].group, arr[i].from_, arr[i].type = g, frm, ty
             arr[i].term, arr[i].index, arr[i].logterm, arr[i].commit = term, index, logterm, commit
         v = F.InboxPacked()
-        v.word, v.prop_count8 = pw.ptr, C.cast(pp.ptr, F.u8p)
-        v.wide, v.n_wide, v.word_bits = arr, len(wide), 8
-        views.append(v)
-        keep += [pw, pp, arr]
-        escapes += len(wide)
-        h2d = max(h2d, int(pw.nbytes + pp.nbytes + len(wide) * C.sizeof(F.Msg)))
-        eng.tick(0)
-    commits_ref = eng.sync_commits().copy()  # what these S ticks commit, from the wide device-generated inbox
+        v.word, v.prop_count8 = bufs[b][0].ptr, C.cast(bufs[b][1].ptr, F.u8p)
+        v.wide, v.n_wide, v.word_bits, v.reserved = arr, len(wide_msgs), 8, 0
+        return v, arr
 
-    L, h = eng.L, eng.h
-    delta = PinnedArray((G,), np.uint8)
-    dptr = C.cast(delta.ptr, F.u8p)
-
-    def run(nsteps, accumulate):
-        eng.import_state(st0)
-        eng.tick_count = 0
-        eng.set_packed_base(base0, st0["term"])
-        base = eng.sync_commits().copy()  # a full read also rebases the delta drain
+    def run(nsteps, accumulate, encode_on_clock=True, frames=None):
+        base = rewind(4)
         acc = np.zeros(G, np.uint64)
+        pk = Pack8(st0["self_id"], base0, st0["term"], Rr)
+        ready: queue.Queue = queue.Queue()
+        free = threading.Semaphore(NB)
+        pack_s = [0.0]
+        n_esc = [0]
+
+        def packer():  # the host's frame builder: one frame per tick, in posting order (the window only moves forward)
+            for k in range(nsteps):
+                free.acquire()
+                b = k % NB
+                t1 = time.perf_counter()
+                _, _, wide_msgs = pk.frame(host_ib[k % S], word_out=bufs[b][0].array[: max(Rr - 1, 0)], prop8_out=bufs[b][1].array)
+                pack_s[0] += time.perf_counter() - t1
+                n_esc[0] += len(wide_msgs)
+                ready.put(view_of(b, wide_msgs))
+
+        sync_all()
         t0 = time.perf_counter()
-        rc = L.mrq_post_inbox_packed(h, 0, C.byref(views[0]))
+        th = threading.Thread(target=packer, daemon=True)
+        th.start()
+        cur = ready.get()
+        rc = L.mrq_post_inbox_packed(h, 0, C.byref(cur[0]))
         for k in range(nsteps):
             rc |= L.mrq_tick(h, k % 2)
-            rc |= L.mrq_drain_commit_deltas(h, dptr)
-            if k + 1 < nsteps:  # next tick's frame starts copying underneath this tick
-                rc |= L.mrq_post_inbox_packed(h, (k + 1) % 2, C.byref(views[k + 1]))
+            rc |= L.mrq_drain_tick_deltas(h, dptr)
+            nxt = None
+            if k + 1 < nsteps:  # the next tick's frame: encoded underneath this tick, copied underneath it too
+                nxt = ready.get()
+                rc |= L.mrq_post_inbox_packed(h, (k + 1) % 2, C.byref(nxt[0]))
             rc |= L.mrq_drain_wait(h)  # this step's result is on the host
             if rc != 0:
                 raise RuntimeError("C-ABI call failed: " + (L.mrq_last_error(h) or b"?").decode())
+            free.release()  # tick k is done, so frame k's copy is too: its pinned buffer may be rebuilt
             if accumulate:
                 assert delta.array.max() < 255
                 acc += delta.array
-        el = time.perf_counter() - t0
+            cur = nxt
+        el = max_over_ranks(time.perf_counter() - t0)
+        th.join()
         eng.synchronize()
-        return el, base + acc
+        return el, base + acc, pack_s[0] / nsteps, n_esc[0]
 
     run(3, False)
-    _, commits = run(S, True)
+    _, commits, _, _ = run(S, True)
     same = bool(np.array_equal(commits, commits_ref)) and bool(np.array_equal(commits, eng.sync_commits()))
-    el, _ = run(S, False)
-    res = {"value": S / el, "unit": "ticks/s", "steps": S, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(delta.nbytes),
-           "equals_wide_form": same, "escapes": escapes, "h2d_GBps_per_gpu": h2d * S / el / 1e9,
-           "inputs": f"{S} distinct consecutive ticks of the trace, one per step",
-           "api": "mrq_pack8 frames (pinned, 8-bit form, copy stream) + mrq_post_inbox_packed + mrq_tick + "
-                  "mrq_drain_commit_deltas/mrq_drain_wait (1 B/group)", "tick_mode": int(tick_mode) if tick_mode else 0}
-    try:
-        eng.close()
-    finally:
-        print(json.dumps(res), flush=True)
+    el, _, pack_avg, n_esc = run(S, False)
+    ws = 1 if dist is None else dist.get_world_size()  # bytes are whole-job figures (all ranks)
+    h2d = (max(Rr - 1, 0) + 1) * G
+    res = {"value": S / el, "unit": "ticks/s", "h2d_bytes_per_step": h2d * ws, "d2h_bytes_per_step": G * ws, "steps": S,
+           "api": "mrq_pack8 (host encode, in the timed region) + mrq_post_inbox_packed (pinned, 8-bit form, copy stream) + "
+                  "mrq_tick (tick mode 4) + mrq_drain_tick_deltas/mrq_drain_wait (1 B/group)",
+           "encode_in_timed_region": True, "pack_us_per_tick": pack_avg * 1e6, "us_per_tick": el / S * 1e6,
+           "equals_wide_form": same, "escapes": n_esc, "h2d_GBps_per_gpu": h2d * S / el / 1e9,
+           "inputs": f"{S} distinct consecutive ticks of the trace, one per step (host wide inbox -> byte frame -> device)",
+           "wide_form": wide}
+    # the same loop with the frames already encoded (a transport that delivers byte frames): what the link + device do alone
+    pre = [(PinnedArray((max(Rr - 1, 1), G), np.uint8), PinnedArray((G,), np.uint8)) for _ in range(S)]
+    pk = Pack8(st0["self_id"], base0, st0["term"], Rr)
+    views = []
+    for k in range(S):
+        _, _, wm = pk.frame(host_ib[k], word_out=pre[k][0].array[: max(Rr - 1, 0)], prop8_out=pre[k][1].array)
+        v = F.InboxPacked()
+        v.word, v.prop_count8 = pre[k][0].ptr, C.cast(pre[k][1].ptr, F.u8p)
+        arr = (F.Msg * max(1, len(wm)))()
+        for i, (g, frm, ty, term, index, logterm, commit) in enumerate(wm):
+            arr[i].group, arr[i].from_, arr[i].type = g, frm, ty
+            arr[i].term, arr[i].index, arr[i].logterm, arr[i].commit = term, index, logterm, commit
+        v.wide, v.n_wide, v.word_bits, v.reserved = arr, len(wm), 8, 0
+        views.append((v, arr))
 
+    def run_pre(nsteps):
+        rewind(4)
+        sync_all()
+        t0 = time.perf_counter()
+        rc = L.mrq_post_inbox_packed(h, 0, C.byref(views[0][0]))
+        for k in range(nsteps):
+            rc |= L.mrq_tick(h, k % 2)
+            rc |= L.mrq_drain_tick_deltas(h, dptr)
+            if k + 1 < nsteps:
+                rc |= L.mrq_post_inbox_packed(h, (k + 1) % 2, C.byref(views[k + 1][0]))
+            rc |= L.mrq_drain_wait(h)
+            assert rc == 0
+        el_ = max_over_ranks(time.perf_counter() - t0)
+        eng.synchronize()
+        return el_
 
-def merge_packed8(e2e: dict, r8) -> None:
-    """Record the child's outcome under e2e['packed8']; adopt it as the e2e figure only if it verified itself
-    against the wide form and is faster.  Never raises: the main line stands whatever the child returned."""
-    try:
-        e2e["packed8"] = r8
-        if r8.get("equals_wide_form") is True and r8.get("value", 0) > e2e["value"]:
-            e2e.update({k: r8[k] for k in ("value", "h2d_bytes_per_step", "d2h_bytes_per_step", "steps", "api")})
-        if r8.get("equals_wide_form") is False:  # a decode that disagrees with the wide form is a bug: say so
-            e2e["packed_equals_wide"] = False
-    except Exception as ex:  # noqa: BLE001
-        e2e["packed8"] = {"error": f"{type(ex).__name__}: {ex}"}
-
-
-def e2e8_from_child(steps: int) -> dict:
-    try:
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--e2e8-child", "--steps", str(steps)],
-                           capture_output=True, text=True, timeout=300, cwd=ROOT)
-        if r.returncode != 0:
-            return {"error": f"exit {r.returncode}: {(r.stderr or r.stdout).strip()[-300:]}"}
-        return json.loads(r.stdout.strip().splitlines()[-1])
-    except Exception as ex:  # noqa: BLE001 — whatever happens there, the main line stands
-        return {"error": f"{type(ex).__name__}: {ex}"}
+    run_pre(3)
+    el_p = run_pre(S)
+    res["preencoded"] = {"value": S / el_p, "us_per_tick": el_p / S * 1e6, "h2d_GBps_per_gpu": h2d * S / el_p / 1e9,
+                         "encode_in_timed_region": False,
+                         "note": "frames encoded before the clock starts (a transport delivering byte frames): link + device only"}
+    for a_, b_ in bufs + pre:
+        a_.free()
+        b_.free()
+    delta.free()
+    return res
 
 
 def main():
@@ -696,23 +704,21 @@ def main():
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl", "none"],
                     help="N>1: how committed[] is all-gathered each tick (none: not at all — the scaling leg "
                          "without the collective in the timed region)")
-    ap.add_argument("--tick-mode", type=int, default=None, choices=[0, 2],
-                    help="0: fast + slow kernels, 2: single fused launch (default: the engine's)")
+    ap.add_argument("--write-back", default="every-tick", choices=["every-tick", "end"],
+                    help="tick mode 4, one launch per K ticks: state columns written after every tick (default) or the last")
     ap.add_argument("--l2", type=int, default=None, choices=[0, 1],
                     help="L2 residency hints of the tick kernel (default: the engine's, on)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
-                    help="CUDA-graph replay of the tick sequence (auto: only for small shards)")
-    ap.add_argument("--inbox", default="wide", choices=["wide", "bytes"],
-                    help="form of the HBM-resident inbox of the timed ticks: wide columns (default) or byte frames "
-                         "read by the tick kernels themselves (tick mode 3; experiment until validated on hardware)")
+                    help="how mrq_tick_many runs K ticks: auto/on = tick mode 4 in ONE launch pair, modes 0-3 as a CUDA graph "
+                         "(auto: small shards only); off = per-tick launches in every mode")
+    ap.add_argument("--inbox", default="compact", choices=["compact", "bytes", "wide"],
+                    help="the timed ticks: compact = byte frames on compact state (tick mode 4, default); bytes = byte frames on "
+                         "wide state (tick mode 3); wide = wide inbox columns (tick mode 0, round 1's path)")
     ap.add_argument("--weak", action="store_true",
                     help="N>1: weak scaling — every GPU keeps 1,048,576 groups, the job is N times that (default: the job "
                          "stays 1,048,576 groups, BASELINE configs[3]); compare group_ticks_per_sec across N")
-    ap.add_argument("--e2e8-child", action="store_true", help=argparse.SUPPRESS)  # internal: see run_e2e8_child
     args = ap.parse_args()
-    if args.e2e8_child:
-        run_e2e8_child(args)
-    elif args.impl == "reference":
+    if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

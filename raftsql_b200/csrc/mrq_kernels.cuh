@@ -1156,9 +1156,10 @@ __global__ void __launch_bounds__(kTickThreads, (R <= 5 ? 6 : 5)) tick_general_k
 // never change.  In mode 4 every index-like column of a group is a 32-bit OFFSET from one per-group u64 base
 // `ibase[g]` that only the general path ever reads:
 //     c.commit[g]        committed  - ibase
-//     c.match[r][g]      Progress.Match[r] - ibase   (0 = "at or below ibase": the exact value stays in the wide column,
-//                         and since ibase <= committed such a match can neither win a quorum nor be told apart by one)
-//     c.match[self-1][g] lastIndex - ibase            (a leader's own Match IS lastIndex; followers keep theirs here too)
+//     c.match[j][g]      Progress.Match of the j-th REMOTE sender - ibase, j = 0..R-2 in ascending id order — the row order
+//                         of the byte frame (0 = "at or below ibase": the exact value stays in the wide column, and since
+//                         ibase <= committed such a match can neither win a quorum nor be told apart by one)
+//     c.match[R-1][g]    lastIndex - ibase            (a leader's own Match IS lastIndex; followers keep theirs here too)
 //     c.win[g]           byte-inbox window base - ibase
 //     c.gate[g]          term_start - ibase, read only while the gate is still closed (flag bit CF_GATE_OPEN clear)
 //     c.flag[g]          CF_COMPACT (these columns, not the wide ones, are the truth for last_index / committed / match /
@@ -1197,50 +1198,118 @@ struct CGroup {  // one group's compact state, in registers
   uint32_t m[R];
 };
 
-// One tick of one group on compact state.  Returns true (and leaves `g` untouched) when the group needs the general
-// path.  `wb[j]`: the frame's byte of compact row j (R-1 rows), `nprop`: the proposal byte.  Mirrors fast_group_tick8
-// line for line, in offset space.
+// Row order.  The byte frame has R-1 rows: the remote senders in ascending id order (the group's own slot left out).
+// The compact match column uses the SAME order — row j is the Match of the j-th remote sender — and its last row,
+// R-1, is the group's own slot, i.e. lastIndex.  Frame row j therefore updates match row j with no mapping at all (the
+// quorum index does not care about the order); the sender's id is only needed for a follower's reply bits.
+__host__ __device__ __forceinline__ uint32_t crow_sender(uint32_t j, uint32_t self_id) {  // row j -> sender slot r (0-based)
+  return j + (j + 1u >= self_id ? 1u : 0u);
+}
+
+// The HOT case of a tick, straight-line: a settled leader (no strict mode, lastTerm == Term) whose frame holds nothing
+// but in-window acks of its own term.  Returns false — with `g` untouched — for anything else; compact_step decides then.
+template <int R>
+__device__ __forceinline__ bool compact_hot_step(CGroup<R> &g, const uint32_t flag, const uint32_t (&wb)[R > 1 ? R - 1 : 1],
+                                                 const uint32_t nprop, const uint32_t gate, const uint32_t et, const uint32_t ht,
+                                                 uint32_t &out, uint32_t &adv, uint32_t &dirty) {
+  constexpr uint64_t kSettled = 3ull | (1ull << 62) | (1ull << 63);  // role, strict, ltok
+  bool hot = (flag & (CF_COMPACT | CF_TERM_OK)) == (CF_COMPACT | CF_TERM_OK) &&
+             (g.meta & kSettled) == ((uint64_t)MRQ_ROLE_LEADER | (1ull << 63));
+  uint32_t li = g.m[R - 1];
+  hot = hot && li + nprop <= kCompactSpan;
+  uint32_t nm[R];
+  uint32_t d = 0, min_ack = MRQ_P8_NO_ACK, kinds = 0;
+#pragma unroll
+  for (int j = 0; j < R - 1; ++j) {
+    const uint32_t w = wb[j];
+    kinds |= w;
+    const bool ack = (w & 1u) != 0u;  // (kind 3 is ruled out below)
+    const uint32_t pay = w >> 2;
+    const uint32_t mx = ack ? g.win + pay : 0u;
+    hot = hot && mx <= li;            // an ack beyond lastIndex: upstream's strict path
+    nm[j] = max(g.m[j], mx);          // Progress.maybeUpdate
+    d |= nm[j] != g.m[j] ? CD_MATCH0 << j : 0u;
+    min_ack = ack ? min(min_ack, pay) : min_ack;
+  }
+  if (!hot || (kinds & 2u) != 0u) return false;  // heartbeats, responses, escapes: not the hot case
+  uint32_t o = 0;
+  li += nprop;  // appendEntry: lastTerm already equals Term (ltok), self Match = lastIndex
+  nm[R - 1] = li;
+  if (nprop) {
+    d |= CD_MATCH0 << (R - 1);
+    o |= MRQ_OUT_BCAST_APPEND;
+  }
+  uint32_t commit = g.commit, q = 0;
+  if (d != 0u) {  // maybeCommit, once (see Group::flushCommit for why once is exact)
+    uint32_t dl[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) dl[r] = max(nm[r], commit) - commit;
+    q = quorum_index32<R>(dl);
+    const bool open = (flag & CF_GATE_OPEN) != 0u || commit + q >= gate;
+    q = (commit + q <= li && open) ? q : 0u;
+  }
+  if (q != 0u) {
+    commit += q;
+    d |= CD_COMMIT;
+    o |= MRQ_OUT_COMMIT_ADVANCED | MRQ_OUT_BCAST_APPEND;
+  }
+  // tickHeartbeat on the packed word: electionElapsed bits [14,26), heartbeatElapsed bits [38,46)
+  uint32_t lo = (uint32_t)g.meta, hi = (uint32_t)(g.meta >> 32);
+  uint32_t el = ((lo >> 14) & 0xFFFu) + 1u, hb = ((hi >> 6) & 0xFFu) + 1u;
+  el = el >= et ? 0u : el;
+  if (hb >= ht) {
+    hb = 0;
+    o |= MRQ_OUT_BCAST_HEARTBEAT;
+  }
+  lo = (lo & ~(0xFFFu << 14)) | (el << 14);
+  hi = (hi & ~(0xFFu << 6)) | (hb << 6);
+  const uint64_t nmeta = ((uint64_t)hi << 32) | lo;
+  d |= nmeta != g.meta ? CD_META : 0u;
+  if (min_ack < MRQ_P8_NO_ACK && min_ack > MRQ_P8_SLACK) {  // the window slides for whoever decodes the frame
+    g.win += min_ack - MRQ_P8_SLACK;
+    d |= CD_WIN;
+  }
+  g.meta = nmeta;
+  g.commit = commit;
+#pragma unroll
+  for (int r = 0; r < R; ++r) g.m[r] = nm[r];
+  out = o;
+  adv = q;
+  dirty = d;
+  return true;
+}
+
+// One tick of one group on compact state, every case the compact form can express.  Returns true (and leaves `g`
+// untouched) when the group needs the general path.  `wb[j]`: the frame's byte of row j, `nprop`: the proposal byte,
+// `gate`: c.gate of the group (only looked at while CF_GATE_OPEN is clear).  Mirrors fast_group_tick8 in offset space.
 template <int R>
 __device__ __forceinline__ bool compact_step(CGroup<R> &g, const uint32_t flag, const uint32_t (&wb)[R > 1 ? R - 1 : 1],
-                                             const uint32_t nprop, const uint32_t *gate_ptr, const uint32_t et, const uint32_t ht,
+                                             const uint32_t nprop, const uint32_t gate, const uint32_t et, const uint32_t ht,
                                              uint32_t &out, uint32_t &adv, uint32_t &dirty) {
   out = 0;
   adv = 0;
   dirty = 0;
   if (!(flag & CF_COMPACT)) return true;
   Meta m = meta_unpack(g.meta);
-  // the frame's bytes by sender slot
-  uint32_t kind[R], pay[R];
-  bool any_ack = false, any_hb = false, other = false;
+  uint32_t kind[R > 1 ? R - 1 : 1], pay[R > 1 ? R - 1 : 1];
+  bool any_ack = false, any_hb = false;
   uint32_t min_ack = MRQ_P8_NO_ACK;
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    kind[r] = 0;
-    pay[r] = 0;
-    const uint32_t row = mrq_p8_row((uint32_t)r, m.self, (uint32_t)R);
-    if (row >= (uint32_t)R - 1u) continue;  // the group's own slot
-    uint32_t w = 0;
-#pragma unroll
-    for (int j = 0; j < R - 1; ++j)
-      if ((uint32_t)j == row) w = wb[j];
-    kind[r] = w & 3u;
-    pay[r] = (w >> 2) & 63u;
-    if (kind[r] == 1u) {
+  for (int j = 0; j < R - 1; ++j) {
+    kind[j] = wb[j] & 3u;
+    pay[j] = (wb[j] >> 2) & 63u;
+    if (kind[j] == 1u) {
       any_ack = true;
-      min_ack = pay[r] < min_ack ? pay[r] : min_ack;
-    } else if (kind[r] == 3u) {
+      min_ack = pay[j] < min_ack ? pay[j] : min_ack;
+    } else if (kind[j] == 3u) {
       any_hb = true;
-    } else if (kind[r] == 2u && (pay[r] <= 2u || pay[r] == 63u)) {
-      other = true;  // heartbeat-resp, vote-resp, or escaped to the wide list: the general path's business
+    } else if (kind[j] == 2u && (pay[j] <= 2u || pay[j] == 63u)) {
+      return true;  // heartbeat-resp, vote-resp, or escaped to the wide list: the general path's business
     } else {
-      kind[r] = 0;  // no message
+      kind[j] = 0;  // no message
     }
   }
-  if (other) return true;
-  uint32_t li = 0;  // lastIndex offset: the group's own match slot
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-    if ((uint32_t)(r + 1) == m.self) li = g.m[r];
+  uint32_t li = g.m[R - 1];
   CGroup<R> n = g;
   if (m.role == MRQ_ROLE_LEADER) {
     if (m.strict || !m.ltok || any_hb) return true;
@@ -1248,24 +1317,20 @@ __device__ __forceinline__ bool compact_step(CGroup<R> &g, const uint32_t flag, 
     if (li + nprop > kCompactSpan) return true;  // time to re-base
     bool changed = false;
 #pragma unroll
-    for (int r = 0; r < R; ++r)
-      if (kind[r] == 1u) {
-        const uint32_t mx = g.win + pay[r];
+    for (int j = 0; j < R - 1; ++j)
+      if (kind[j] == 1u) {
+        const uint32_t mx = g.win + pay[j];
         if (mx > li) return true;  // ack beyond lastIndex: upstream's strict path
-        if (n.m[r] < mx) {         // Progress.maybeUpdate
-          n.m[r] = mx;
-          dirty |= CD_MATCH0 << r;
+        if (n.m[j] < mx) {         // Progress.maybeUpdate
+          n.m[j] = mx;
+          dirty |= CD_MATCH0 << j;
           changed = true;
         }
       }
     if (nprop) {  // appendEntry: lastTerm already equals Term (ltok), self Match = lastIndex
       li += nprop;
-#pragma unroll
-      for (int r = 0; r < R; ++r)
-        if ((uint32_t)(r + 1) == m.self) {
-          n.m[r] = li;
-          dirty |= CD_MATCH0 << r;
-        }
+      n.m[R - 1] = li;
+      dirty |= CD_MATCH0 << (R - 1);
       out |= MRQ_OUT_BCAST_APPEND;
       changed = true;
     }
@@ -1275,15 +1340,11 @@ __device__ __forceinline__ bool compact_step(CGroup<R> &g, const uint32_t flag, 
       for (int r = 0; r < R; ++r) d[r] = max(n.m[r], n.commit) - n.commit;
       const uint32_t q = quorum_index32<R>(d);
       const uint32_t mci = n.commit + q;
-      if (q != 0u && mci <= li) {
-        bool open = (flag & CF_GATE_OPEN) != 0u;
-        if (!open) open = mci >= ld_stream_u32(gate_ptr);
-        if (open) {
-          adv = q;
-          n.commit = mci;
-          dirty |= CD_COMMIT;
-          out |= MRQ_OUT_COMMIT_ADVANCED | MRQ_OUT_BCAST_APPEND;
-        }
+      if (q != 0u && mci <= li && ((flag & CF_GATE_OPEN) != 0u || mci >= gate)) {
+        adv = q;
+        n.commit = mci;
+        dirty |= CD_COMMIT;
+        out |= MRQ_OUT_COMMIT_ADVANCED | MRQ_OUT_BCAST_APPEND;
       }
     }
     ++m.hb;  // tickHeartbeat
@@ -1297,27 +1358,26 @@ __device__ __forceinline__ bool compact_step(CGroup<R> &g, const uint32_t flag, 
     if (nprop != 0u || any_ack) return true;
     if (any_hb && !(flag & CF_TERM_OK)) return true;
 #pragma unroll
-    for (int r = 0; r < R; ++r)
-      if (kind[r] == 3u && ((uint32_t)(r + 1) != m.lead || g.win + pay[r] > li)) return true;
+    for (int j = 0; j < R - 1; ++j)
+      if (kind[j] == 3u && (crow_sender((uint32_t)j, m.self) + 1u != m.lead || g.win + pay[j] > li)) return true;
     if ((any_hb ? 1u : m.elapsed + 1u) >= m.rto) return true;  // the election timer would fire: campaign() is general
 #pragma unroll
-    for (int r = 0; r < R; ++r)
-      if (kind[r] == 3u) {  // stepFollower MsgHeartbeat: electionElapsed = 0, lead = From, commitTo, reply
-        const uint32_t mx = g.win + pay[r];
+    for (int j = 0; j < R - 1; ++j)
+      if (kind[j] == 3u) {  // stepFollower MsgHeartbeat: electionElapsed = 0, lead = From, commitTo, reply
+        const uint32_t mx = g.win + pay[j];
         if (n.commit < mx) {
           adv += mx - n.commit;
           n.commit = mx;
           dirty |= CD_COMMIT;
           out |= MRQ_OUT_COMMIT_ADVANCED;
         }
-        out |= 1u << (MRQ_OUT_ACK_REPLY_SHIFT + r);
+        out |= 1u << (MRQ_OUT_ACK_REPLY_SHIFT + crow_sender((uint32_t)j, m.self));
       }
     m.elapsed = any_hb ? 1u : m.elapsed + 1u;
   } else {
     return true;
   }
-  // the window slides for whoever decodes the frame
-  if (min_ack < MRQ_P8_NO_ACK && min_ack > MRQ_P8_SLACK) {
+  if (min_ack < MRQ_P8_NO_ACK && min_ack > MRQ_P8_SLACK) {  // the window slides for whoever decodes the frame
     n.win = g.win + (min_ack - MRQ_P8_SLACK);
     dirty |= CD_WIN;
   }
@@ -1335,11 +1395,12 @@ __device__ __forceinline__ void materialise_group(const StateView &s, const Comp
   const uint64_t ib = c.ibase[i];
   s.committed[i] = ib + c.commit[i];
   base_index[i] = ib + c.win[i];
-  if (m.self >= 1 && m.self <= R) s.last_index[i] = ib + c.match[(uint64_t)(m.self - 1u) * gs + i];
+  s.last_index[i] = ib + c.match[(uint64_t)(R - 1u) * gs + i];
   if (m.role == MRQ_ROLE_LEADER) {
-    for (uint32_t r = 0; r < R; ++r) {
-      const uint32_t v = c.match[(uint64_t)r * gs + i];
-      if (v != 0u) s.match[(uint64_t)r * gs + i] = ib + v;
+    s.match[(uint64_t)(m.self - 1u) * gs + i] = ib + c.match[(uint64_t)(R - 1u) * gs + i];  // a leader's own Match is lastIndex
+    for (uint32_t j = 0; j + 1u < R; ++j) {
+      const uint32_t v = c.match[(uint64_t)j * gs + i];
+      if (v != 0u) s.match[(uint64_t)crow_sender(j, m.self) * gs + i] = ib + v;  // 0: the wide value (<= ibase) stands
     }
   }
 }
@@ -1364,16 +1425,15 @@ __device__ __forceinline__ void compact_group(const StateView &s, const CompactV
   c.iblo[i] = (uint32_t)ib;
   c.commit[i] = (uint32_t)(cm - ib);
   c.win[i] = (uint32_t)(wb - ib);
-  for (uint32_t r = 0; r < R; ++r) {
+  for (uint32_t j = 0; j + 1u < R; ++j) {
     uint32_t v = 0;
-    if ((uint32_t)(r + 1) == m.self) {
-      v = (uint32_t)(li - ib);
-    } else if (leader) {
-      const uint64_t mv = s.match[(uint64_t)r * gs + i];
+    if (leader) {
+      const uint64_t mv = s.match[(uint64_t)crow_sender(j, m.self) * gs + i];
       v = mv > ib ? (uint32_t)(mv - ib) : 0u;  // mv <= lastIndex (not strict), so the offset fits
     }
-    c.match[(uint64_t)r * gs + i] = v;
+    c.match[(uint64_t)j * gs + i] = v;
   }
+  c.match[(uint64_t)(R - 1u) * gs + i] = (uint32_t)(li - ib);
   uint32_t go = 0xFFFFFFFFu;  // closed for good (not a leader)
   if (leader) go = gate > ib ? (gate - ib > 0xFFFFFFFEull ? 0xFFFFFFFFu : (uint32_t)(gate - ib)) : 0u;
   c.gate[i] = go;
@@ -1484,6 +1544,8 @@ __global__ void __launch_bounds__(kQuadThreads, (R <= 5 ? 4 : 3)) tick_fast4_ker
 #pragma unroll
   for (int k = 0; k < 4; ++k)
     if (!active || i0 + k >= a.G) stopped |= 1u << k;
+  u32x4 gate{};  // only the few groups whose commit gate is still closed look at it
+  if (((flag[0] & flag[1] & flag[2] & flag[3]) & CF_GATE_OPEN) == 0u) gate = ld_v4u32_p(A.c.gate + i, pol_keep);
   const bool gather = a.world > 1;
   u32x4 iblo{};
   if (gather) iblo = ld_v4u32_p(A.c.iblo + i, pol_keep);
@@ -1517,8 +1579,10 @@ __global__ void __launch_bounds__(kQuadThreads, (R <= 5 ? 4 : 3)) tick_fast4_ker
 #pragma unroll
       for (int j = 0; j < (R > 1 ? R - 1 : 1); ++j) wk[j] = (wb[j] >> (8 * k)) & 0xFFu;
       uint32_t o, adv, dirty;
-      const bool slow = compact_step<R>(g[k], flag[k], wk, (pb >> (8 * k)) & 0xFFu, A.c.gate + i + k, a.election_tick,
-                                        a.heartbeat_tick, o, adv, dirty);
+      const uint32_t np = (pb >> (8 * k)) & 0xFFu;
+      bool slow = false;
+      if (!compact_hot_step<R>(g[k], flag[k], wk, np, gate.v[k], a.election_tick, a.heartbeat_tick, o, adv, dirty))
+        slow = compact_step<R>(g[k], flag[k], wk, np, gate.v[k], a.election_tick, a.heartbeat_tick, o, adv, dirty);
       if (slow) {
         newly |= 1u << k;
       } else {
@@ -1583,7 +1647,7 @@ __global__ void __launch_bounds__(kQuadThreads, (R <= 5 ? 4 : 3)) tick_fast4_ker
     const bool last = t + 1 == A.nticks;
     if (A.write_through || last) {
       uint32_t wd = __reduce_or_sync(0xFFFFFFFFu, A.write_through ? tdirty : acc_dirty);
-      if (active && stopped != 0xFu) {
+      if (active) {  // (a quad whose groups all left the fast path still owes the columns its earlier ticks changed)
         if (wd & CD_META) {
           st_v2u64_p(a.s.meta + i, g[0].meta, g[1].meta, pol_keep);
           st_v2u64_p(a.s.meta + i + 2, g[2].meta, g[3].meta, pol_keep);

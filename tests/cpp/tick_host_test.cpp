@@ -472,7 +472,7 @@ struct CompactHost {
   std::vector<uint8_t> flag;
   std::vector<uint32_t> commit, win, gate, iblo, match;
   std::vector<uint64_t> ibase;
-  uint64_t fast_ticks = 0, slow_entries = 0;
+  uint64_t fast_ticks = 0, slow_entries = 0, hot_ticks = 0;
   CompactHost(uint64_t gs_, uint32_t R_) : gs(gs_), R(R_), flag(gs_, 0), commit(gs_, 0), win(gs_, 0), gate(gs_, 0), iblo(gs_, 0),
                                             match(gs_ * R_, 0), ibase(gs_, 0) {}
   CompactView view() { return CompactView{flag.data(), commit.data(), win.data(), gate.data(), iblo.data(), match.data(), ibase.data()}; }
@@ -492,6 +492,7 @@ struct HostSlot {  // one tick's frame, wide inbox slot (escapes + the general p
   }
 };
 
+bool hot_path = true;  // (off: every compact tick through compact_step alone — the two must agree with the oracle either way)
 template <int R>
 void host_ticks_c(HostEngine &e, CompactHost &ch, const TickArgs &a, std::vector<TickDesc> &descs, uint64_t *base_index,
                   const uint64_t *base_term) {
@@ -518,7 +519,12 @@ void host_ticks_c(HostEngine &e, CompactHost &ch, const TickArgs &a, std::vector
       uint32_t wb[R > 1 ? R - 1 : 1] = {0};
       for (int j = 0; j < R - 1; ++j) wb[j] = d.word8[(uint64_t)j * e.gs + i];
       uint32_t o, adv, dirty;
-      slow = compact_step<R>(g, flag, wb, d.prop8 ? d.prop8[i] : 0u, ch.gate.data() + i, a.election_tick, a.heartbeat_tick, o, adv, dirty);
+      const uint32_t np = d.prop8 ? d.prop8[i] : 0u;
+      slow = false;
+      if (!hot_path || !compact_hot_step<R>(g, flag, wb, np, ch.gate[i], a.election_tick, a.heartbeat_tick, o, adv, dirty))
+        slow = compact_step<R>(g, flag, wb, np, ch.gate[i], a.election_tick, a.heartbeat_tick, o, adv, dirty);
+      else
+        ++ch.hot_ticks;
       if (slow) break;
       d.out[i] = o;
       d.delta[i] = (uint8_t)(adv > 255u ? 255u : adv);
@@ -703,9 +709,9 @@ void run_case_c(uint64_t G, uint32_t R, uint32_t cfg, int T, int rebase_every, u
   }
   uint64_t n_compact = 0;
   for (uint64_t g = 0; g < G; ++g) n_compact += ch.flag[g] & CF_COMPACT;
-  std::printf("  %-44s %4d ticks  bytes %8llu  escapes %7llu  fast group-ticks %8llu  general entries %7llu  compact now %llu/%llu\n", where, T,
-              (unsigned long long)n_bytes, (unsigned long long)n_escapes, (unsigned long long)ch.fast_ticks, (unsigned long long)ch.slow_entries,
-              (unsigned long long)n_compact, (unsigned long long)G);
+  std::printf("  %-44s %4d ticks  bytes %8llu  escapes %7llu  fast group-ticks %8llu (hot %8llu)  general entries %7llu  compact now %llu/%llu\n",
+              where, T, (unsigned long long)n_bytes, (unsigned long long)n_escapes, (unsigned long long)ch.fast_ticks,
+              (unsigned long long)ch.hot_ticks, (unsigned long long)ch.slow_entries, (unsigned long long)n_compact, (unsigned long long)G);
   if (!bad && !soup && R > 1 && ch.fast_ticks < (uint64_t)T * G / 4) {
     std::printf("FAIL %s: the compact fast path handled too little (%llu of %llu group-ticks)\n", where, (unsigned long long)ch.fast_ticks,
                 (unsigned long long)((uint64_t)T * G));
@@ -902,6 +908,10 @@ int main(int argc, char **) {
   run_case_c(200 / k, 3, 5, 240, 40, 1);
   kCompactSpan = 0x7FFFFFFFu;
   for (uint32_t R : {2u, 3u, 5u, 8u}) run_case_c(120 / k + 8, R, 300 + R, 240, 8, R == 5 ? 4 : 1, true);  // message soups
+  hot_path = false;  // the complete compact step alone (the hot step is an early exit of it, never a different answer)
+  run_case_c(300 / k, 5, 5, 224, 32, 1);
+  run_case_c(300 / k, 3, 3, 300, 1000, 4, false, 0, 60);
+  hot_path = true;
   std::printf(failures ? "tick_host_test: %d failure(s)\n" : "tick_host_test: ok\n", failures);
   return failures ? 1 : 0;
 }

@@ -63,6 +63,10 @@ class FakeL:
         e.prev = np.where(d > 255, e.prev, c)
         return 0
 
+    def mrq_drain_tick_deltas(self, h, dptr):
+        np.ctypeslib.as_array(dptr, shape=(self.e.G,))[:] = self.e.last_adv
+        return 0
+
     def mrq_drain_wait(self, h):
         return 0
 
@@ -81,6 +85,7 @@ class FakeEngine:
         self.prev = np.zeros(G, np.uint64)
         self.L, self.h = FakeL(self), 1
         self.tick_mode, self.frames = 0, {}
+        self.last_adv, self.slot_out = np.zeros(G, np.uint8), {}
 
     def _self_id(self):
         return self.o.export()["self_id"]
@@ -104,7 +109,7 @@ class FakeEngine:
     def post_inbox_packed(self, word, prop8=None, wide=(), slot=0, keep=False):
         assert word.dtype == np.uint8 and word.shape == (max(self.R - 1, 0), self.G)
         frame = (np.array(word), None if prop8 is None else np.array(prop8), list(wide), bool(keep))
-        if self.tick_mode == 3:  # the frame waits in its slot; the TICK decodes it, against the base of that moment
+        if self.tick_mode >= 3:  # the frame waits in its slot; the TICK decodes it, against the base of that moment
             self.frames[slot] = frame
         else:  # the unpack pass runs at post time
             self.frames.pop(slot, None)
@@ -131,12 +136,42 @@ class FakeEngine:
         self.slots[slot] = oracle.empty_inbox(self.G, self.R)
 
     def tick(self, slot=0):
-        if self.tick_mode == 3 and slot in self.frames:
+        if self.tick_mode >= 3 and slot in self.frames:
             frame = self.frames[slot]
             self._decode(frame, slot)
             if not frame[3]:  # MRQ_PACKED_KEEP not set: one tick per post
                 del self.frames[slot]
+        before = self.o.export()["committed"]
         self.o.tick(self.slots[slot])
+        after = self.o.export()
+        self.last_adv = np.minimum(after["committed"] - before, 255).astype(np.uint8)  # mode 4's per-tick advance bytes
+        self.slot_out[slot] = (after["out"].copy(), self.last_adv.copy())
+
+    def tick_many(self, slots):
+        for s in slots:
+            self.tick(s)
+
+    def sync_tick_deltas(self):
+        return self.last_adv.copy()
+
+    def sync_slot_outputs(self, slot):
+        return self.slot_out[slot]
+
+    def set_write_through(self, on):
+        pass
+
+    def post_inbox_dense(self, ib, slot=0):
+        self.frames.pop(slot, None)
+        self.slots[slot] = {k: np.array(v) for k, v in ib.items()}
+
+    def match_update(self, groups, frm, index):
+        st = self.o.export()
+        for g, f, i in zip(groups, frm, index):
+            self.o.step(int(g), 4, frm=int(f), term=int(st["term"][int(g)]), index=int(i))
+            self._undo_commit = True
+
+    def quorum_commit(self):
+        pass  # (the double's match_update already Stepped the acks one at a time, commit included)
 
     def tick_idle(self, n=1):
         for _ in range(n):
@@ -195,10 +230,6 @@ class FakeBenchEngine(FakeEngine):
     def tick(self, slot=0):
         super().tick(slot)
         self.launches += 2
-
-    def tick_many(self, slots):
-        for s in slots:
-            self.tick(s)
 
     def counters(self):
         return {"kernel_launches": self.launches, "ticks": self.o.tick_count, "errors": self.o.errors}
