@@ -8,7 +8,7 @@ CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -Wextra -pthread
 ROOT := $(abspath .)
 LIB := raftsql_b200/libmrq.so
 HOSTLIB := raftsql_b200/libraftpipe.so
-SRC := raftsql_b200/csrc/mrq_engine.cu
+SRC := raftsql_b200/csrc/mrq_engine.cu raftsql_b200/csrc/mrq_pack8_rows.cpp
 HDR := raftsql_b200/csrc/mrq_kernels.cuh include/mrq.h include/mrq_trace.h include/mrq_packed8.h
 HOSTSRC := raftsql_b200/csrc/host/hostnode.cpp raftsql_b200/csrc/host/raftpipe.cpp
 HOSTHDR := raftsql_b200/csrc/host/chan.hpp raftsql_b200/csrc/host/hostnode.hpp raftsql_b200/csrc/host/raftpipe.hpp include/mrq.h

@@ -12,6 +12,7 @@
 
 #include <condition_variable>
 #include <functional>
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <string>
@@ -1001,6 +1002,11 @@ namespace {
 // Contiguous group ranges on a PERSISTENT pool of host threads: frames of a million groups are memory-bound host work
 // (17 B of wide columns read per cell), so the builder scales with the cores the host gives it, and a live host builds
 // one frame per tick — spawning threads per call would cost more than the frame.  MRQ_HOST_THREADS overrides the size.
+extern "C" void mrqi_pack8_row(const uint8_t *ty, const uint64_t *tm, const uint64_t *ix, const uint64_t *bi, const uint64_t *bt,
+                               uint64_t n, uint8_t *out);  // mrq_pack8_rows.cpp
+extern "C" void mrqi_pack8_place(const uint8_t *b, const uint8_t *self, uint32_t r, uint64_t n, uint8_t *lo, uint8_t *hi, uint8_t *mn);
+extern "C" int mrqi_pack8_marked(const uint8_t *b, uint64_t n);
+
 class HostPool {
  public:
   ~HostPool() {
@@ -1080,7 +1086,7 @@ std::mutex g_pack_mu;
 
 unsigned host_threads(uint64_t G) {
   unsigned hw = std::thread::hardware_concurrency();
-  unsigned cap = 32;  // memory-bound work: past a few threads per memory channel more buys nothing
+  unsigned cap = 128;  // measured on the 128-thread B200 host: ~7 ns per cell per thread, scaling with the threads it gets
   if (const char *s = getenv("MRQ_HOST_THREADS")) hw = cap = (unsigned)strtoul(s, nullptr, 10);
   if (hw < 1) hw = 1;
   const uint64_t by_size = G / 16384;  // below ~16k groups per thread the hand-off costs more than it saves
@@ -1108,44 +1114,58 @@ int mrq_pack8(const mrq_inbox *in, const uint8_t *self_id, uint64_t G, uint32_t 
   if (slid.size() < G) slid.resize(G);
   std::vector<uint64_t> bad(nt, kNone);
   host_pool().run(nt, [&](unsigned c) {
-    const uint64_t g0 = G * c / nt, g1 = G * (c + 1) / nt;
-    for (uint64_t g = g0; g < g1; ++g) {
-      uint32_t min_ack = MRQ_P8_NO_ACK;
-      const uint64_t bi = base_index[g], bt = base_term[g];
-      const uint32_t self = self_id[g];
+    const uint64_t c0 = G * c / nt, c1 = G * (c + 1) / nt;
+    // Row-major inside blocks of kBlk groups: each sender row is a straight streaming pass over its three columns
+    // (type, then term / index / commit only where a message sits), the per-group window minimum lives in a block-sized
+    // scratch that stays in L1.  The order of the escapes (by group, then by sender) is restored per block.
+    constexpr uint64_t kBlk = 1024;
+    uint8_t min_ack[kBlk], row_bytes[kBlk];
+    std::vector<mrq_msg> blk_esc;
+    for (uint64_t g0 = c0; g0 < c1; g0 += kBlk) {
+      const uint64_t g1 = g0 + kBlk < c1 ? g0 + kBlk : c1;
+      memset(min_ack, MRQ_P8_NO_ACK, sizeof min_ack);
+      blk_esc.clear();
       for (uint32_t r = 0; r < R; ++r) {
-        const uint32_t row = mrq_p8_row(r, self, R);
-        if (row >= R - 1u) continue;  // the group's own slot: nothing is ever stepped from there
-        const uint64_t o = (uint64_t)r * G + g;
-        const uint32_t ty = in->type[o];
-        if ((ty & 0x0Fu) == 0u) {
-          word_out[(uint64_t)row * G + g] = 0;
-          continue;
+        const uint8_t *ty = in->type + (uint64_t)r * G;
+        const uint64_t *tm = in->term + (uint64_t)r * G, *ix = in->index + (uint64_t)r * G, *cm = in->commit + (uint64_t)r * G;
+        // the common case for the whole row in one vectorised pass ...
+        mrqi_pack8_row(ty + g0, tm + g0, ix + g0, base_index + g0, base_term + g0, g1 - g0, row_bytes);
+        if (mrqi_pack8_marked(row_bytes, g1 - g0)) {  // ... the few marked cells re-encoded exactly, one by one
+          for (uint64_t g = g0; g < g1; ++g) {
+            if (row_bytes[g - g0] != MRQ_P8_ESCAPE) continue;
+            const uint32_t self = self_id[g];
+            if (r + 1u == self || self < 1u || self > R) continue;  // the group's own slot: nothing is ever stepped from there
+            const uint8_t b = mrq_p8_encode(ty[g], tm[g], ix[g], cm[g], base_index[g], base_term[g]);
+            row_bytes[g - g0] = b;
+            if (b == MRQ_P8_ESCAPE) {
+              mrq_msg m;
+              memset(&m, 0, sizeof m);
+              m.group = g;
+              m.from = (uint8_t)(r + 1u);
+              m.type = ty[g];
+              m.term = tm[g];
+              m.index = ix[g];
+              m.logterm = in->logterm ? in->logterm[(uint64_t)r * G + g] : 0;
+              m.commit = cm[g];
+              blk_esc.push_back(m);
+            }
+          }
         }
-        const uint32_t kind = ty & 0x0Fu;
-        const uint8_t b = mrq_p8_encode(ty, in->term[o], kind == 4u ? in->index[o] : 0, kind == 8u ? in->commit[o] : 0, bi, bt);
-        word_out[(uint64_t)row * G + g] = b;
-        if (b == MRQ_P8_ESCAPE) {
-          mrq_msg m;
-          memset(&m, 0, sizeof m);
-          m.group = g;
-          m.from = (uint8_t)(r + 1u);
-          m.type = in->type[o];
-          m.term = in->term[o];
-          m.index = in->index[o];
-          m.logterm = in->logterm ? in->logterm[o] : 0;
-          m.commit = in->commit[o];
-          esc[c].push_back(m);
-        } else if ((b & 3u) == 1u) {
-          const uint32_t p = b >> 2;
-          min_ack = p < min_ack ? p : min_ack;
-        }
+        // ... and the row placed into the frame (row r or r - 1 by the group's own id) with byte-wide blends
+        mrqi_pack8_place(row_bytes, self_id + g0, r, g1 - g0, r >= 1 ? word_out + (uint64_t)(r - 1u) * G + g0 : nullptr,
+                         r + 1u < R ? word_out + (uint64_t)r * G + g0 : nullptr, min_ack);
       }
-      slid[g] = mrq_p8_next_base(bi, min_ack);
+      if (!blk_esc.empty()) {  // rows were walked sender-major: put the block's escapes back in (group, sender) order
+        std::stable_sort(blk_esc.begin(), blk_esc.end(), [](const mrq_msg &x, const mrq_msg &y) { return x.group < y.group; });
+        esc[c].insert(esc[c].end(), blk_esc.begin(), blk_esc.end());
+      }
+      for (uint64_t g = g0; g < g1; ++g) slid[g] = mrq_p8_next_base(base_index[g], min_ack[g - g0]);
       if (prop8_out) {
-        const uint32_t n = in->prop_count ? in->prop_count[g] : 0u;
-        if (n > 255u && bad[c] == kNone) bad[c] = g;
-        prop8_out[g] = (uint8_t)n;
+        for (uint64_t g = g0; g < g1; ++g) {
+          const uint32_t n = in->prop_count ? in->prop_count[g] : 0u;
+          if (n > 255u && bad[c] == kNone) bad[c] = g;
+          prop8_out[g] = (uint8_t)n;
+        }
       }
     }
   });
@@ -1387,6 +1407,12 @@ int mrq_set_tick_mode(mrq_engine *e, int mode) {
   if (mode == 4) {
     int r = ensure_compact_alloc(e);
     if (r) return r;
+  }
+  if (mode != e->tick_mode && e->l2_policy) {
+    // Each mode marks ITS state columns evict-last; lines another mode left marked would squat in L2 and starve this
+    // one (measured: the wide tick ran 2.5x slower after a mode-4 run).  Drop every persisting line at the switch.
+    CK(e, cudaStreamSynchronize(e->stream));
+    cudaCtxResetPersistingL2Cache();
   }
   e->tick_mode = mode;
   return MRQ_OK;

@@ -37,36 +37,31 @@ def test_reference_arm_prints_the_contract_line():
     assert line["config"]["groups"] == 1 << 20 and line["config"]["replicas"] == 5
 
 
-def test_byte_form_leg_can_only_add_to_the_bench_line():
-    """bench.py measures the byte-form inbox in a child process and merges its outcome: adopted only when it
-    verified itself and is faster, recorded otherwise, and nothing the child returns can break the line."""
+def test_bench_byte_accounting_and_the_traffic_guard(tmp_path, monkeypatch):
+    """the roofline's algorithmic bytes per group-tick for every form bench.py can time, and the rule that an ncu traffic
+    figure captured from another build of the kernel is refused instead of quoted"""
     sys.path.insert(0, ROOT)
     import bench
 
-    def e2e():
-        return {"value": 4467.0, "unit": "ticks/s", "h2d_bytes_per_step": 11_534_336, "d2h_bytes_per_step": 1 << 20, "steps": 20,
-                "api": "16-bit", "packed_equals_wide": True}
-
-    good = {"value": 9000.0, "unit": "ticks/s", "steps": 20, "h2d_bytes_per_step": 5 << 20, "d2h_bytes_per_step": 1 << 20,
-            "equals_wide_form": True, "escapes": 0, "api": "8-bit"}
-    e = e2e()
-    bench.merge_packed8(e, good)
-    assert e["value"] == 9000.0 and e["api"] == "8-bit" and e["h2d_bytes_per_step"] == 5 << 20 and e["packed8"] is good
-    assert e["packed_equals_wide"] is True
-    e = e2e()
-    bench.merge_packed8(e, dict(good, value=3000.0))  # verified but slower: recorded, not adopted
-    assert e["value"] == 4467.0 and e["api"] == "16-bit" and e["packed8"]["value"] == 3000.0
-    e = e2e()
-    bench.merge_packed8(e, dict(good, equals_wide_form=False))  # wrong answers: never adopted, and flagged
-    assert e["value"] == 4467.0 and e["packed_equals_wide"] is False
-    for junk in ({"error": "exit 1: boom"}, {}, None, [1, 2], "text", {"equals_wide_form": True}):
-        e = e2e()
-        bench.merge_packed8(e, junk)
-        assert e["value"] == 4467.0 and e["api"] == "16-bit" and "packed8" in e
-        json.dumps(e)
-    # and on a machine without a GPU the child itself fails cleanly
-    r = bench.e2e8_from_child(4)
-    assert set(r) == {"error"} and "no CUDA device" in r["error"]
+    assert bench.tick_bytes_per_group(5, "wide")["total"] == 217
+    assert bench.tick_bytes_per_group(5, "bytes")["total"] == 173
+    c1 = bench.tick_bytes_per_group(5, "compact", 1)
+    assert c1 == {"read": 42, "write": 40, "total": 82}
+    c20 = bench.tick_bytes_per_group(5, "compact", 20, True)
+    assert abs(c20["read"] - (5 + 37 / 20)) < 0.01 and c20["write"] == 40  # frame + state/K read; write-through writes it all
+    c20e = bench.tick_bytes_per_group(5, "compact", 20, False)
+    assert abs(c20e["total"] - (5 + 5 + (37 + 35) / 20)) < 0.02
+    assert bench.quorum_bytes_per_group(5) == 56 and bench.quorum_bytes_per_group(7) == 72
+    # traffic guard
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    os.makedirs(tmp_path / "profiles")
+    (tmp_path / "profiles" / "r02_traffic.json").write_text(json.dumps(
+        {"k": {"dram_read_bytes": 100, "dram_write_bytes": 23, "sass_instructions": 1000}}))
+    monkeypatch.setattr(bench, "sass_instruction_count", lambda sub: 1000)
+    assert bench.ncu_traffic("k", "k") == 123
+    monkeypatch.setattr(bench, "sass_instruction_count", lambda sub: 1001)
+    assert bench.ncu_traffic("k", "k") is None, "a capture of another kernel build must not be quoted"
+    assert bench.ncu_traffic("missing", "k") is None
 
 
 def test_reference_arm_other_ranks_exit_quietly():

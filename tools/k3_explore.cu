@@ -57,6 +57,79 @@ __device__ __forceinline__ unsigned quad(const QuorumArgs &a, uint64_t i) {
   return nmoved;
 }
 
+// ---- diagnostic variants: what bounds the 7-stream read + 1-stream write at this size? -----------------------------
+// MODE 0: the product body; 1: no store (read-only); 2: loads + xor only (no selection network, no store);
+// 3: loads carry the .L2::256B prefetch hint; 4: stores carry an evict-first policy (st.global.cs)
+__device__ __forceinline__ u64x4 ld_v4_pf256(const uint64_t *p) {
+  u64x4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.b64 {%0, %1, %2, %3}, [%4];"
+               : "=l"(r.v[0]), "=l"(r.v[1]), "=l"(r.v[2]), "=l"(r.v[3])
+               : "l"(p));
+  return r;
+}
+template <int MODE>
+__device__ __forceinline__ unsigned quad_x(const QuorumArgs &a, uint64_t i) {
+  u64x4 mv[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) mv[r] = MODE == 3 ? ld_v4_pf256(a.match + (uint64_t)r * a.gs + i) : ld_stream_v4(a.match + (uint64_t)r * a.gs + i);
+  const u64x4 cm = ld_plain_v4(a.committed + i);
+  const u64x4 gt = MODE == 3 ? ld_v4_pf256(a.term_start + i) : ld_stream_v4(a.term_start + i);
+  unsigned nmoved = 0;
+  if (MODE == 2) {
+    uint64_t x = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) x ^= mv[r].v[k];
+      x ^= cm.v[k] ^ gt.v[k];
+    }
+    return (unsigned)(x == 0x123456789ull);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint64_t m[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) m[r] = mv[r].v[k];
+    bool moved;
+    const uint64_t c = quorum_commit_one<R>(m, cm.v[k], gt.v[k], moved);
+    if (MODE == 1) {
+      nmoved += moved;
+      continue;
+    }
+    if (moved) {
+      if (MODE == 4)
+        asm volatile("st.global.cs.u64 [%0], %1;" ::"l"(a.committed + i + k), "l"(c) : "memory");
+      else
+        st_state(a.committed + i + k, c);
+    }
+    nmoved += moved;
+  }
+  return nmoved;
+}
+template <int THREADS, int MINB, int MODE>
+__global__ void __launch_bounds__(THREADS, MINB) k3_diag(const QuorumArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const uint64_t i = ((uint64_t)blockIdx.x * THREADS + threadIdx.x) * 4;
+  unsigned n = 0;
+  if (i + 3 < a.G) n = quad_x<MODE>(a, i);
+  count_moved(a.ctr, n);
+}
+// one contiguous array of the same 58.7 MB, 256-bit loads: the pure read-stream ceiling of this GPU at this size
+__global__ void __launch_bounds__(128) k3_onestream(const QuorumArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const uint64_t n4 = a.G * (R + 2) / 4;  // 256-bit words in match[R] + 2 columns' worth
+  uint64_t x = 0;
+  for (uint64_t q = (uint64_t)blockIdx.x * 128 + threadIdx.x; q < n4; q += (uint64_t)gridDim.x * 128) {
+    const uint64_t m4 = a.G * R / 4, g4 = a.G / 4;  // match is [R][G]; then term_start, then committed: three arrays, each contiguous
+    const uint64_t *src = q < m4 ? a.match + q * 4 : (q < m4 + g4 ? a.term_start + (q - m4) * 4 : a.committed + (q - m4 - g4) * 4);
+    const u64x4 v = ld_stream_v4(src);
+    x ^= v.v[0] ^ v.v[1] ^ v.v[2] ^ v.v[3];
+  }
+  count_moved(a.ctr, (unsigned)(x == 0x123456789ull));
+}
+
 template <int THREADS, int QUADS, bool WAIT>
 __global__ void __launch_bounds__(THREADS) k3_tile(const QuorumArgs a) {
   pdl_launch_dependents();
@@ -181,6 +254,12 @@ int main(int argc, char **argv) {
     RUN(name, (k3_persistent<128>), (unsigned)sm * k, 128, true);
   }
   RUN("pers4, 256 thr", (k3_persistent<256>), (unsigned)sm * 4, 256, true);
+  RUN("diag: read-only (no store)", (k3_diag<128, 1, 1>), blocks(128, 1), 128, true);
+  RUN("diag: loads + xor only", (k3_diag<128, 1, 2>), blocks(128, 1), 128, true);
+  RUN("diag: .L2::256B prefetch hint", (k3_diag<128, 1, 3>), blocks(128, 1), 128, true);
+  RUN("diag: st.global.cs stores", (k3_diag<128, 1, 4>), blocks(128, 1), 128, true);
+  RUN("diag: <=64 regs (8 CTAs/SM)", (k3_diag<128, 8, 0>), blocks(128, 1), 128, true);
+  RUN("diag: one contiguous stream*", (k3_onestream), (unsigned)sm * 8, 128, true);
   RUN("nowait (independent sets)", (k3_tile<128, 1, false>), blocks(128, 1), 128, true);
   RUN("nowait g8", (k3_tile<128, 2, false>), blocks(128, 2), 128, true);
   unsigned long long moved = 0;
