@@ -301,19 +301,6 @@ def run_ours(args):
     want_e2e = not fast
     host_ib = [eng.read_inbox(s) for s in range(e2e_steps if want_e2e else 0)]  # every rank runs the e2e leg on its own shard
 
-    # byte frames (include/mrq_packed8.h) of the same trace, one per slot, resident in HBM: tick modes 3 / 4 read the
-    # bytes themselves (no wide inbox, no unpack pass)
-    base0 = (st0["last_index"] - np.uint64(40)).astype(np.uint64)
-    n_escapes = 0
-    if mode >= 3:
-        pk = Pack8(st0["self_id"], base0, st0["term"], R)
-        eng.set_tick_mode(mode)
-        for t in range(nslots):  # in tick order: the window only moves forward
-            ib = host_ib[t] if t < len(host_ib) else eng.read_inbox(t)
-            w8, p8, wide8 = pk.frame(ib)
-            n_escapes += len(wide8)
-            eng.post_inbox_packed(w8, p8, wide8, slot=t, keep=True)
-
     def rewind(tick_mode, graph, write_through=1):
         eng.set_tick_mode(0)
         eng.import_state(st0)
@@ -381,6 +368,36 @@ def run_ours(args):
 
     graph = {"off": 0, "on": 1, "auto": 2}[args.graph]
     wt = 0 if args.write_back == "end" else 1
+    legs = {}
+
+    def leg_record(name, tm, gr, w_):
+        m_, r_, l_, _ = timed_leg(tm, gr, w_, nreps=3)
+        ib_name = {4: "compact", 3: "bytes", 0: "wide"}[tm]
+        tbl = tick_bytes_per_group(R, ib_name, K if (tm == 4 and gr != 0) else 1, bool(w_))
+        gbs = tbl["total"] * G / (m_ / K * 1e-3) / 1e9
+        peak_ = measured_peak_gbs()[0]
+        legs[name] = {"ticks_per_s": K / (m_ / 1e3), "us_per_tick": m_ / K * 1e3, "launches": l_,
+                      "bytes_per_group_tick": tbl["total"], "achieved_GBps": gbs, "frac": gbs / peak_,
+                      "us_per_tick_reps": [round(x / K * 1e3, 2) for x in r_]}
+
+    want_variants = rank == 0 and world == 1 and not fast and mode == 4
+    if want_variants:
+        # round 1's path — wide inbox, 64-bit state, a launch pair per tick — timed FIRST, on an L2 no later mode has
+        # marked (its evict-last lines would otherwise squat there: measured 91 us instead of 37 us per tick)
+        leg_record("wide_inbox_mode0", 0, graph, 1)
+    # byte frames (include/mrq_packed8.h) of the same trace, one per slot, resident in HBM: tick modes 3 / 4 read the
+    # bytes themselves (no wide inbox, no unpack pass)
+    base0 = (st0["last_index"] - np.uint64(40)).astype(np.uint64)
+    n_escapes = 0
+    if mode >= 3:
+        pk = Pack8(st0["self_id"], base0, st0["term"], R)
+        eng.set_tick_mode(mode)
+        for t in range(nslots):  # in tick order: the window only moves forward
+            ib = host_ib[t] if t < len(host_ib) else eng.read_inbox(t)
+            w8, p8, wide8 = pk.frame(ib)
+            n_escapes += len(wide8)
+            eng.post_inbox_packed(w8, p8, wide8, slot=t, keep=True)
+
     ms, ms_reps, launches_timed, clocks = timed_leg(mode, graph, wt, sample_clocks=True)
     ticks_per_s = K / (ms / 1e3)
     peak, peak_src = measured_peak_gbs()
@@ -433,21 +450,15 @@ def run_ours(args):
 
     if rank == 0 and world == 1:
         # the other ways to run the same K ticks, each [rewind, W, K] x 3 (median): what the batching and the layout buy
-        legs = {}
-        if mode == 4:
+        if want_variants:
             for name, (tm, gr, w_) in {"compact_per_tick_launches": (4, 0, 1), "compact_batched_write_through": (4, 2, 1),
-                                        "compact_batched_write_back_at_end": (4, 2, 0), "bytes_on_wide_state_mode3": (3, 0, 1),
-                                        "wide_inbox_mode0": (0, graph, 1)}.items():
-                m_, r_, l_, _ = timed_leg(tm, gr, w_, nreps=3)
-                ib_name = {4: "compact", 3: "bytes", 0: "wide"}[tm]
-                tbl = tick_bytes_per_group(R, ib_name, K if (tm == 4 and gr != 0) else 1, bool(w_))
-                gbs = tbl["total"] * G / (m_ / K * 1e-3) / 1e9
-                legs[name] = {"ticks_per_s": K / (m_ / 1e3), "us_per_tick": m_ / K * 1e3, "launches": l_,
-                              "bytes_per_group_tick": tbl["total"], "achieved_GBps": gbs, "frac": gbs / peak,
-                              "us_per_tick_reps": [round(x / K * 1e3, 2) for x in r_]}
+                                        "compact_batched_write_back_at_end": (4, 2, 0), "bytes_on_wide_state_mode3": (3, 0, 1)}.items():
+                leg_record(name, tm, gr, w_)
             rewind(mode, graph, wt)
         line["variants"] = legs
         line["roofline_quorum_kernel"] = bench_quorum_kernel(torch, eng, peak, K, W)
+        with Engine(262144, 7, seed=0x5EED0005, device=dev) as e7:  # BASELINE configs[4]'s shape: R = 7, 72 B per group
+            line["roofline_quorum_kernel_262144x7"] = bench_quorum_kernel(torch, e7, peak, K, W, G=262144, Rr=7)
     if rank == 0 and world == 1 and fast:
         line["e2e"] = None
     elif world == 1:
@@ -474,7 +485,7 @@ def run_ours(args):
         else:
             line["gather_check"] = None
         # end to end at N GPUs: every rank encodes and ships its shard's byte frames over its own PCIe link each tick
-        e2e = bench_e2e(eng, st0, base0, host_ib, commits_after, e2e_steps, dist=dist, torch=torch)
+        e2e = None if fast else bench_e2e(eng, st0, base0, host_ib, commits_after, e2e_steps, dist=dist, torch=torch)
         if rank == 0:
             line["e2e"] = e2e
     eng.close()
@@ -485,9 +496,12 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def bench_quorum_kernel(torch, eng, peak, K, W):
-    """The standalone quorum kernel (K3) on never-touched column sets: achieved = (8R+16) * G / launch time."""
-    G, stride = G_TOTAL, G_TOTAL
+def bench_quorum_kernel(torch, eng, peak, K, W, G=None, Rr=None):
+    """The standalone quorum kernel (K3) on never-touched column sets: achieved = (8R+16) * G / launch time.
+    (G, Rr) default to the headline shape; bench.py also runs BASELINE configs[4]'s shape, 262,144 x 7, on an engine of 7 replicas.)"""
+    G = G_TOTAL if G is None else G
+    R = globals()["R"] if Rr is None else Rr  # noqa: N806 — shadows the module constant on purpose inside this function
+    stride = G
     nsets = min(K + W, 40)
     gen = torch.Generator(device="cuda")
     gen.manual_seed(1234)

@@ -90,6 +90,12 @@ class FakeEngine:
     def _self_id(self):
         return self.o.export()["self_id"]
 
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
     def import_state(self, st):
         self.o.import_state(st)
 

@@ -64,6 +64,40 @@ def test_config5_full_size_262144x7():
     assert c["step_downs"] > 10000
 
 
+def test_config5_spec_length_262144x7_4096_ticks_compared_every_tick():
+    """BASELINE configs[4] exactly as SURVEY §8d states it: 262,144 groups x 7 replicas, 20 % lagging followers, leader
+    churn, 4,096 ticks, `term / vote / role / committed` bit-equal to the oracle after EVERY tick.  Engine and oracle each
+    generate the tick's trace from their own state (same generator: include/mrq_trace.h), so a divergence of either
+    shows at once; the full state, the out word and the generated inbox are compared every 256th tick as well."""
+    G, R, T = 262144, 7, 4096
+    nt = oracle.hw_threads()
+    p = preset_trace(5)
+    po = _orc_params(p)
+    eng = Engine(G, R, seed=0x5EED0005)
+    orc = Oracle(G, R, seed=0x5EED0005)
+    cols = ("term", "vote", "role", "committed")
+    for t in range(T):
+        eng.gen_trace(p, t, slot=0)
+        if t % 256 == 0:
+            assert_inbox_equal(eng.read_inbox(0), orc.gen_trace(po, t, nthreads=nt), f"tick {t}")
+        eng.tick(0)
+        orc.tick(orc.gen_trace(po, t, nthreads=nt), nthreads=nt)
+        es, os_ = eng.export_state(columns=cols), orc.export()
+        for k in cols:
+            if not np.array_equal(es[k], os_[k]):
+                bad = np.flatnonzero(es[k] != os_[k])
+                raise AssertionError(f"tick {t}: column {k} differs on {len(bad)} groups, first {bad[0]}: "
+                                     f"engine {es[k][bad[0]]} oracle {os_[k][bad[0]]}")
+        if t % 256 == 255 or t == T - 1:
+            assert_state_equal(eng.export_state(), os_, f"tick {t}")
+            np.testing.assert_array_equal(eng.sync_out(), os_["out"], err_msg=f"out word, tick {t}")
+    c = eng.counters()
+    s = orc.export()
+    assert c["errors"] == 0 and orc.errors == 0
+    assert c["step_downs"] > 200000 and c["elections_won"] > 200000 and (s["role"] == LEADER).mean() > 0.5
+    eng.close()
+
+
 @pytest.mark.parametrize("R", [1, 2, 3, 4, 5, 6, 7, 8])
 def test_all_replica_counts(R):
     run_trace_parity(1000, R, 5, 200, seed=77 + R)

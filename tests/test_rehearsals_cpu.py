@@ -37,7 +37,7 @@ def _bench_on_the_double(monkeypatch, eng_cls, G=2048):
     monkeypatch.setattr(packed, "PinnedArray", FakePinned)
     monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
-    monkeypatch.setattr(bench, "bench_quorum_kernel", lambda *a: {"bound": "hbm", "achieved": 1.0, "peak": 2.0, "frac": 0.5})
+    monkeypatch.setattr(bench, "bench_quorum_kernel", lambda *a, **k: {"bound": "hbm", "achieved": 1.0, "peak": 2.0, "frac": 0.5})
     monkeypatch.setattr(bench, "cpu_reference_ticks", lambda *a, **k: (80.0, 8, 3, 0.04, None))
     monkeypatch.setenv("MRQ_BENCH_REPS", "2")
     monkeypatch.delenv("WORLD_SIZE", raising=False)

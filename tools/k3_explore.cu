@@ -59,7 +59,8 @@ __device__ __forceinline__ unsigned quad(const QuorumArgs &a, uint64_t i) {
 
 // ---- diagnostic variants: what bounds the 7-stream read + 1-stream write at this size? -----------------------------
 // MODE 0: the product body; 1: no store (read-only); 2: loads + xor only (no selection network, no store);
-// 3: loads carry the .L2::256B prefetch hint; 4: stores carry an evict-first policy (st.global.cs)
+// 3: loads carry the .L2::256B prefetch hint; 4: stores carry an evict-first policy (st.global.cs);
+// 5: 3 + 4 + one 256-bit store per quad when all four groups moved (what the product's ldg256 form now does)
 __device__ __forceinline__ u64x4 ld_v4_pf256(const uint64_t *p) {
   u64x4 r;
   asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.b64 {%0, %1, %2, %3}, [%4];"
@@ -71,9 +72,9 @@ template <int MODE>
 __device__ __forceinline__ unsigned quad_x(const QuorumArgs &a, uint64_t i) {
   u64x4 mv[R];
 #pragma unroll
-  for (int r = 0; r < R; ++r) mv[r] = MODE == 3 ? ld_v4_pf256(a.match + (uint64_t)r * a.gs + i) : ld_stream_v4(a.match + (uint64_t)r * a.gs + i);
+  for (int r = 0; r < R; ++r) mv[r] = (MODE == 3 || MODE == 5) ? ld_v4_pf256(a.match + (uint64_t)r * a.gs + i) : ld_stream_v4(a.match + (uint64_t)r * a.gs + i);
   const u64x4 cm = ld_plain_v4(a.committed + i);
-  const u64x4 gt = MODE == 3 ? ld_v4_pf256(a.term_start + i) : ld_stream_v4(a.term_start + i);
+  const u64x4 gt = (MODE == 3 || MODE == 5) ? ld_v4_pf256(a.term_start + i) : ld_stream_v4(a.term_start + i);
   unsigned nmoved = 0;
   if (MODE == 2) {
     uint64_t x = 0;
@@ -84,6 +85,26 @@ __device__ __forceinline__ unsigned quad_x(const QuorumArgs &a, uint64_t i) {
       x ^= cm.v[k] ^ gt.v[k];
     }
     return (unsigned)(x == 0x123456789ull);
+  }
+  if (MODE == 5) {
+    u64x4 out;
+    bool mvd[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint64_t m[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) m[r] = mv[r].v[k];
+      out.v[k] = quorum_commit_one<R>(m, cm.v[k], gt.v[k], mvd[k]);
+      nmoved += mvd[k];
+    }
+    if (nmoved == 4u) {
+      st_stream_v4(a.committed + i, out);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (mvd[k]) st_stream_u64(a.committed + i + k, out.v[k]);
+    }
+    return nmoved;
   }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -258,6 +279,8 @@ int main(int argc, char **argv) {
   RUN("diag: loads + xor only", (k3_diag<128, 1, 2>), blocks(128, 1), 128, true);
   RUN("diag: .L2::256B prefetch hint", (k3_diag<128, 1, 3>), blocks(128, 1), 128, true);
   RUN("diag: st.global.cs stores", (k3_diag<128, 1, 4>), blocks(128, 1), 128, true);
+  RUN("diag: pf256 + cs + v4 store", (k3_diag<128, 1, 5>), blocks(128, 1), 128, true);
+  RUN("diag: same, 256 threads", (k3_diag<256, 1, 5>), blocks(256, 1), 256, true);
   RUN("diag: <=64 regs (8 CTAs/SM)", (k3_diag<128, 8, 0>), blocks(128, 1), 128, true);
   RUN("diag: one contiguous stream*", (k3_onestream), (unsigned)sm * 8, 128, true);
   RUN("nowait (independent sets)", (k3_tile<128, 1, false>), blocks(128, 1), 128, true);
