@@ -276,7 +276,7 @@ def run_ours(args):
     mode = {"compact": 4, "bytes": 3, "wide": 0}[inbox]
     fast = os.environ.get("MRQ_BENCH_FAST") == "1"  # profiling runs (ncu): kernels only, no CPU legs
 
-    eng = Engine(G, R, seed=SEED, group_base=base, device=dev, inbox_slots=nslots)
+    eng = Engine(G, R, seed=SEED, group_base=base, device=dev, inbox_slots=nslots + 1)  # + one slot for the post-roll's empty inbox
     if args.l2 is not None:
         eng.set_l2_policy(args.l2)
     st0 = steady_state(G, R, base, SEED)
@@ -323,10 +323,29 @@ def run_ours(args):
         # issue the per-tick launches
         eng.tick_many([(first_slot + k) % nslots for k in range(n)])
 
+    def post_roll(med_ms):
+        n_more = max(4, min(20000, int(2.0 / max(1e-6, 8 * med_ms / K * 1e-3))))  # the same count on every rank
+        if eng_mode() >= 3:
+            zero = np.zeros((R - 1, G), np.uint8)
+            eng.post_inbox_packed(zero, np.zeros(G, np.uint8), (), slot=nslots, keep=True)
+            for _ in range(n_more):
+                eng.tick_many([nslots] * 8)
+        else:
+            eng.clear_inbox(nslots)
+            for _ in range(n_more):
+                eng.tick_many([nslots] * 8)
+        eng.synchronize()
+
+    cur_mode = [0]
+
+    def eng_mode():
+        return cur_mode[0]
+
     def timed_leg(tick_mode, graph, write_through=1, nreps=reps, sample_clocks=False):
         """`nreps` repetitions of: rewind, W warm-up ticks, then EXACTLY K ticks between barrier + synchronize, CUDA
         events on the engine's stream, max over ranks.  Returns (median ms for K ticks, all reps, launches, clocks)."""
         out_ms, launches, clocks = [], 0, None
+        cur_mode[0] = tick_mode
         rewind(tick_mode, graph, write_through)  # rehearsal (untimed): graphs captured, descriptor tables built
         run_ticks(W, 0)
         run_ticks(K, W)
@@ -354,11 +373,10 @@ def run_ours(args):
             out_ms.append(ms)
         med = float(np.median(out_ms))
         if sampler is not None:
-            # keep the GPU under this load ~2 s more so the sampler sees it (same count on every rank)
-            n_more = max(4, min(40000, int(2.0 / max(1e-6, 8 * med / K * 1e-3))))
-            for _ in range(n_more):
-                run_ticks(8, 0)
-            eng.synchronize()
+            # keep the GPU under the tick kernels ~2 s more so that the sampler sees it at the clocks of the timed region
+            # (the region itself lasts a fraction of a millisecond).  Replaying the trace's slots without a rewind would
+            # feed stale acks to a state that has moved on, so the post-roll ticks EMPTY inboxes (timers only) instead.
+            post_roll(med)
             clocks = sampler.finish()
         if dist is not None:
             lt = torch.tensor([launches], dtype=torch.int64, device="cuda")

@@ -189,3 +189,104 @@ func (e *Engine) QuorumCommit() error {
 	}
 	return nil
 }
+
+// ---- the dense multi-raft path: byte frames on compact state (tick mode 4) ----------------------------------
+// A host that leads (or follows) a million groups does not post messages one by one: per tick it encodes the
+// whole inbox into ONE byte frame — R-1 sender bytes + 1 proposal byte per group (include/mrq_packed8.h) — ships
+// it, ticks, and drains one byte per group (that tick's commit advance).  The frame buffers must be C memory
+// (cgo: C may not keep Go pointers across calls, and the copy is asynchronous): AllocPinned / FreePinned.
+
+// SetTickMode selects how Tick runs (include/mrq.h mrq_set_tick_mode); 4 = byte frames on compact state.
+func (e *Engine) SetTickMode(mode int) error {
+	if rc := C.mrq_set_tick_mode(e.h, C.int(mode)); rc != 0 {
+		return lastErr(e.h)
+	}
+	return nil
+}
+
+// AllocPinned returns n bytes of page-locked C memory as a Go slice (not managed by the Go GC).
+func AllocPinned(n int) []byte {
+	p := C.mrq_alloc_pinned(C.size_t(n))
+	if p == nil {
+		return nil
+	}
+	return unsafe.Slice((*byte)(p), n)
+}
+
+// FreePinned releases a slice obtained from AllocPinned.
+func FreePinned(b []byte) {
+	if len(b) > 0 {
+		C.mrq_free_pinned(unsafe.Pointer(&b[0]))
+	}
+}
+
+// SetPackedBase hands the engine the window bases the frame builder starts from (one per group).
+func (e *Engine) SetPackedBase(baseIndex, baseTerm []uint64) error {
+	rc := C.mrq_set_packed_base(e.h, (*C.uint64_t)(unsafe.Pointer(&baseIndex[0])), (*C.uint64_t)(unsafe.Pointer(&baseTerm[0])))
+	if rc != 0 {
+		return lastErr(e.h)
+	}
+	return nil
+}
+
+// PostFrame starts the asynchronous copy of one byte frame (word: [R-1][G] in pinned memory, prop8: [G]) into
+// inbox slot `slot`; wide carries the few messages that did not fit a byte.  Returns at once: the copy overlaps
+// whatever tick is running.
+func (e *Engine) PostFrame(slot uint32, word, prop8 []byte, wide []Msg) error {
+	var v C.mrq_inbox_packed
+	v.word = unsafe.Pointer(&word[0])
+	v.prop_count8 = (*C.uint8_t)(unsafe.Pointer(&prop8[0]))
+	v.word_bits = 8
+	var buf []C.mrq_msg
+	if len(wide) > 0 {
+		buf = make([]C.mrq_msg, len(wide))
+		for i, m := range wide {
+			buf[i].group, buf[i].term, buf[i].index = C.uint64_t(m.Group), C.uint64_t(m.Term), C.uint64_t(m.Index)
+			buf[i].logterm, buf[i].commit = C.uint64_t(m.LogTerm), C.uint64_t(m.Commit)
+			buf[i]._type, buf[i].from = C.uint8_t(m.Type), C.uint8_t(m.From)
+		}
+		v.wide, v.n_wide = &buf[0], C.size_t(len(buf))
+	}
+	if rc := C.mrq_post_inbox_packed(e.h, C.uint32_t(slot), &v); rc != 0 {
+		return lastErr(e.h)
+	}
+	return nil
+}
+
+// DrainTick enqueues the copy of the last tick's commit advances (one byte per group, 255 = read the index in
+// full with Ready) into pinned memory; Wait blocks until THAT copy has landed.
+func (e *Engine) DrainTick(deltaPinned []byte) error {
+	if rc := C.mrq_drain_tick_deltas(e.h, (*C.uint8_t)(unsafe.Pointer(&deltaPinned[0]))); rc != 0 {
+		return lastErr(e.h)
+	}
+	return nil
+}
+
+// Wait blocks until the drain enqueued last has landed on the host.
+func (e *Engine) Wait() error {
+	if rc := C.mrq_drain_wait(e.h); rc != 0 {
+		return lastErr(e.h)
+	}
+	return nil
+}
+
+// TickMany runs the ticks of the given inbox slots in ONE pair of kernel launches (tick mode 4: every thread
+// carries its groups' state in registers from tick to tick) — a backlog of posted frames, or a replay.
+func (e *Engine) TickMany(slots []uint32) error {
+	if len(slots) == 0 {
+		return nil
+	}
+	if rc := C.mrq_tick_many(e.h, (*C.uint32_t)(unsafe.Pointer(&slots[0])), C.uint32_t(len(slots))); rc != 0 {
+		return lastErr(e.h)
+	}
+	return nil
+}
+
+// SlotOutputs reads the out words and commit advances of the tick that consumed `slot` in the last TickMany.
+func (e *Engine) SlotOutputs(slot uint32, out []uint32, delta []byte) error {
+	rc := C.mrq_sync_slot_outputs(e.h, C.uint32_t(slot), (*C.uint32_t)(unsafe.Pointer(&out[0])), (*C.uint8_t)(unsafe.Pointer(&delta[0])))
+	if rc != 0 {
+		return lastErr(e.h)
+	}
+	return nil
+}

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmrq.so")
+LIB_PATH = os.environ.get("MRQ_LIB_PATH") or os.path.join(_HERE, "libmrq.so")  # (MRQ_LIB_PATH: development builds of the same ABI)
 
 MRQ_ABI_VERSION = 1
 MRQ_MAX_REPLICAS = 8

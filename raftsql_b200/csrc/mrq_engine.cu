@@ -358,9 +358,16 @@ int launch_tick4(mrq_engine *e, const uint32_t *slots, uint32_t n) {
     e->last_out = e->out_slot[slots[n - 1]];
     e->last_delta = e->delta_slot[slots[n - 1]];
   }
-  const unsigned nb = nblocks(e->gs / 4, kQuadThreads);
+  const uint64_t quads = e->gs / 4;
+  const uint64_t want = 4ull * (uint64_t)g_sm_count;  // enough CTAs to give every SM its resident set
   cudaError_t lst = cudaErrorInvalidValue;
-  MRQ_DISPATCH_R(e->R, lst = launch_pdl(tick_fast4_kernel<kR>, nb, kQuadThreads, 0, e->stream, A));
+  if (quads / 128 >= want) {
+    MRQ_DISPATCH_R(e->R, lst = launch_pdl(tick_fast4_kernel<kR, 128>, nblocks(quads, 128), 128, 0, e->stream, A));
+  } else if (quads / 64 >= want) {
+    MRQ_DISPATCH_R(e->R, lst = launch_pdl(tick_fast4_kernel<kR, 64>, nblocks(quads, 64), 64, 0, e->stream, A));
+  } else {
+    MRQ_DISPATCH_R(e->R, lst = launch_pdl(tick_fast4_kernel<kR, 32>, nblocks(quads, 32), 32, 0, e->stream, A));
+  }
   CK(e, lst);
   unsigned nslow = (unsigned)g_sm_count * 6u;
   const unsigned nb1 = nblocks(e->G, kTickThreads);

@@ -1483,6 +1483,28 @@ __device__ __forceinline__ uint32_t slow_group_ticks_c(const Tick4Args &A, const
 }
 
 #ifndef MRQ_HOST_EMULATION
+// The complete compact step, OUT OF LINE for the quad kernel: the hot step covers the steady state, so this body runs for
+// a few groups per tick — inlined four times it only bloated the loop (2,824 SASS instructions, 11 % of the issue
+// slots lost to instruction fetch).  By value in, by value out: the caller's registers stay registers.
+template <int R>
+struct CStepResult {
+  CGroup<R> g;
+  uint32_t out, adv, dirty, slow;
+};
+template <int R>
+__device__ __noinline__ CStepResult<R> compact_step_cold(CGroup<R> g, uint32_t flag, uint32_t w0123, uint32_t w4567, uint32_t nprop,
+                                                         uint32_t gate, uint32_t et, uint32_t ht) {
+  uint32_t wb[R > 1 ? R - 1 : 1];
+#pragma unroll
+  for (int j = 0; j < (R > 1 ? R - 1 : 1); ++j) wb[j] = ((j < 4 ? w0123 : w4567) >> (8 * (j & 3))) & 0xFFu;  // the group's R-1 bytes, packed
+  CStepResult<R> r;
+  r.slow = compact_step<R>(g, flag, wb, nprop, gate, et, ht, r.out, r.adv, r.dirty) ? 1u : 0u;
+  r.g = g;
+  return r;
+}
+#endif
+
+#ifndef MRQ_HOST_EMULATION
 // 128-bit / 256-bit column accesses with the L2 residency policy of the scalar kernels
 struct u32x4 {
   uint32_t v[4];
@@ -1506,10 +1528,13 @@ __device__ __forceinline__ void st_v2u64_p(uint64_t *p, uint64_t a, uint64_t b, 
   asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.u64 [%0], {%1, %2}, %3;" ::"l"(p), "l"(a), "l"(b), "l"(pol) : "memory");
 }
 
-static constexpr int kQuadThreads = 128;  // x 4 groups per thread = 512 groups per CTA
-
-template <int R>
-__global__ void __launch_bounds__(kQuadThreads, (R <= 5 ? 4 : 3)) tick_fast4_kernel(const Tick4Args A) {
+// THREADS x 4 groups per CTA.  128 for big shards; a shard of a many-GPU job is too small to fill 148 SMs with 512-group
+// CTAs (131,072 groups = 256 of them), so the host picks 64 or 32 threads there: same register budget per SM, more CTAs.
+template <int R, int THREADS>
+#ifndef MRQ_T4_THREADS_PER_SM
+#define MRQ_T4_THREADS_PER_SM 512  // resident threads per SM the register budget is cut for (development knob)
+#endif
+__global__ void __launch_bounds__(THREADS, (R <= 5 ? MRQ_T4_THREADS_PER_SM : 384) / THREADS) tick_fast4_kernel(const Tick4Args A) {
   const TickArgs &a = A.t;
   pdl_launch_dependents();
   const uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4u;
@@ -1581,8 +1606,20 @@ __global__ void __launch_bounds__(kQuadThreads, (R <= 5 ? 4 : 3)) tick_fast4_ker
       uint32_t o, adv, dirty;
       const uint32_t np = (pb >> (8 * k)) & 0xFFu;
       bool slow = false;
-      if (!compact_hot_step<R>(g[k], flag[k], wk, np, gate.v[k], a.election_tick, a.heartbeat_tick, o, adv, dirty))
-        slow = compact_step<R>(g[k], flag[k], wk, np, gate.v[k], a.election_tick, a.heartbeat_tick, o, adv, dirty);
+      if (!compact_hot_step<R>(g[k], flag[k], wk, np, gate.v[k], a.election_tick, a.heartbeat_tick, o, adv, dirty)) {
+        uint32_t p0 = 0, p1 = 0;  // the group's bytes, four to a word
+#pragma unroll
+        for (int j = 0; j < R - 1; ++j) {
+          if (j < 4) p0 |= wk[j] << (8 * j);
+          else p1 |= wk[j] << (8 * (j - 4));
+        }
+        const CStepResult<R> cr = compact_step_cold<R>(g[k], flag[k], p0, p1, np, gate.v[k], a.election_tick, a.heartbeat_tick);
+        g[k] = cr.g;
+        o = cr.out;
+        adv = cr.adv;
+        dirty = cr.dirty;
+        slow = cr.slow != 0u;
+      }
       if (slow) {
         newly |= 1u << k;
       } else {

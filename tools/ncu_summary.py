@@ -14,7 +14,7 @@ import sys
 from collections import Counter, defaultdict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OUT = os.path.join(ROOT, "profiles")
+OUT = os.environ.get("NCU_SUMMARY_OUT") or os.path.join(ROOT, "profiles")  # (on the GPU box: a directory under gpurun_out/)
 
 RAW = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__cycles_active.avg.pct_of_peak_sustained_elapsed",
