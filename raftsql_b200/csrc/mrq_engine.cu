@@ -295,8 +295,8 @@ void fill_tick_args(mrq_engine *e, TickArgs &a) {
   a.gather_prime = e->gather_prime ? 1u : 0u;
   a.l2_policy = e->l2_policy ? 1u : 0u;
   for (uint32_t p = 0; p < 8; ++p) {
-    a.peer_lo[p] = reinterpret_cast<uint32_t *>(e->peer_gather[p]);
-    a.peer_hi[p] = a.peer_lo[p] ? a.peer_lo[p] + (size_t)e->world * e->G : nullptr;
+    a.peer_full[p] = e->peer_gather[p];  // [world * G] full indices, then [world * G] low bytes (see TickArgs)
+    a.peer_lo[p] = a.peer_full[p] ? reinterpret_cast<uint8_t *>(a.peer_full[p] + (size_t)e->world * e->G) : nullptr;
   }
   a.slow_list = e->slow_list;
   a.slow_count = e->slow_count + (e->slow_parity & 1u);
@@ -359,14 +359,16 @@ int launch_tick4(mrq_engine *e, const uint32_t *slots, uint32_t n) {
     e->last_delta = e->delta_slot[slots[n - 1]];
   }
   const uint64_t quads = e->gs / 4;
-  const uint64_t want = 4ull * (uint64_t)g_sm_count;  // enough CTAs to give every SM its resident set
   cudaError_t lst = cudaErrorInvalidValue;
-  if (quads / 128 >= want) {
-    MRQ_DISPATCH_R(e->R, lst = launch_pdl(tick_fast4_kernel<kR, 128>, nblocks(quads, 128), 128, 0, e->stream, A));
-  } else if (quads / 64 >= want) {
-    MRQ_DISPATCH_R(e->R, lst = launch_pdl(tick_fast4_kernel<kR, 64>, nblocks(quads, 64), 64, 0, e->stream, A));
+  // Big shards: four groups per thread (128-bit column accesses, a quarter of the instructions per group).  Small shards
+  // (a many-GPU job's): one group per thread — the GPU needs warps in flight more than it needs wide accesses.
+  const char *gpt_env = getenv("MRQ_T4_GPT");  // development / test knob: force 1 or 4 groups per thread
+  const int force_gpt = gpt_env ? atoi(gpt_env) : 0;
+  const bool one_per_thread = force_gpt == 1 || (force_gpt != 4 && quads < 2048ull * (uint64_t)g_sm_count / 4);
+  if (one_per_thread) {
+    MRQ_DISPATCH_R(e->R, lst = launch_pdl(tick_fast1_kernel<kR>, nblocks(e->gs, 128), 128, 0, e->stream, A));
   } else {
-    MRQ_DISPATCH_R(e->R, lst = launch_pdl(tick_fast4_kernel<kR, 32>, nblocks(quads, 32), 32, 0, e->stream, A));
+    MRQ_DISPATCH_R(e->R, lst = launch_pdl(tick_fast4_kernel<kR, 128>, nblocks(quads, 128), 128, 0, e->stream, A));
   }
   CK(e, lst);
   unsigned nslow = (unsigned)g_sm_count * 6u;
@@ -1307,7 +1309,7 @@ int mrq_tick_many(mrq_engine *e, const uint32_t *slots, uint32_t n) {
     bool all8 = true;
     for (uint32_t k = 0; k < n; ++k) all8 = all8 && slot_has_frame8(e, slots[k]);
     if (all8) {
-      constexpr uint32_t kMaxBatch = 4096;
+      constexpr uint32_t kMaxBatch = kMaxTicksPerLaunch;
       for (uint32_t k = 0; k < n; k += kMaxBatch) {
         int r = launch_tick4(e, slots + k, n - k < kMaxBatch ? n - k : kMaxBatch);
         if (r) return r;
@@ -1640,7 +1642,8 @@ static int ensure_gather(mrq_engine *e, uint32_t world) {
   CK(e, cudaStreamSynchronize(e->stream));
   if (e->gathered) CK(e, cudaFree(e->gathered));
   e->gathered = nullptr;
-  return dalloc(e, &e->gathered, (size_t)world * (e->G ? e->G : 1));
+  const size_t n = (size_t)world * (e->G ? e->G : 1);
+  return dalloc(e, &e->gathered, n + (n + 7) / 8);  // n full indices + n low bytes (the peer-store layout); NCCL uses the first n
 }
 
 int mrq_comm_init(mrq_engine *e, const uint8_t id[MRQ_COMM_ID_BYTES], uint32_t rank, uint32_t world) {
@@ -1715,11 +1718,12 @@ int mrq_sync_gathered(mrq_engine *e, uint64_t *gathered_out) {
   CK(e, cudaSetDevice(e->device));
   const size_t n = (size_t)e->world * e->G;
   if (e->comm_mode == 1 && e->ipc_attached) {
-    // peer-store layout: low words [n] then high words [n]; stitch them back into 64-bit indices
-    std::vector<uint32_t> tmp(2 * n);
-    CK(e, cudaMemcpyAsync(tmp.data(), e->gathered, n * 8, cudaMemcpyDeviceToHost, e->stream));
+    // peer-store layout: full indices [n] (as of the last time anything above the low byte changed) then low bytes [n]
+    std::vector<uint8_t> lo(n);
+    CK(e, cudaMemcpyAsync(gathered_out, e->gathered, n * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaMemcpyAsync(lo.data(), reinterpret_cast<const uint8_t *>(e->gathered + n), n, cudaMemcpyDeviceToHost, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
-    for (size_t k = 0; k < n; ++k) gathered_out[k] = ((uint64_t)tmp[n + k] << 32) | tmp[k];
+    for (size_t k = 0; k < n; ++k) gathered_out[k] = (gathered_out[k] & ~0xFFull) | lo[k];
     return MRQ_OK;
   }
   CK(e, cudaMemcpyAsync(gathered_out, e->gathered, n * 8, cudaMemcpyDeviceToHost, e->stream));

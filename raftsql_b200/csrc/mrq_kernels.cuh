@@ -79,9 +79,12 @@ struct TickArgs {
   uint64_t *tick_next;
   uint32_t election_tick, heartbeat_tick;
   // Fused peer-store all-gather (multi-GPU mode 1): the commit index of every group this rank owns is stored
-  // straight into every rank's gather buffer over NVLink.  To halve the bytes on the wire the buffer is split
-  // into low words (stored every tick) and high words (stored only when they change, or when priming).
-  uint32_t *peer_lo[8], *peer_hi[8];
+  // straight into every rank's gather buffer over NVLink.  NVLink bytes are what bounds a many-GPU job (N = 8:
+  // 131,072 groups x 7 peers per GPU per tick), so the buffer is split: the LOW BYTE of every index is stored every
+  // tick, the full 64-bit index only when anything above the low byte changed (every ~170 ticks per group at this
+  // trace's commit rate) or when priming: ~1.05 B per group-tick per peer instead of 8.  mrq_sync_gathered stitches.
+  uint8_t *peer_lo[8];
+  uint64_t *peer_full[8];
   uint32_t world, rank, gather_prime;
   uint32_t l2_policy;  // 1: inbox evict-first / state evict-last hints in the fast kernel (see l2_policy())
   // fast/slow split: groups the fast kernel leaves untouched are listed here for the slow kernel
@@ -95,6 +98,18 @@ struct TickArgs {
 // and flushed (wait).  No-ops when the launch did not ask for programmatic serialization.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// one group's commit index into every rank's gather buffer (see TickArgs)
+template <class Args>
+__device__ __forceinline__ void gather_store(const Args &a, const uint64_t i, const uint64_t committed, const uint64_t committed0) {
+  const uint64_t at = (uint64_t)a.rank * a.G + i;
+  const bool full = a.gather_prime || ((committed ^ committed0) >> 8) != 0;
+#pragma unroll 1
+  for (uint32_t p = 0; p < a.world; ++p) {
+    a.peer_lo[p][at] = (uint8_t)committed;
+    if (full) a.peer_full[p][at] = committed;
+  }
+}
 
 // ---- cache-hinted accessors ---------------------------------------------------------------------
 // (MRQ_HOST_EMULATION is defined only by tests/cpp/tick_host_test.cpp, which compiles the per-group tick
@@ -648,14 +663,7 @@ __device__ __forceinline__ uint32_t general_group_tick(const TickArgs &a, const 
         if (g.dirty & (D_MATCH0 << r)) st_state(a.s.match + (uint64_t)r * a.gs + i, g.match[r]);
     }
     st_state_u32(a.s.out + i, g.out);
-    if (a.world > 1) {  // fused all-gather: store the commit index straight into every rank's buffer
-#pragma unroll 1
-      for (uint32_t p = 0; p < a.world; ++p) {
-        a.peer_lo[p][(uint64_t)a.rank * a.G + i] = (uint32_t)g.committed;
-        if (a.gather_prime || (g.committed >> 32) != (committed0 >> 32))
-          a.peer_hi[p][(uint64_t)a.rank * a.G + i] = (uint32_t)(g.committed >> 32);
-      }
-    }
+    if (a.world > 1) gather_store(a, i, g.committed, committed0);  // fused all-gather
     ev = g.ev;
   }
   return ev;
@@ -805,14 +813,7 @@ __device__ __forceinline__ void fast_group_tick(const TickArgs &a, const uint64_
       for (int r = 0; r < R; ++r)
         if (wdirty & (D_MATCH0 << r)) st_state_p(a.s.match + (uint64_t)r * a.gs + i, match[r], pol_keep);
       st_state_u32_p(a.s.out + i, out, pol_stream);
-      if (a.world > 1) {  // fused all-gather: store the commit index straight into every rank's buffer
-#pragma unroll 1
-        for (uint32_t p = 0; p < a.world; ++p) {
-          a.peer_lo[p][(uint64_t)a.rank * a.G + i] = (uint32_t)committed;
-          if (a.gather_prime || (committed >> 32) != (committed0 >> 32))
-            a.peer_hi[p][(uint64_t)a.rank * a.G + i] = (uint32_t)(committed >> 32);
-        }
-      }
+      if (a.world > 1) gather_store(a, i, committed, committed0);  // fused all-gather
     }
   }
 }
@@ -971,14 +972,7 @@ __device__ __forceinline__ void fast_group_tick8(const TickArgs &a, const Inbox8
       for (int r = 0; r < R; ++r)
         if (wdirty & (D_MATCH0 << r)) st_state_p(a.s.match + (uint64_t)r * a.gs + i, match[r], pol_keep);
       st_state_u32_p(a.s.out + i, out, pol_stream);
-      if (a.world > 1) {
-#pragma unroll 1
-        for (uint32_t p = 0; p < a.world; ++p) {
-          a.peer_lo[p][(uint64_t)a.rank * a.G + i] = (uint32_t)committed;
-          if (a.gather_prime || (committed >> 32) != (committed0 >> 32))
-            a.peer_hi[p][(uint64_t)a.rank * a.G + i] = (uint32_t)(committed >> 32);
-        }
-      }
+      if (a.world > 1) gather_store(a, i, committed, committed0);
     }
   }
 }
@@ -1448,6 +1442,7 @@ struct TickDesc {
   uint32_t *out;         // [gs] this tick's out words
   uint8_t *delta;        // [gs] this tick's commit advances, saturating at 255 ("read the index in full")
 };
+static constexpr uint32_t kMaxTicksPerLaunch = 96;  // descriptors of one launch live in shared memory (96 x 88 B)
 struct Tick4Args {
   TickArgs t;  // t.in and t.s.out are per tick (TickDesc)
   CompactView c;
@@ -1575,24 +1570,36 @@ __global__ void __launch_bounds__(THREADS, (R <= 5 ? MRQ_T4_THREADS_PER_SM : 384
   u32x4 iblo{};
   if (gather) iblo = ld_v4u32_p(A.c.iblo + i, pol_keep);
   uint32_t acc_dirty = 0, ncommit = 0;
-  // the first tick's frame; every later frame is loaded one tick ahead of its use
-  TickDesc d = A.descs ? A.descs[0] : A.d0;
-  uint32_t wb[R > 1 ? R - 1 : 1], pb;
+  // Frames are loaded TWO ticks ahead of their use (a shard of a many-GPU job has too few warps per SM to hide a load
+  // behind other warps: the thread's own next ticks have to cover it), and the per-tick descriptors come from shared
+  // memory, so that a frame load never waits for a descriptor load first.
+  __shared__ TickDesc s_desc[kMaxTicksPerLaunch];
+  if (A.descs) {
+    const uint32_t nw = A.nticks * (uint32_t)(sizeof(TickDesc) / 4);
+    for (uint32_t w = threadIdx.x; w < nw; w += THREADS) reinterpret_cast<uint32_t *>(s_desc)[w] = reinterpret_cast<const uint32_t *>(A.descs)[w];
+  } else if (threadIdx.x == 0) {
+    s_desc[0] = A.d0;
+  }
+  __syncthreads();
+  constexpr int NW = R > 1 ? R - 1 : 1;
+  auto load_frame = [&](uint32_t t, uint32_t (&w)[NW], uint32_t &pbytes) {
+    const TickDesc &dd = s_desc[t];
 #pragma unroll
-  for (int j = 0; j < R - 1; ++j) wb[j] = ld_stream_u32_p(reinterpret_cast<const uint32_t *>(d.word8 + (uint64_t)j * a.gs + i), pol_stream);
-  if (R == 1) wb[0] = 0;
-  pb = d.prop8 ? ld_stream_u32_p(reinterpret_cast<const uint32_t *>(d.prop8 + i), pol_stream) : 0u;
+    for (int j = 0; j < R - 1; ++j) w[j] = ld_stream_u32_p(reinterpret_cast<const uint32_t *>(dd.word8 + (uint64_t)j * a.gs + i), pol_stream);
+    if (R == 1) w[0] = 0;
+    pbytes = dd.prop8 ? ld_stream_u32_p(reinterpret_cast<const uint32_t *>(dd.prop8 + i), pol_stream) : 0u;
+  };
+  uint32_t wb[NW], pb, wb1[NW], pb1 = 0;
+  load_frame(0, wb, pb);
+#pragma unroll
+  for (int j = 0; j < NW; ++j) wb1[j] = 0;
+  if (A.nticks > 1) load_frame(1, wb1, pb1);
   for (uint32_t t = 0; t < A.nticks; ++t) {
-    uint32_t nwb[R > 1 ? R - 1 : 1], npb = 0;
-    TickDesc dn = d;
-    if (t + 1 < A.nticks) {  // prefetch the next tick's frame while this one is computed
-      dn = A.descs[t + 1];
+    uint32_t wb2[NW], pb2 = 0;
 #pragma unroll
-      for (int j = 0; j < R - 1; ++j)
-        nwb[j] = ld_stream_u32_p(reinterpret_cast<const uint32_t *>(dn.word8 + (uint64_t)j * a.gs + i), pol_stream);
-      npb = dn.prop8 ? ld_stream_u32_p(reinterpret_cast<const uint32_t *>(dn.prop8 + i), pol_stream) : 0u;
-    }
-    if (R == 1) nwb[0] = 0;
+    for (int j = 0; j < NW; ++j) wb2[j] = 0;
+    if (t + 2 < A.nticks) load_frame(t + 2, wb2, pb2);
+    const TickDesc &d = s_desc[t];
     u32x4 outw{};
     uint32_t dw = 0, newly = 0, tdirty = 0;
     u32x4 lo_old{};
@@ -1649,33 +1656,35 @@ __global__ void __launch_bounds__(THREADS, (R <= 5 ? MRQ_T4_THREADS_PER_SM : 384
     if (active) {
       st_v4u32_p(d.out + i, outw, pol_stream);
       st_state_u32_p(reinterpret_cast<uint32_t *>(d.delta + i), dw, pol_stream);
-      if (gather) {  // fused all-gather: low words of the quad's commit indices, one 16-byte store per peer
+      if (gather) {  // fused all-gather: the quad's four low bytes in one 32-bit store per peer
+        uint32_t lo4 = 0;
+        bool carry = false;
         u32x4 lo;
-        bool wrap = false;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           lo.v[k] = iblo.v[k] + g[k].commit;
-          wrap = wrap || lo.v[k] < lo_old.v[k];
-        }
+          lo4 |= (lo.v[k] & 0xFFu) << (8 * k);
+          carry = carry || ((lo.v[k] ^ lo_old.v[k]) >> 8) != 0u;  // anything above the low byte moved (a wrap of the
+        }                                                         // low word changes bits 8..31 too)
         const uint64_t at = (uint64_t)a.rank * a.G + i;
         const bool whole = i0 + 3 < a.G && (at & 3u) == 0u && stopped == 0u;
 #pragma unroll 1
         for (uint32_t p = 0; p < a.world; ++p) {
           if (whole) {
-            st_v4u32_p(a.peer_lo[p] + at, lo, pol_stream);
+            st_state_u32_p(reinterpret_cast<uint32_t *>(a.peer_lo[p] + at), lo4, pol_stream);
           } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              if (!(stopped & (1u << k))) a.peer_lo[p][at + k] = lo.v[k];
+              if (!(stopped & (1u << k))) a.peer_lo[p][at + k] = (uint8_t)lo.v[k];
           }
         }
-        if (a.gather_prime || wrap) {  // high words: only when they change (or when priming)
+        if (a.gather_prime || carry) {  // the full index: only when more than its low byte changed (or when priming)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            if (!(stopped & (1u << k)) && (a.gather_prime || lo.v[k] < lo_old.v[k])) {
-              const uint32_t hi = (uint32_t)((A.c.ibase[i + k] + g[k].commit) >> 32);
+            if (!(stopped & (1u << k)) && (a.gather_prime || ((lo.v[k] ^ lo_old.v[k]) >> 8) != 0u)) {
+              const uint64_t full = A.c.ibase[i + k] + g[k].commit;
 #pragma unroll 1
-              for (uint32_t p = 0; p < a.world; ++p) a.peer_hi[p][at + k] = hi;
+              for (uint32_t p = 0; p < a.world; ++p) a.peer_full[p][at + k] = full;
             }
         }
       }
@@ -1697,12 +1706,143 @@ __global__ void __launch_bounds__(THREADS, (R <= 5 ? MRQ_T4_THREADS_PER_SM : 384
             st_v4u32_p(A.c.match + (uint64_t)r * a.gs + i, u32x4{{g[0].m[r], g[1].m[r], g[2].m[r], g[3].m[r]}}, pol_keep);
       }
     }
-    d = dn;
 #pragma unroll
-    for (int j = 0; j < (R > 1 ? R - 1 : 1); ++j) wb[j] = nwb[j];
-    pb = npb;
+    for (int j = 0; j < NW; ++j) {
+      wb[j] = wb1[j];
+      wb1[j] = wb2[j];
+    }
+    pb = pb1;
+    pb1 = pb2;
   }
   // "commit advanced" events: one warp-reduced atomic
+  const unsigned tot = __reduce_add_sync(0xFFFFFFFFu, ncommit);
+  if (tot != 0 && (threadIdx.x & 31u) == 0)
+    atomicAdd(&a.ctr[blockIdx.x & (kCtrShards - 1)].commits_advanced, (unsigned long long)tot);
+}
+
+// The same tick with ONE group per thread: for shards too small to occupy the GPU four groups to a thread (a warp then
+// walks ~800 dependent instructions per tick alone on its scheduler; at 131,072 groups that floor was 2.3 us per tick).
+// Scalar column accesses — the bytes no longer matter at this size, the number of warps in flight does.
+template <int R>
+__global__ void __launch_bounds__(128, 6) tick_fast1_kernel(const Tick4Args A) {
+  const TickArgs &a = A.t;
+  pdl_launch_dependents();
+  const uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i0 < a.G;
+  const uint64_t i = i0 < a.gs ? i0 : 0;  // (columns are padded to gs: lanes past G read padding)
+  const uint64_t pol_stream = l2_policy(a.l2_policy ? 1u : 0u);
+  const uint64_t pol_keep = l2_policy(a.l2_policy ? 2u : 0u);
+  pdl_wait();
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.tick_next = *a.tick_cur + A.nticks;
+  __shared__ TickDesc s_desc[kMaxTicksPerLaunch];
+  if (A.descs) {
+    const uint32_t nw = A.nticks * (uint32_t)(sizeof(TickDesc) / 4);
+    for (uint32_t w = threadIdx.x; w < nw; w += blockDim.x) reinterpret_cast<uint32_t *>(s_desc)[w] = reinterpret_cast<const uint32_t *>(A.descs)[w];
+  } else if (threadIdx.x == 0) {
+    s_desc[0] = A.d0;
+  }
+  __syncthreads();
+  CGroup<R> g;
+  const uint32_t flag = ld_stream_u8_p(A.c.flag + i, pol_keep);
+  g.meta = ld_state_p(a.s.meta + i, pol_keep);
+  g.commit = ld_stream_u32_p(A.c.commit + i, pol_keep);
+  g.win = ld_stream_u32_p(A.c.win + i, pol_keep);
+#pragma unroll
+  for (int r = 0; r < R; ++r) g.m[r] = ld_stream_u32_p(A.c.match + (uint64_t)r * a.gs + i, pol_keep);
+  const uint32_t gate = (flag & CF_GATE_OPEN) ? 0u : ld_stream_u32_p(A.c.gate + i, pol_keep);
+  const bool gather = a.world > 1;
+  const uint32_t iblo = gather ? ld_stream_u32_p(A.c.iblo + i, pol_keep) : 0u;
+  constexpr int NW = R > 1 ? R - 1 : 1;
+  auto load_frame = [&](uint32_t t, uint32_t (&w)[NW], uint32_t &np) {
+    const TickDesc &dd = s_desc[t];
+#pragma unroll
+    for (int j = 0; j < R - 1; ++j) w[j] = ld_stream_u8_p(dd.word8 + (uint64_t)j * a.gs + i, pol_stream);
+    if (R == 1) w[0] = 0;
+    np = dd.prop8 ? ld_stream_u8_p(dd.prop8 + i, pol_stream) : 0u;
+  };
+  uint32_t wb[NW], pb, wb1[NW], pb1 = 0;
+  load_frame(0, wb, pb);
+#pragma unroll
+  for (int j = 0; j < NW; ++j) wb1[j] = 0;
+  if (A.nticks > 1) load_frame(1, wb1, pb1);
+  bool stopped = !valid;
+  uint32_t acc_dirty = 0, ncommit = 0;
+  for (uint32_t t = 0; t < A.nticks; ++t) {
+    uint32_t wb2[NW], pb2 = 0;
+#pragma unroll
+    for (int j = 0; j < NW; ++j) wb2[j] = 0;
+    if (t + 2 < A.nticks) load_frame(t + 2, wb2, pb2);
+    const TickDesc &d = s_desc[t];
+    uint32_t o = 0, adv = 0, dirty = 0;
+    bool newly = false;
+    const uint32_t lo_old = iblo + g.commit;
+    if (!stopped) {
+      if (!compact_hot_step<R>(g, flag, wb, pb, gate, a.election_tick, a.heartbeat_tick, o, adv, dirty)) {
+        uint32_t p0 = 0, p1 = 0;
+#pragma unroll
+        for (int j = 0; j < R - 1; ++j) {
+          if (j < 4) p0 |= wb[j] << (8 * j);
+          else p1 |= wb[j] << (8 * (j - 4));
+        }
+        const CStepResult<R> cr = compact_step_cold<R>(g, flag, p0, p1, pb, gate, a.election_tick, a.heartbeat_tick);
+        g = cr.g;
+        o = cr.out;
+        adv = cr.adv;
+        dirty = cr.dirty;
+        newly = cr.slow != 0u;
+      }
+      if (newly) {
+        o = 0;
+        adv = 0;
+        dirty = 0;
+      }
+      ncommit += adv != 0u;
+    }
+    const unsigned smask = __ballot_sync(0xFFFFFFFFu, newly);
+    if (smask != 0) {  // hand those groups (from this tick on) to the general kernel
+      const unsigned lane = threadIdx.x & 31u;
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(a.slow_count, (unsigned)__popc(smask));
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      if (newly) A.slow_list64[base + __popc(smask & ((1u << lane) - 1u))] = ((unsigned long long)t << 32) | (unsigned long long)i0;
+      stopped = stopped || newly;
+    }
+    acc_dirty |= dirty;
+    if (valid) {  // this tick's outputs (a stopped group's are rewritten by the general kernel, which runs afterwards)
+      st_state_u32_p(d.out + i, o, pol_stream);
+      d.delta[i] = (uint8_t)(adv > 255u ? 255u : adv);
+      if (gather && !stopped) {
+        const uint32_t lo = iblo + g.commit;
+        const uint64_t at = (uint64_t)a.rank * a.G + i;
+        const bool full = a.gather_prime || ((lo ^ lo_old) >> 8) != 0u;
+        const uint64_t fv = full ? A.c.ibase[i] + g.commit : 0ull;
+#pragma unroll 1
+        for (uint32_t p = 0; p < a.world; ++p) {
+          a.peer_lo[p][at] = (uint8_t)lo;
+          if (full) a.peer_full[p][at] = fv;
+        }
+      }
+    }
+    const bool last = t + 1 == A.nticks;
+    if (A.write_through || last) {  // state write-back, per warp (see fast_group_tick)
+      const uint32_t wd = __reduce_or_sync(0xFFFFFFFFu, A.write_through ? dirty : acc_dirty);
+      if (valid) {
+        if (wd & CD_META) st_state_p(a.s.meta + i, g.meta, pol_keep);
+        if (wd & CD_COMMIT) st_state_u32_p(A.c.commit + i, g.commit, pol_keep);
+        if (wd & CD_WIN) st_state_u32_p(A.c.win + i, g.win, pol_keep);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (wd & (CD_MATCH0 << r)) st_state_u32_p(A.c.match + (uint64_t)r * a.gs + i, g.m[r], pol_keep);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NW; ++j) {
+      wb[j] = wb1[j];
+      wb1[j] = wb2[j];
+    }
+    pb = pb1;
+    pb1 = pb2;
+  }
   const unsigned tot = __reduce_add_sync(0xFFFFFFFFu, ncommit);
   if (tot != 0 && (threadIdx.x & 31u) == 0)
     atomicAdd(&a.ctr[blockIdx.x & (kCtrShards - 1)].commits_advanced, (unsigned long long)tot);

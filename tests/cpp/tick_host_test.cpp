@@ -725,7 +725,7 @@ void run_case_c(uint64_t G, uint32_t R, uint32_t cfg, int T, int rebase_every, u
 // whose commit indices sit just below a multiple of 2^32, so that they CROSS it during the run: after every tick the
 // stitched (hi << 32 | lo) view in both "ranks'" buffers must equal committed[] — a stale high word would show here.
 void run_gather_case(uint64_t G, uint32_t R, int T) {
-  const char *where = "fused gather across a 2^32 boundary";
+  const char *where = "fused gather: low bytes + full on change, across 2^32";
   const uint64_t seed = 0x5EED6A7Eull;
   orc_engine *o = orc_create(G, R, 0, 10, 1, seed, 0);
   OracleCols c(G, R);
@@ -757,7 +757,8 @@ void run_gather_case(uint64_t G, uint32_t R, int T) {
   std::vector<uint64_t> term(G * R), index(G * R), logterm(G * R), commit(G * R);
   std::vector<uint32_t> prop(G);
   const uint32_t world = 2, rank = 1;  // this shard is rank 1 of 2: its words land at [rank * G + g]
-  std::vector<uint32_t> lo0(world * G, 0xDEADBEEFu), hi0(world * G, 0xDEADBEEFu), lo1(world * G, 0xDEADBEEFu), hi1(world * G, 0xDEADBEEFu);
+  std::vector<uint8_t> lo0(world * G, 0xAB), lo1(world * G, 0xAB);  // low bytes, every tick
+  std::vector<uint64_t> hi0(world * G, 0xDEADBEEFDEADBEEFull), hi1(world * G, 0xDEADBEEFDEADBEEFull);  // full indices, on change
   uint64_t crossed = 0;
   for (int t = 0; t < T; ++t) {
     orc_gen_trace(o, &p, (uint64_t)t, type.data(), term.data(), index.data(), logterm.data(), commit.data(), prop.data(), 1);
@@ -775,17 +776,17 @@ void run_gather_case(uint64_t G, uint32_t R, int T) {
     a.rank = rank;
     a.gather_prime = t == 0 ? 1u : 0u;  // the first tick publishes every high word, later ticks only the changed ones
     a.peer_lo[0] = lo0.data();
-    a.peer_hi[0] = hi0.data();
+    a.peer_full[0] = hi0.data();
     a.peer_lo[1] = lo1.data();
-    a.peer_hi[1] = hi1.data();
+    a.peer_full[1] = hi1.data();
     const std::vector<uint64_t> before(e.committed.begin(), e.committed.begin() + G);
     dispatch_tick(e, a, t % 2);  // alternate: fast + general, general only
     c.load(o);
     if (!compare(e, c, where, (uint64_t)t)) break;
     for (uint64_t g = 0; g < G; ++g) {
-      crossed += (before[g] >> 32) != (e.committed[g] >> 32);
+      crossed += (before[g] >> 8) != (e.committed[g] >> 8);
       for (const auto &bufs : {std::make_pair(&lo0, &hi0), std::make_pair(&lo1, &hi1)}) {
-        const uint64_t got = ((uint64_t)(*bufs.second)[rank * G + g] << 32) | (*bufs.first)[rank * G + g];
+        const uint64_t got = ((*bufs.second)[rank * G + g] & ~0xFFull) | (*bufs.first)[rank * G + g];
         if (got != e.committed[g]) {
           std::printf("FAIL %s tick %d group %llu: gathered %llx, committed %llx\n", where, t, (unsigned long long)g,
                       (unsigned long long)got, (unsigned long long)e.committed[g]);
@@ -797,12 +798,12 @@ void run_gather_case(uint64_t G, uint32_t R, int T) {
     }
   }
   for (uint64_t k = 0; k < G; ++k)  // and nothing was written into the other rank's half
-    if (lo0[k] != 0xDEADBEEFu || hi1[k] != 0xDEADBEEFu) {
+    if (lo0[k] != 0xAB || hi1[k] != 0xDEADBEEFDEADBEEFull) {
       std::printf("FAIL %s: a word outside this rank's range was written\n", where);
       ++failures;
       break;
     }
-  std::printf("  %-34s %4d ticks  groups that crossed a 2^32 boundary: %llu\n", where, T, (unsigned long long)crossed);
+  std::printf("  %-34s %4d ticks  group-ticks whose index changed above its low byte: %llu\n", where, T, (unsigned long long)crossed);
   if (crossed < G / 2) {
     std::printf("FAIL %s: only %llu crossings — the case does not exercise the high-word path\n", where, (unsigned long long)crossed);
     ++failures;

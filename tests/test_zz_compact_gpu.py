@@ -17,6 +17,13 @@ from util import assert_state_equal
 pytestmark = [pytest.mark.gpu]
 
 
+@pytest.fixture(params=["4 groups per thread", "1 group per thread"], autouse=True)
+def both_kernel_shapes(request, monkeypatch):
+    """the library picks the quad kernel for big shards and the one-group-per-thread kernel for small ones; the tests
+    here are small, so each runs once under either shape (MRQ_T4_GPT is read at every launch)"""
+    monkeypatch.setenv("MRQ_T4_GPT", "4" if request.param.startswith("4") else "1")
+
+
 def _orc_params(p):
     q = oracle.TraceParams()
     for n, _ in F.TraceParams._fields_:
