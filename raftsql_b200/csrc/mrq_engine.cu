@@ -364,7 +364,8 @@ int launch_tick4(mrq_engine *e, const uint32_t *slots, uint32_t n) {
   // (a many-GPU job's): one group per thread — the GPU needs warps in flight more than it needs wide accesses.
   const char *gpt_env = getenv("MRQ_T4_GPT");  // development / test knob: force 1 or 4 groups per thread
   const int force_gpt = gpt_env ? atoi(gpt_env) : 0;
-  const bool one_per_thread = force_gpt == 1 || (force_gpt != 4 && quads < 2048ull * (uint64_t)g_sm_count / 4);
+  // (one per thread only while the whole shard is resident at once: 7 CTAs of 128 threads per SM)
+  const bool one_per_thread = force_gpt == 1 || (force_gpt != 4 && nblocks(e->gs, 128) <= 7u * (unsigned)g_sm_count);
   if (one_per_thread) {
     MRQ_DISPATCH_R(e->R, lst = launch_pdl(tick_fast1_kernel<kR>, nblocks(e->gs, 128), 128, 0, e->stream, A));
   } else {

@@ -1724,7 +1724,7 @@ __global__ void __launch_bounds__(THREADS, (R <= 5 ? MRQ_T4_THREADS_PER_SM : 384
 // walks ~800 dependent instructions per tick alone on its scheduler; at 131,072 groups that floor was 2.3 us per tick).
 // Scalar column accesses — the bytes no longer matter at this size, the number of warps in flight does.
 template <int R>
-__global__ void __launch_bounds__(128, 6) tick_fast1_kernel(const Tick4Args A) {
+__global__ void __launch_bounds__(128, 7) tick_fast1_kernel(const Tick4Args A) {
   const TickArgs &a = A.t;
   pdl_launch_dependents();
   const uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1767,6 +1767,9 @@ __global__ void __launch_bounds__(128, 6) tick_fast1_kernel(const Tick4Args A) {
   if (A.nticks > 1) load_frame(1, wb1, pb1);
   bool stopped = !valid;
   uint32_t acc_dirty = 0, ncommit = 0;
+  __shared__ __align__(16) uint8_t s_lo[128];
+  // CTA-wide gather stores need the whole CTA inside the shard and this rank's segment 4-byte aligned
+  const bool cta_gather = gather && (uint64_t)(blockIdx.x + 1u) * 128u <= a.G && (((uint64_t)a.rank * a.G) & 3u) == 0u;
   for (uint32_t t = 0; t < A.nticks; ++t) {
     uint32_t wb2[NW], pb2 = 0;
 #pragma unroll
@@ -1811,17 +1814,32 @@ __global__ void __launch_bounds__(128, 6) tick_fast1_kernel(const Tick4Args A) {
     if (valid) {  // this tick's outputs (a stopped group's are rewritten by the general kernel, which runs afterwards)
       st_state_u32_p(d.out + i, o, pol_stream);
       d.delta[i] = (uint8_t)(adv > 255u ? 255u : adv);
-      if (gather && !stopped) {
+      if (gather && !cta_gather && !stopped) {  // (ragged CTA, or a shard size that breaks the 4-byte alignment: byte stores)
         const uint32_t lo = iblo + g.commit;
         const uint64_t at = (uint64_t)a.rank * a.G + i;
-        const bool full = a.gather_prime || ((lo ^ lo_old) >> 8) != 0u;
-        const uint64_t fv = full ? A.c.ibase[i] + g.commit : 0ull;
 #pragma unroll 1
-        for (uint32_t p = 0; p < a.world; ++p) {
-          a.peer_lo[p][at] = (uint8_t)lo;
-          if (full) a.peer_full[p][at] = fv;
+        for (uint32_t p = 0; p < a.world; ++p) a.peer_lo[p][at] = (uint8_t)lo;
+      }
+      if (gather && !stopped) {  // the full index: only when more than its low byte changed (or when priming)
+        const uint32_t lo = iblo + g.commit;
+        if (a.gather_prime || ((lo ^ lo_old) >> 8) != 0u) {
+          const uint64_t at = (uint64_t)a.rank * a.G + i;
+          const uint64_t fv = A.c.ibase[i] + g.commit;
+#pragma unroll 1
+          for (uint32_t p = 0; p < a.world; ++p) a.peer_full[p][at] = fv;
         }
       }
+    }
+    if (cta_gather) {
+      // The CTA's 128 low bytes leave as ONE 128-byte store per peer (warp w serves peers w, w+4): NVLink moves a few
+      // large writes far better than 32-byte ones (measured at N = 8: 3.6 us of a 6.2 us tick went into byte stores).
+      s_lo[threadIdx.x] = (uint8_t)(iblo + g.commit);  // (a stopped group's byte is rewritten by the general kernel later)
+      __syncthreads();
+      const uint32_t word = reinterpret_cast<const uint32_t *>(s_lo)[threadIdx.x & 31u];
+      const uint64_t at0 = (uint64_t)a.rank * a.G + (uint64_t)blockIdx.x * 128u;
+      for (uint32_t p = threadIdx.x >> 5; p < a.world; p += 4u)
+        st_state_u32_p(reinterpret_cast<uint32_t *>(a.peer_lo[p] + at0) + (threadIdx.x & 31u), word, pol_stream);
+      __syncthreads();
     }
     const bool last = t + 1 == A.nticks;
     if (A.write_through || last) {  // state write-back, per warp (see fast_group_tick)

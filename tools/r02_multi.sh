@@ -7,12 +7,12 @@ N=${1:-2}
 OUT=gpurun_out/r02_multi_n$N
 mkdir -p "$OUT"
 if [ "${2:-}" != "notests" ]; then
-  timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -p no:cacheprovider > "$OUT/multi_tests.log" 2>&1
+  timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_zz_compact_gpu.py -m gpu -q -p no:cacheprovider > "$OUT/multi_tests.log" 2>&1
   echo "multi tests exit $?"
   tail -4 "$OUT/multi_tests.log"
 fi
 PORT=29511
-for G in fused none nccl; do
+for G in ${GATHERS:-fused none nccl}; do
   PORT=$((PORT + 1))
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port $PORT \
     bench.py --gpus "$N" --gather $G > "$OUT/bench_$G.json" 2> "$OUT/bench_$G.err"
@@ -29,6 +29,7 @@ except Exception as ex:
 PY
   tail -2 "$OUT/bench_$G.err"
 done
+if [ "${SKIP_PERTICK:-0}" = "1" ]; then exit 0; fi
 # the same job, one launch pair per TICK (no batching): what the launch floor costs at this shard size
 PORT=$((PORT + 1))
 MRQ_BENCH_FAST=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port $PORT \
