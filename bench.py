@@ -141,7 +141,9 @@ def sass_instruction_count(kernel_substr: str):
         for part in txt.split("Function : ")[1:]:
             name = part.split("\n", 1)[0].strip()
             if kernel_substr in name:
-                return sum(1 for ln in part.splitlines() if ln.lstrip().startswith("/*") and ln.rstrip().endswith(";") and "*/" in ln[:14])
+                import re
+
+                return len(re.findall(r"/\*[0-9a-f]{4}\*/\s+[^;]*;", part))
     except Exception:
         pass
     return None
@@ -419,7 +421,7 @@ def run_ours(args):
     ms, ms_reps, launches_timed, clocks = timed_leg(mode, graph, wt, sample_clocks=True)
     ticks_per_s = K / (ms / 1e3)
     peak, peak_src = measured_peak_gbs()
-    batched = mode == 4 and graph != 0
+    batched = mode == 4 and graph != 0 and not (world > 1 and args.gather == "nccl")  # (a per-tick ncclAllGather forces per-tick launches)
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------------
     tb = tick_bytes_per_group(R, inbox, K if batched else 1, bool(wt))
