@@ -326,17 +326,25 @@ def run_ours(args):
         eng.tick_many([(first_slot + k) % nslots for k in range(n)])
 
     def post_roll(med_ms):
-        n_more = max(4, min(20000, int(2.0 / max(1e-6, 8 * med_ms / K * 1e-3))))  # the same count on every rank
+        """~2 s of tick launches on EMPTY inboxes after the timed repetitions, so that the clock sampler sees the GPU under
+        the tick kernels (every rank runs the same number of chunks: the stop decision is rank 0's, all-reduced)."""
         if eng_mode() >= 3:
-            zero = np.zeros((R - 1, G), np.uint8)
+            zero = np.zeros((max(R - 1, 0), G), np.uint8)
             eng.post_inbox_packed(zero, np.zeros(G, np.uint8), (), slot=nslots, keep=True)
-            for _ in range(n_more):
-                eng.tick_many([nslots] * 8)
         else:
             eng.clear_inbox(nslots)
-            for _ in range(n_more):
-                eng.tick_many([nslots] * 8)
-        eng.synchronize()
+        t_start = time.perf_counter()
+        while True:
+            for _ in range(100):
+                eng.tick_many([nslots] * 64)
+            eng.synchronize()
+            done = time.perf_counter() - t_start >= 2.0
+            if dist is not None:
+                flag_t = torch.tensor([1 if done else 0], dtype=torch.int32, device="cuda")
+                dist.broadcast(flag_t, 0)
+                done = bool(flag_t.item())
+            if done:
+                break
 
     cur_mode = [0]
 
