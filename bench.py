@@ -467,9 +467,11 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": kernel_name,
                      "achieved": tick_gbs, "peak": peak, "unit": "GB/s",
                      "frac": tick_gbs / peak,
-                     "traffic": (ncu_traffic("tick_fast4_kernel<5>", "tick_fast4_kernelILi5") if world == 1 and mode == 4 and not batched
-                                 else None),
-                     "traffic_source": "profiles/r02_traffic.json (ncu --set full, cold cache, isolated per-tick launch)",
+                     "traffic": (None if world != 1 or mode != 4 else
+                                 ncu_traffic("tick_fast4_kernel<5>", "tick_fast4_kernelILi5") if not batched else
+                                 ncu_traffic("tick_fast4_kernel<5> (20 ticks per launch)", "tick_fast4_kernelILi5") if K == 20 else None),
+                     "traffic_source": "profiles/r02_traffic.json (ncu --set full, cold cache, one isolated launch" +
+                                       (f" of {K} ticks: stores still dirty in L2 at its end are not in it)" if batched else ")"),
                      "peak_source": peak_src, "algorithmic_bytes_per_group": tb,
                      "algorithmic_bytes_per_launch": tb["total"] * G * (K if batched else 1)},
         "gpu_launches": launches_timed,
@@ -622,7 +624,16 @@ def bench_e2e(eng, st0, base0, host_ib, commits_ref, steps, dist=None, torch=Non
     wide = {"value": nw / el_w, "h2d_bytes_per_step": sum(a.nbytes for a in host_ib[0].values()),
             "d2h_bytes_per_step": G * 8, "api": "mrq_post_inbox_dense + mrq_tick + mrq_sync_commits"}
 
-    bufs = [(PinnedArray((max(Rr - 1, 1), G), np.uint8), PinnedArray((G,), np.uint8)) for _ in range(NB)]
+    class Frame:  # one pinned buffer per frame: R-1 sender rows, then the proposal bytes (a single H2D copy)
+        def __init__(self):
+            self.buf = PinnedArray((max(Rr - 1, 0) + 1, G), np.uint8)
+            self.word, self.prop = self.buf.array[: max(Rr - 1, 0)], self.buf.array[max(Rr - 1, 0)]
+            self.word_ptr, self.prop_ptr = self.buf.ptr, self.buf.ptr + max(Rr - 1, 0) * G
+
+        def free(self):
+            self.buf.free()
+
+    bufs = [Frame() for _ in range(NB)]
     delta = PinnedArray((G,), np.uint8)
     dptr = C.cast(delta.ptr, F.u8p)
 
@@ -632,7 +643,7 @@ def bench_e2e(eng, st0, base0, host_ib, commits_ref, steps, dist=None, torch=Non
             arr[i].group, arr[i].from_, arr[i].type = g, frm, ty
             arr[i].term, arr[i].index, arr[i].logterm, arr[i].commit = term, index, logterm, commit
         v = F.InboxPacked()
-        v.word, v.prop_count8 = bufs[b][0].ptr, C.cast(bufs[b][1].ptr, F.u8p)
+        v.word, v.prop_count8 = bufs[b].word_ptr, C.cast(bufs[b].prop_ptr, F.u8p)
         v.wide, v.n_wide, v.word_bits, v.reserved = arr, len(wide_msgs), 8, 0
         return v, arr
 
@@ -650,7 +661,7 @@ def bench_e2e(eng, st0, base0, host_ib, commits_ref, steps, dist=None, torch=Non
                 free.acquire()
                 b = k % NB
                 t1 = time.perf_counter()
-                _, _, wide_msgs = pk.frame(host_ib[k % S], word_out=bufs[b][0].array[: max(Rr - 1, 0)], prop8_out=bufs[b][1].array)
+                _, _, wide_msgs = pk.frame(host_ib[k % S], word_out=bufs[b].word, prop8_out=bufs[b].prop)
                 pack_s[0] += time.perf_counter() - t1
                 n_esc[0] += len(wide_msgs)
                 ready.put(view_of(b, wide_msgs))
@@ -695,13 +706,13 @@ def bench_e2e(eng, st0, base0, host_ib, commits_ref, steps, dist=None, torch=Non
            "inputs": f"{S} distinct consecutive ticks of the trace, one per step (host wide inbox -> byte frame -> device)",
            "wide_form": wide}
     # the same loop with the frames already encoded (a transport that delivers byte frames): what the link + device do alone
-    pre = [(PinnedArray((max(Rr - 1, 1), G), np.uint8), PinnedArray((G,), np.uint8)) for _ in range(S)]
+    pre = [Frame() for _ in range(S)]
     pk = Pack8(st0["self_id"], base0, st0["term"], Rr)
     views = []
     for k in range(S):
-        _, _, wm = pk.frame(host_ib[k], word_out=pre[k][0].array[: max(Rr - 1, 0)], prop8_out=pre[k][1].array)
+        _, _, wm = pk.frame(host_ib[k], word_out=pre[k].word, prop8_out=pre[k].prop)
         v = F.InboxPacked()
-        v.word, v.prop_count8 = pre[k][0].ptr, C.cast(pre[k][1].ptr, F.u8p)
+        v.word, v.prop_count8 = pre[k].word_ptr, C.cast(pre[k].prop_ptr, F.u8p)
         arr = (F.Msg * max(1, len(wm)))()
         for i, (g, frm, ty, term, index, logterm, commit) in enumerate(wm):
             arr[i].group, arr[i].from_, arr[i].type = g, frm, ty
@@ -730,9 +741,8 @@ def bench_e2e(eng, st0, base0, host_ib, commits_ref, steps, dist=None, torch=Non
     res["preencoded"] = {"value": S / el_p, "us_per_tick": el_p / S * 1e6, "h2d_GBps_per_gpu": h2d * S / el_p / 1e9,
                          "encode_in_timed_region": False,
                          "note": "frames encoded before the clock starts (a transport delivering byte frames): link + device only"}
-    for a_, b_ in bufs + pre:
-        a_.free()
-        b_.free()
+    for fr in bufs + pre:
+        fr.free()
     delta.free()
     return res
 

@@ -950,8 +950,16 @@ int mrq_post_inbox_packed(mrq_engine *e, uint32_t slot, const mrq_inbox_packed *
   uint8_t *d_prop = d_word + wbytes;
   MsgRec *d_wide = (MsgRec *)(d_word + wbytes + pbytes);
   if (sg.used) CK(e, cudaStreamWaitEvent(e->copy_stream, sg.consumed, 0));
-  if (rows) CK(e, cudaMemcpy2DAsync(d_word, e->gs * wsz, in->word, e->G * wsz, e->G * wsz, rows, cudaMemcpyHostToDevice, e->copy_stream));
-  if (in->prop_count8) CK(e, cudaMemcpyAsync(d_prop, in->prop_count8, e->G, cudaMemcpyHostToDevice, e->copy_stream));
+  // One frame, one copy, when the host laid it out the way the staging buffer is (rows without padding, the proposal
+  // bytes right behind them): every async copy costs ~10 us of set-up on the link, and the link is this path's bound.
+  const bool one_copy = rows && in->prop_count8 && e->gs == e->G && wbytes == e->G * rows * wsz &&
+                        (const uint8_t *)in->prop_count8 == (const uint8_t *)in->word + wbytes;
+  if (one_copy) {
+    CK(e, cudaMemcpyAsync(d_word, in->word, wbytes + e->G, cudaMemcpyHostToDevice, e->copy_stream));
+  } else {
+    if (rows) CK(e, cudaMemcpy2DAsync(d_word, e->gs * wsz, in->word, e->G * wsz, e->G * wsz, rows, cudaMemcpyHostToDevice, e->copy_stream));
+    if (in->prop_count8) CK(e, cudaMemcpyAsync(d_prop, in->prop_count8, e->G, cudaMemcpyHostToDevice, e->copy_stream));
+  }
   if (in->n_wide) CK(e, cudaMemcpyAsync(d_wide, in->wide, xbytes, cudaMemcpyHostToDevice, e->copy_stream));
   CK(e, cudaEventRecord(sg.copied, e->copy_stream));
   CK(e, cudaStreamWaitEvent(e->stream, sg.copied, 0));

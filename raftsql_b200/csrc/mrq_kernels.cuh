@@ -819,8 +819,8 @@ __device__ __forceinline__ void fast_group_tick(const TickArgs &a, const uint64_
 }
 
 // ---- the tick on the BYTE FORM of the inbox (include/mrq_packed8.h), without the unpack pass -------------------
-// NOT YET LAUNCHED BY THE LIBRARY: the per-group arithmetic below is verified on the host against the CPU checker
-// (tests/cpp/tick_host_test.cpp); kernels and engine plumbing around it come with the first GPU session.
+// (tick mode 3; validated on hardware in round 2 — tests/test_zz_packed8_gpu.py — and on the host against the CPU
+// checker, tests/cpp/tick_host_test.cpp.  Tick mode 4 below supersedes it for dense multi-raft hosts.)
 // Reads 4 sender bytes + 1 proposal byte + the two base words per group instead of the 73 B of wide inbox
 // columns.  Same split as above: the fast function handles what needs none of the role machinery and leaves every
 // other group untouched; the general one materialises that group's bytes into its wide inbox slot (escaped
@@ -1055,7 +1055,7 @@ __global__ void __launch_bounds__(kTickThreads, (R <= 5 ? 6 : 5)) tick_slow_kern
   }
 }
 
-// The same two launches on the byte form (tick mode 3; opt-in, first hardware run pending): identical wrappers
+// The same two launches on the byte form (tick mode 3): identical wrappers
 // around fast_group_tick8 / general_group_tick8.
 struct Tick8Args {
   TickArgs t;
