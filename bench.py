@@ -235,8 +235,8 @@ def run_reference(args):
         "impl": "reference", "metric": "raft_ticks_per_sec_1Mx5", "value": tps, "unit": "ticks/s",
         "n_gpus": args.gpus, "steps": n, "warmup": max(1, args.warmup), "ms_per_step": 1e3 * el / n,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "1,048,576 groups x 5 replicas, steady-state append/ack trace (BASELINE configs[2])",
-                   "groups": G, "replicas": R},
+        "config": {"workload": "1,048,576 groups x 5 replicas, steady-state append/ack trace (BASELINE configs[2]/[3])",
+                   "groups_total": G, "replicas": R},
         "cpu_baseline": {"value": tps, "unit": "ticks/s", "cores": nt, "kind": "port",
                          "sample": f"{n} full ticks over all {G} groups on {nt} threads"},
         "e2e": {"value": tps, "unit": "ticks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -34,7 +34,7 @@ def test_reference_arm_prints_the_contract_line():
     assert line["higher_is_better"] is True and line["steps"] == 2 and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "ticks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert line["config"]["groups"] == 1 << 20 and line["config"]["replicas"] == 5
+    assert line["config"]["groups_total"] == 1 << 20 and line["config"]["replicas"] == 5
 
 
 def test_bench_byte_accounting_and_the_traffic_guard(tmp_path, monkeypatch):
