@@ -165,6 +165,16 @@ def ncu_traffic(kernel: str, mangled_substr: str | None = None):
         return None
 
 
+def cpu_quota_cores():
+    """CPUs' worth of time the container's cgroup allows (cpu.max), or None when unlimited / unknown: the host may show
+    128 hardware threads and still give this process 16 CPUs of time, which is what bounds every host-side leg."""
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        return None if quota == "max" else round(int(quota) / int(period), 2)
+    except Exception:
+        return None
+
+
 def measured_peak_gbs() -> tuple[float, str]:
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -237,7 +247,7 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": "1,048,576 groups x 5 replicas, steady-state append/ack trace (BASELINE configs[2]/[3])",
                    "groups_total": G, "replicas": R},
-        "cpu_baseline": {"value": tps, "unit": "ticks/s", "cores": nt, "kind": "port",
+        "cpu_baseline": {"value": tps, "unit": "ticks/s", "cores": nt, "kind": "port", "cpu_quota_cores": cpu_quota_cores(),
                          "sample": f"{n} full ticks over all {G} groups on {nt} threads"},
         "e2e": {"value": tps, "unit": "ticks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -496,7 +506,7 @@ def run_ours(args):
         # CPU baseline: the oracle port on this box's host cores, bounded sample
         try:
             tps, nt, n, el, _ = cpu_reference_ticks(G_TOTAL, R, st0, host_ib[:4], budget_s=12.0)
-            line["cpu_baseline"] = {"value": tps, "unit": "ticks/s", "cores": nt, "kind": "port",
+            line["cpu_baseline"] = {"value": tps, "unit": "ticks/s", "cores": nt, "kind": "port", "cpu_quota_cores": cpu_quota_cores(),
                                     "sample": f"{n} full ticks over all {G_TOTAL} groups x {R} replicas in {el:.1f} s on {nt} threads"}
             tps1, _, n1, el1, _ = cpu_reference_ticks(G_TOTAL, R, st0, host_ib[:4], budget_s=3.0, nthreads=1)
             line["cpu_baseline"]["single_thread"] = {"value": tps1, "cores": 1, "sample": f"{n1} full ticks in {el1:.1f} s"}
@@ -702,6 +712,7 @@ def bench_e2e(eng, st0, base0, host_ib, commits_ref, steps, dist=None, torch=Non
            "api": "mrq_pack8 (host encode, in the timed region) + mrq_post_inbox_packed (pinned, 8-bit form, copy stream) + "
                   "mrq_tick (tick mode 4) + mrq_drain_tick_deltas/mrq_drain_wait (1 B/group)",
            "encode_in_timed_region": True, "pack_us_per_tick": pack_avg * 1e6, "us_per_tick": el / S * 1e6,
+           "host_cpu_quota_cores": cpu_quota_cores(),
            "equals_wide_form": same, "escapes": n_esc, "h2d_GBps_per_gpu": h2d * S / el / 1e9,
            "inputs": f"{S} distinct consecutive ticks of the trace, one per step (host wide inbox -> byte frame -> device)",
            "wide_form": wide}
