@@ -1168,7 +1168,7 @@ __global__ void __launch_bounds__(kTickThreads, (R <= 5 ? 6 : 5)) tick_general_k
 // whose frame holds anything but in-window acks / its leader's heartbeat is handed to the general path, which
 // materialises the wide columns, runs the unchanged general tick on them, and re-compacts.
 enum : uint32_t { CF_COMPACT = 1u, CF_TERM_OK = 2u, CF_GATE_OPEN = 4u };
-enum : uint32_t { CD_META = 1u, CD_COMMIT = 2u, CD_WIN = 4u, CD_MATCH0 = 1u << 8 };
+enum : uint32_t { CD_META = 1u, CD_COMMIT = 2u, CD_WIN = 4u, CD_MATCH0 = 1u << 8, CD_MATCH_ANY = 0xFFu << 8 };
 #ifndef MRQ_HOST_EMULATION
 static constexpr uint32_t kCompactSpan = 0x7FFFFFFFu;  // offsets stay below 2^31: sums of two never wrap
 #else
@@ -1212,7 +1212,7 @@ __device__ __forceinline__ bool compact_hot_step(CGroup<R> &g, const uint32_t fl
   uint32_t li = g.m[R - 1];
   hot = hot && li + nprop <= kCompactSpan;
   uint32_t nm[R];
-  uint32_t d = 0, min_ack = MRQ_P8_NO_ACK, kinds = 0;
+  uint32_t d = 0, min_ack = MRQ_P8_NO_ACK, kinds = 0, mx_max = 0, moved = 0;
 #pragma unroll
   for (int j = 0; j < R - 1; ++j) {
     const uint32_t w = wb[j];
@@ -1220,19 +1220,21 @@ __device__ __forceinline__ bool compact_hot_step(CGroup<R> &g, const uint32_t fl
     const bool ack = (w & 1u) != 0u;  // (kind 3 is ruled out below)
     const uint32_t pay = w >> 2;
     const uint32_t mx = ack ? g.win + pay : 0u;
-    hot = hot && mx <= li;            // an ack beyond lastIndex: upstream's strict path
+    mx_max = max(mx_max, mx);
     nm[j] = max(g.m[j], mx);          // Progress.maybeUpdate
-    d |= nm[j] != g.m[j] ? CD_MATCH0 << j : 0u;
+    moved |= nm[j] ^ g.m[j];
     min_ack = ack ? min(min_ack, pay) : min_ack;
   }
-  if (!hot || (kinds & 2u) != 0u) return false;  // heartbeats, responses, escapes: not the hot case
+  // an ack beyond lastIndex is upstream's strict path; heartbeats, responses, escapes: not the hot case
+  if (!hot || mx_max > li || (kinds & 2u) != 0u) return false;
   uint32_t o = 0;
   li += nprop;  // appendEntry: lastTerm already equals Term (ltok), self Match = lastIndex
   nm[R - 1] = li;
   if (nprop) {
-    d |= CD_MATCH0 << (R - 1);
+    moved = 1u;
     o |= MRQ_OUT_BCAST_APPEND;
   }
+  d = moved != 0u ? CD_MATCH0 : 0u;  // one bit for the whole match column: the write-back stores all its rows
   uint32_t commit = g.commit, q = 0;
   if (d != 0u) {  // maybeCommit, once (see Group::flushCommit for why once is exact)
     uint32_t dl[R];
@@ -1249,14 +1251,20 @@ __device__ __forceinline__ bool compact_hot_step(CGroup<R> &g, const uint32_t fl
   }
   // tickHeartbeat on the packed word: electionElapsed bits [14,26), heartbeatElapsed bits [38,46)
   uint32_t lo = (uint32_t)g.meta, hi = (uint32_t)(g.meta >> 32);
-  uint32_t el = ((lo >> 14) & 0xFFFu) + 1u, hb = ((hi >> 6) & 0xFFu) + 1u;
+  uint32_t el = ((lo >> 14) & 0xFFFu) + 1u;
   el = el >= et ? 0u : el;
-  if (hb >= ht) {
-    hb = 0;
-    o |= MRQ_OUT_BCAST_HEARTBEAT;
-  }
   lo = (lo & ~(0xFFFu << 14)) | (el << 14);
-  hi = (hi & ~(0xFFu << 6)) | (hb << 6);
+  if (ht <= 1u) {  // HeartbeatTick 1 (reference raft.go:155; launch-uniform): every tick beats, the counter stays 0
+    hi &= ~(0xFFu << 6);
+    o |= MRQ_OUT_BCAST_HEARTBEAT;
+  } else {
+    uint32_t hb = ((hi >> 6) & 0xFFu) + 1u;
+    if (hb >= ht) {
+      hb = 0;
+      o |= MRQ_OUT_BCAST_HEARTBEAT;
+    }
+    hi = (hi & ~(0xFFu << 6)) | (hb << 6);
+  }
   const uint64_t nmeta = ((uint64_t)hi << 32) | lo;
   d |= nmeta != g.meta ? CD_META : 0u;
   if (min_ack < MRQ_P8_NO_ACK && min_ack > MRQ_P8_SLACK) {  // the window slides for whoever decodes the frame
@@ -1603,9 +1611,12 @@ __global__ void __launch_bounds__(THREADS, (R <= 5 ? MRQ_T4_THREADS_PER_SM : 384
     u32x4 outw{};
     uint32_t dw = 0, newly = 0, tdirty = 0;
     u32x4 lo_old{};
+    if (gather) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) lo_old.v[k] = iblo.v[k] + g[k].commit;
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      lo_old.v[k] = iblo.v[k] + g[k].commit;
       if (stopped & (1u << k)) continue;
       uint32_t wk[R > 1 ? R - 1 : 1];
 #pragma unroll
@@ -1700,10 +1711,11 @@ __global__ void __launch_bounds__(THREADS, (R <= 5 ? MRQ_T4_THREADS_PER_SM : 384
         }
         if (wd & CD_COMMIT) st_v4u32_p(A.c.commit + i, u32x4{{g[0].commit, g[1].commit, g[2].commit, g[3].commit}}, pol_keep);
         if (wd & CD_WIN) st_v4u32_p(A.c.win + i, u32x4{{g[0].win, g[1].win, g[2].win, g[3].win}}, pol_keep);
+        if (wd & CD_MATCH_ANY) {
 #pragma unroll
-        for (int r = 0; r < R; ++r)
-          if (wd & (CD_MATCH0 << r))
+          for (int r = 0; r < R; ++r)
             st_v4u32_p(A.c.match + (uint64_t)r * a.gs + i, u32x4{{g[0].m[r], g[1].m[r], g[2].m[r], g[3].m[r]}}, pol_keep);
+        }
       }
     }
 #pragma unroll
@@ -1848,9 +1860,10 @@ __global__ void __launch_bounds__(128, 7) tick_fast1_kernel(const Tick4Args A) {
         if (wd & CD_META) st_state_p(a.s.meta + i, g.meta, pol_keep);
         if (wd & CD_COMMIT) st_state_u32_p(A.c.commit + i, g.commit, pol_keep);
         if (wd & CD_WIN) st_state_u32_p(A.c.win + i, g.win, pol_keep);
+        if (wd & CD_MATCH_ANY) {
 #pragma unroll
-        for (int r = 0; r < R; ++r)
-          if (wd & (CD_MATCH0 << r)) st_state_u32_p(A.c.match + (uint64_t)r * a.gs + i, g.m[r], pol_keep);
+          for (int r = 0; r < R; ++r) st_state_u32_p(A.c.match + (uint64_t)r * a.gs + i, g.m[r], pol_keep);
+        }
       }
     }
 #pragma unroll
