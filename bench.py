@@ -577,7 +577,10 @@ def bench_quorum_kernel(torch, eng, peak, K, W, G=None, Rr=None):
                      "us_per_launch_reps": [round(x * 1e3, 2) for x in reps]}
     best = max(out, key=lambda k: out[k]["achieved"])
     return {"bound": "hbm", "kernel": f"quorum_kernel ({best})", "achieved": out[best]["achieved"], "peak": peak,
-            "unit": "GB/s", "frac": out[best]["frac"], "traffic": ncu_traffic("quorum_kernel_ldg<5>"),
+            "unit": "GB/s", "frac": out[best]["frac"],
+            "traffic": (ncu_traffic(*{"ldg256": ("quorum_kernel_ldg256<5>", "quorum_kernel_ldg256ILi5"),
+                                      "tma_bulk": ("quorum_kernel_tma<5>", "quorum_kernel_tmaILi5"),
+                                      "ldg128": ("quorum_kernel_ldg<5>", "quorum_kernel_ldgILi5")}[best]) if (R == 5 and G == G_TOTAL) else None),
             "algorithmic_bytes_per_group": quorum_bytes_per_group(R), "variants": out,
             "cold": f"{len(sets)} distinct column sets ({quorum_bytes_per_group(R) * G / 1e6:.1f} MB each), L2 flushed before timing"}
 
