@@ -344,6 +344,11 @@ int launch_tick4(mrq_engine *e, const uint32_t *slots, uint32_t n) {
     key.append((const char *)&e->stage_gen, sizeof e->stage_gen);
     auto it = e->desc_tables.find(key);
     if (it == e->desc_tables.end()) {  // first use of this slot sequence: build and upload its descriptor table
+      if (e->desc_tables.size() >= 64) {  // a host that never repeats a sequence must not grow the cache without bound
+        CK(e, cudaStreamSynchronize(e->stream));  // (tables of launches still in flight)
+        for (auto &kv : e->desc_tables) cudaFree(kv.second);
+        e->desc_tables.clear();
+      }
       std::vector<TickDesc> host(n);
       for (uint32_t k = 0; k < n; ++k)
         if ((r = desc_of(slots[k], true, &host[k]))) return r;
