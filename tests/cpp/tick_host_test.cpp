@@ -558,10 +558,10 @@ void dispatch_ticks_c(HostEngine &e, CompactHost &ch, const TickArgs &a, std::ve
 // soup = false: the synthetic trace `cfg` (as run_case8);  soup = true: the adversarial message soup (as run_soup),
 // re-based every `rebase_every` ticks with the window sliding in between.
 void run_case_c(uint64_t G, uint32_t R, uint32_t cfg, int T, int rebase_every, uint32_t K, bool soup = false, uint64_t big = 0,
-                int also_rebase_at = -1) {
+                int also_rebase_at = -1, bool edges = false) {
   char where[112];
   std::snprintf(where, sizeof where, "compact%s K=%u G=%llu R=%u %s=%u%s", soup ? " soup" : "", K, (unsigned long long)G, R, soup ? "seed" : "cfg", cfg,
-                big ? " near 2^31" : "");
+                edges ? " window edges" : big ? " near 2^31" : "");
   const uint64_t seed = 0x5EEDC000ull + cfg * 131 + R;
   const uint32_t et = soup ? 5 : 10;
   orc_engine *o = orc_create(G, R, 0, et, 1, seed, 0);
@@ -635,12 +635,35 @@ void run_case_c(uint64_t G, uint32_t R, uint32_t cfg, int T, int rebase_every, u
               term[w] = index[w] = logterm[w] = commit[w] = 0;
               continue;
             }
-            const uint64_t u = rnd() % 64;
+            const uint64_t u = rnd() % (edges ? 4096 : 64);  // (the window-edge soup: terms mostly stay put)
             term[w] = around(c.term[g], u == 0 ? -2 : u == 1 ? -1 : u == 2 ? 1 : u == 3 ? 2 : 0);
             index[w] = around(c.last_index[g], (int64_t)(rnd() % 7) - 4);
             logterm[w] = around(c.last_term[g], (int64_t)(rnd() % 3) - 1);
             commit[w] = c.committed[g] + rnd() % 4;
-            if ((ty & 0x0F) == 3) {
+            if (edges) {  // mostly compact-representable traffic aimed at the EDGES of the 64-entry window and of the log
+              static const uint8_t kEdge[] = {4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 0, 0, 8, 9, 6, 4 | 0x80};
+              const uint8_t t2 = (rnd() % 16 == 0) ? kEdge[14 + rnd() % 6] : kEdge[rnd() % 14];  // 6 % non-ack cells
+              type[w] = t2;
+              if ((t2 & 0x0F) == 0) {
+                term[w] = index[w] = logterm[w] = commit[w] = 0;
+                continue;
+              }
+              const uint64_t wbase = enc_base[g], li = c.last_index[g];
+              const uint64_t top = wbase + 63 < li ? wbase + 63 : li;
+              switch (rnd() % 64) {
+                case 0: index[w] = wbase + 64; break;              // one past the window: escapes
+                case 1: index[w] = wbase ? wbase - 1 : 0; break;   // one below it: escapes
+                case 2: index[w] = (rnd() % 64 == 0) ? li + 1 : li; break;  // (rarely) beyond the log: upstream's strict path, sticky
+                case 3: case 4: case 5: case 6: index[w] = wbase; break;   // offset 0
+                case 7: case 8: case 9: case 10: index[w] = top; break;    // the last offset the window (or the log) allows
+                case 11: case 12: index[w] = li; break;
+                default: index[w] = top > wbase ? wbase + rnd() % (top - wbase + 1) : wbase; break;
+              }
+              commit[w] = (rnd() % 4 == 0) ? wbase + rnd() % 64 : c.committed[g] + rnd() % 3;  // heartbeat commits around the window too
+              if (commit[w] > li) commit[w] = li;
+            }
+            const uint8_t ty2 = type[w];
+            if ((ty2 & 0x0F) == 3) {
               if (commit[w] > index[w]) commit[w] = index[w];
               if (index[w] == 0) logterm[w] = 0;
               if (logterm[w] > term[w]) logterm[w] = term[w];
@@ -909,6 +932,8 @@ int main(int argc, char **) {
   run_case_c(200 / k, 3, 5, 240, 40, 1);
   kCompactSpan = 0x7FFFFFFFu;
   for (uint32_t R : {2u, 3u, 5u, 8u}) run_case_c(120 / k + 8, R, 300 + R, 240, 8, R == 5 ? 4 : 1, true);  // message soups
+  // the window-edge soup on steady-state leaders: acks / heartbeats at offset 0, 63, 64, -1, at and beyond lastIndex, rare term changes
+  for (uint32_t R : {2u, 3u, 4u, 5u, 7u, 8u}) run_case_c(160 / k + 8, R, 500 + R, 320, 16, R % 2 ? 1 : 4, true, 1ull << 22, -1, true);
   hot_path = false;  // the complete compact step alone (the hot step is an early exit of it, never a different answer)
   run_case_c(300 / k, 5, 5, 224, 32, 1);
   run_case_c(300 / k, 3, 3, 300, 1000, 4, false, 0, 60);
