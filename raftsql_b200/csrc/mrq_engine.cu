@@ -1432,12 +1432,6 @@ int mrq_set_tick_mode(mrq_engine *e, int mode) {
     int r = ensure_compact_alloc(e);
     if (r) return r;
   }
-  if (mode != e->tick_mode && e->l2_policy) {
-    // Each mode marks ITS state columns evict-last; lines another mode left marked would squat in L2 and starve this
-    // one (measured: the wide tick ran 2.5x slower after a mode-4 run).  Drop every persisting line at the switch.
-    CK(e, cudaStreamSynchronize(e->stream));
-    cudaCtxResetPersistingL2Cache();
-  }
   e->tick_mode = mode;
   return MRQ_OK;
 }
