@@ -880,6 +880,7 @@ int main(int argc, char **) {
       for (uint32_t R = 1; R <= 8; ++R) {
         for (int mode : {0, 1, 8}) run_soup(96, R, 300, 1000 + 37 * (uint64_t)s + R, mode);
         run_case_c(96, R, 1000 + 37 * (uint32_t)s + R, 300, 8, 1 + (uint32_t)s % 4, true);
+        run_case_c(96, R, 2000 + 37 * (uint32_t)s + R, 300, 16, 1 + (uint32_t)(s + 1) % 4, true, 1ull << 22, -1, true);  // window-edge soup
       }
     std::printf(failures ? "tick_host_test soak: %d failure(s)\n" : "tick_host_test soak: ok\n", failures);
     return failures ? 1 : 0;
