@@ -175,6 +175,16 @@ __global__ void __launch_bounds__(THREADS) k3_persistent(const QuorumArgs a) {
   count_moved(a.ctr, n);
 }
 
+// persistent grid over 512-group tiles with the shipped body (prefetch hint + streaming 256-bit store)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k3_persistent5(const QuorumArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  unsigned n = 0;
+  for (uint64_t i = ((uint64_t)blockIdx.x * THREADS + threadIdx.x) * 4; i + 3 < a.G; i += (uint64_t)gridDim.x * THREADS * 4) n += quad_x<5>(a, i);
+  count_moved(a.ctr, n);
+}
+
 struct Set {
   uint64_t *match, *committed, *gate, *committed0;
 };
@@ -281,6 +291,9 @@ int main(int argc, char **argv) {
   RUN("diag: st.global.cs stores", (k3_diag<128, 1, 4>), blocks(128, 1), 128, true);
   RUN("diag: pf256 + cs + v4 store", (k3_diag<128, 1, 5>), blocks(128, 1), 128, true);
   RUN("diag: same, 256 threads", (k3_diag<256, 1, 5>), blocks(256, 1), 256, true);
+  RUN("diag: shipped body, persistent 148*8", (k3_persistent5<128>), (unsigned)sm * 8, 128, true);
+  RUN("diag: shipped body, persistent 148*7", (k3_persistent5<128>), (unsigned)sm * 7, 128, true);
+  RUN("diag: shipped body, pers 148*4 x 256", (k3_persistent5<256>), (unsigned)sm * 4, 256, true);
   RUN("diag: <=64 regs (8 CTAs/SM)", (k3_diag<128, 8, 0>), blocks(128, 1), 128, true);
   RUN("diag: one contiguous stream*", (k3_onestream), (unsigned)sm * 8, 128, true);
   RUN("nowait (independent sets)", (k3_tile<128, 1, false>), blocks(128, 1), 128, true);
