@@ -149,6 +149,13 @@ def sass_instruction_count(kernel_substr: str):
     return None
 
 
+def ncu_field(kernel: str, field: str):
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))[kernel][field]
+    except Exception:
+        return None
+
+
 def ncu_traffic(kernel: str, mangled_substr: str | None = None):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu summary (bench.py never runs
     under a profiler itself).  The figure is REFUSED (None) when the summary was captured from a binary whose SASS
@@ -487,6 +494,16 @@ def run_ours(args):
         "gpu_launches": launches_timed,
         "clocks": clocks,
     }
+    if world == 1 and mode == 4 and batched and K == 20 and line["roofline"]["traffic"]:
+        # what the HBM fraction does not say: the launch is instruction-issue bound, and the L2 absorbs most of the write-through
+        winst = ncu_field("tick_fast4_kernel<5> (20 ticks per launch)", "warp_instructions")
+        mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        line["roofline"]["note"] = ("algorithmic bytes include the per-tick write-through of the state (40 B per group-tick); the 126 MB L2 "
+                                    "absorbs most of it (DRAM traffic of the launch = `traffic`), and the kernel is bound by instruction issue")
+        if winst:
+            line["roofline"]["issue"] = {"warp_instructions_per_launch": winst, "schedulers": 148 * 4,
+                                         "ipc_per_scheduler": winst / (148 * 4 * mhz * 1e6 * (ms * 1e-3)),
+                                         "source": "profiles/r02_traffic.json (smsp__inst_executed.sum of the same launch shape) / measured time"}
 
     if rank == 0 and world == 1:
         # the other ways to run the same K ticks, each [rewind, W, K] x 3 (median): what the batching and the layout buy
