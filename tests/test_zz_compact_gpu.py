@@ -286,3 +286,34 @@ def test_mode_4_at_the_benchmark_shape_equals_mode_0():
     assert c["errors"] == 0 and c["commits_advanced"] == ref.counters()["commits_advanced"]
     ref.close()
     eng.close()
+
+
+def test_mode_4_many_distinct_slot_sequences_stay_exact():
+    """mrq_tick_many caches one descriptor table per slot sequence and drops the cache when it holds 64: a host that never
+    repeats a sequence (here 80 different ones over 5 slots) must get the same results as the oracle throughout"""
+    import itertools
+
+    G, R = 700, 3
+    eng, orc, p = _warm(G, R, 17, 50, 2, slots=5)
+    eng.set_tick_mode(4)
+    self_id = orc.export()["self_id"].copy()
+    pk = _rebase(eng, orc, self_id, R)
+    po = _orc_params(p)
+    t = 50
+    seqs = [list(s) for n in (2, 3, 4, 5) for s in itertools.permutations(range(5), n)][:80]
+    assert len({tuple(s) for s in seqs}) == 80
+    for k, seq in enumerate(seqs):
+        if k % 10 == 9:
+            pk = _rebase(eng, orc, self_id, R)
+        for slot in seq:
+            ib = orc.gen_trace(po, t)
+            word, prop8, wide = pk.frame(ib)
+            eng.post_inbox_packed(word, prop8, wide, slot=slot)
+            orc.tick(ib)
+            t += 1
+        eng.tick_many(seq)
+        if k % 8 == 7:
+            assert_state_equal(eng.export_state(), orc.export(), f"sequence {k}")
+    assert_state_equal(eng.export_state(), orc.export(), "final")
+    assert eng.tick_count == t and eng.counters()["errors"] == 0
+    eng.close()
