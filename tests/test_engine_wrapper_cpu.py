@@ -134,6 +134,23 @@ def test_every_simple_wrapper_forwards_its_arguments():
     assert e.sync_out().dtype == np.uint32 and e.sync_commit_deltas().dtype == np.uint8
 
 
+def test_mode_4_wrappers_forward_their_arguments():
+    e = make(12, 5)
+    e.set_tick_mode(4)
+    assert last(e, "mrq_set_tick_mode")[1] == 4
+    e.set_write_through(0)
+    assert last(e, "mrq_set_write_through")[1] == 0
+    d = e.sync_tick_deltas()
+    a = last(e, "mrq_drain_tick_deltas")
+    assert d.dtype == np.uint8 and d.shape == (12,) and C.addressof(a[1].contents) == d.ctypes.data
+    names = [n for n, _ in e.L.calls]
+    assert names.index("mrq_drain_tick_deltas") < names.index("mrq_drain_wait")  # the copy is waited for before the array is used
+    o, dl = e.sync_slot_outputs(3)
+    a = last(e, "mrq_sync_slot_outputs")
+    assert a[1] == 3 and o.dtype == np.uint32 and dl.dtype == np.uint8
+    assert C.addressof(a[2].contents) == o.ctypes.data and C.addressof(a[3].contents) == dl.ctypes.data
+
+
 def test_the_engine_double_has_the_same_method_signatures_as_the_real_wrapper():
     """the rehearsal double must not drift from the wrapper it stands in for"""
     from engine_double import FakeEngine as EngineDouble
