@@ -237,15 +237,20 @@ func (e *Engine) PostFrame(slot uint32, word, prop8 []byte, wide []Msg) error {
 	v.word = unsafe.Pointer(&word[0])
 	v.prop_count8 = (*C.uint8_t)(unsafe.Pointer(&prop8[0]))
 	v.word_bits = 8
-	var buf []C.mrq_msg
 	if len(wide) > 0 {
-		buf = make([]C.mrq_msg, len(wide))
+		// cgo: a struct handed to C must not hold pointers into Go memory, so the escape list lives in C memory for the
+		// call (the engine copies it before returning: include/mrq.h, ownership rules)
+		n := C.size_t(len(wide)) * C.size_t(unsafe.Sizeof(C.mrq_msg{}))
+		cbuf := (*C.mrq_msg)(C.malloc(n))
+		defer C.free(unsafe.Pointer(cbuf))
+		buf := unsafe.Slice(cbuf, len(wide))
 		for i, m := range wide {
+			buf[i] = C.mrq_msg{}
 			buf[i].group, buf[i].term, buf[i].index = C.uint64_t(m.Group), C.uint64_t(m.Term), C.uint64_t(m.Index)
 			buf[i].logterm, buf[i].commit = C.uint64_t(m.LogTerm), C.uint64_t(m.Commit)
 			buf[i]._type, buf[i].from = C.uint8_t(m.Type), C.uint8_t(m.From)
 		}
-		v.wide, v.n_wide = &buf[0], C.size_t(len(buf))
+		v.wide, v.n_wide = cbuf, C.size_t(len(wide))
 	}
 	if rc := C.mrq_post_inbox_packed(e.h, C.uint32_t(slot), &v); rc != 0 {
 		return lastErr(e.h)
