@@ -1,12 +1,12 @@
 #!/bin/bash
-# The first GPU call of round 2, in one go (≈ 12 GPU-minutes at N = 1):
+# The first GPU call of round 2, in one go (it ran at the start of the round: profiles/r02_first_call_summary.txt; the
+# byte-form child process it also timed no longer exists — bench.py's e2e leg is in-process now — so those steps are gone):
 #
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'
 #
 # 1. the full -m gpu suite without -x (every shield removed), and the byte form under compute-sanitizer memcheck;
 # 2. the default bench (e2e.packed8 = the byte form's end-to-end number, from its child process);
 # 3. the persisting-L2 experiment of DESIGN.md §10 item 0: the same bench with the device limit raised;
-# 4. a launch list of the byte-form e2e leg (share of unpack8 / tick / drain kernels in its step).
 # Everything lands in gpurun_out/r02_first/ — summarise into profiles/ afterwards (tools/ncu_summary.py).
 set -u
 OUT=gpurun_out/r02_first
@@ -40,11 +40,6 @@ except Exception as ex:
     print("could not read the bench line:", ex)
 EOF
 
-echo "== 2b. byte-form e2e with the tick reading the bytes itself (tick mode 3: no unpack pass)" | tee -a "$OUT/summary.txt"
-MRQ_E2E8_TICK_MODE=3 timeout 600 python bench.py --e2e8-child --steps 20 > "$OUT/e2e8_mode3.json" 2> "$OUT/e2e8_mode3.err"
-echo "exit $?" | tee -a "$OUT/summary.txt"
-tail -1 "$OUT/e2e8_mode3.json" | cut -c1-400 | tee -a "$OUT/summary.txt"
-
 echo "== 2c. the HBM-resident tick on byte frames (bench --inbox bytes, tick mode 3), kernels only" | tee -a "$OUT/summary.txt"
 MRQ_BENCH_FAST=1 timeout 600 python bench.py --inbox bytes > "$OUT/bench_inbox_bytes.json" 2> "$OUT/bench_inbox_bytes.err"
 echo "exit $?" | tee -a "$OUT/summary.txt"
@@ -72,10 +67,6 @@ EOF
 done
 MRQ_BENCH_FAST=1 timeout 600 python bench.py --l2 0 > "$OUT/bench_l2_off.json" 2> "$OUT/bench_l2_off.err"
 
-echo "== 4. launch list of the byte-form e2e leg (a number printed under ncu is not a bench value)" | tee -a "$OUT/summary.txt"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches_e2e8.csv" \
-  python bench.py --e2e8-child --steps 8 > "$OUT/e2e8_under_ncu.log" 2>&1
-echo "exit $?" | tee -a "$OUT/summary.txt"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_event_reasons.active --format=csv >> "$OUT/summary.txt" 2>&1
 cat "$OUT/summary.txt"
 
