@@ -367,7 +367,11 @@ int mrq_comm_unique_id(uint8_t id_out[MRQ_COMM_ID_BYTES]);
  * n_groups.  After this, mrq_tick() ends with ncclAllGather(committed[G]) -> gathered[world*G]. */
 int mrq_comm_init(mrq_engine *e, const uint8_t id[MRQ_COMM_ID_BYTES], uint32_t rank, uint32_t world);
 /* mode 0: ncclAllGather of uint64 committed[] (default); mode 1: peer-store gather fused into the
- * tick kernel over CUDA-IPC mapped peer buffers (requires mrq_ipc_attach).                      */
+ * tick kernels over CUDA-IPC mapped peer buffers (requires mrq_ipc_attach): every tick each group's
+ * commit index goes straight into every rank's buffer over NVLink — its low byte every tick, the
+ * full 64-bit value only when anything above the low byte changed (or right after this call /
+ * mrq_ipc_attach, which re-publish everything).  mrq_sync_gathered returns the stitched indices
+ * in either mode.                                                                                */
 int mrq_comm_set_mode(mrq_engine *e, uint32_t mode);
 int mrq_sync_gathered(mrq_engine *e, uint64_t *gathered_out); /* blocking; world*G elements     */
 /* CUDA-IPC plumbing for the fused peer-store gather: export this rank's gather buffer, then attach

@@ -108,7 +108,7 @@ struct mrq_engine {
   uint32_t slow_parity = 0;
   uint64_t *tickbuf = nullptr;      // [2] device-resident tick number (current / next), see TickArgs
   uint32_t tick_parity = 0;
-  bool gather_prime = false;        // next tick stores the high words of every commit index to the peers
+  bool gather_prime = false;        // next tick stores the FULL commit index of every group to the peers (not just its low byte)
   bool graphs_disabled = false;
   int graph_mode = 2;               // mrq_set_graph_mode: 0 never, 1 always, 2 auto (small shards only)
   int l2_policy = 1;                // mrq_set_l2_policy: keep state L2-resident, stream the inbox
@@ -1673,7 +1673,7 @@ int mrq_comm_set_mode(mrq_engine *e, uint32_t mode) {
   if (!e || mode > 1) return MRQ_E_INVAL;
   if (mode == 1 && !e->ipc_attached) return fail(e, MRQ_E_STATE, "peer-store gather needs mrq_ipc_attach first");
   e->comm_mode = mode;
-  if (mode == 1) e->gather_prime = true;  // (re)publish the high words on the next tick
+  if (mode == 1) e->gather_prime = true;  // (re)publish the full indices on the next tick
   return MRQ_OK;
 }
 
@@ -1717,7 +1717,7 @@ int mrq_ipc_attach(mrq_engine *e, const uint8_t *handles, uint32_t rank, uint32_
   e->world = world;
   e->rank = rank;
   e->ipc_attached = true;
-  e->gather_prime = true;  // the first tick publishes the high words of every commit index
+  e->gather_prime = true;  // the first tick publishes the full index of every group
   return MRQ_OK;
 }
 
